@@ -1,0 +1,218 @@
+/* rdm_b200.h -- C ABI of librdm_b200.so: the B200 (sm_100a) implementation of the
+ * MD_RDM depth-map fusion path.
+ *
+ * The reference (az16/MD_RDM) has no FFI layer: the path is a set of plain Python
+ * functions in network/computations.py ("CP") and methods of Ordinal_Layer /
+ * Weights in network/RDM_Net.py ("RN").  Each entry point below names the
+ * reference function(s) it replaces (file:line).  The Python host code
+ * (md_rdm_b200/ops.py) binds these symbols with ctypes and registers torch custom
+ * ops on top; INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer on the current device unless noted; buffers
+ *    are dense row-major; the caller owns every buffer including workspaces;
+ *    nothing is allocated, freed or retained by the library;
+ *  - work is enqueued on `stream`; no host synchronisation, no host callbacks
+ *    (CUDA-graph capturable);
+ *  - return 0 = enqueued, <0 = argument error (nothing launched, see
+ *    rdm_last_error()), >0 = cudaError_t of the failed launch;
+ *  - "image" = one element of the reference batch dimension B; "group" = the B
+ *    images of one reference call, which share the ALS arg-min (CP:74, CP:143).
+ */
+#ifndef RDM_B200_H
+#define RDM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RDM_ABI_VERSION 1
+
+typedef void* rdm_stream_t; /* cudaStream_t */
+
+int rdm_abi_version(void);
+/* thread-local, valid until the next failing call on this thread */
+const char* rdm_last_error(void);
+
+/* ------------------------------------------------------------------ stage 1: pair build */
+
+/* RN:244-252 Ordinal_Layer.sparse_comparison_v1 (before its Lloyd call):
+ * raw[n,i,j] = fl32(d[n,i] * fl32(1/d[n,j])), d = (N,64) f32 (the 8x8 map, row-major). */
+int rdm_pair_v1_f32(const float* d3, int64_t n_images, float* raw_out, rdm_stream_t stream);
+
+/* CP:308-311 cp.resize for newsize == side/2 (bicubic, align_corners=False, f64 out).
+ * in: (N,side,side) f32 (in_is_f64=0) or f64; out: (N,side/2,side/2) f64. side in 2..128. */
+int rdm_resize_half(const void* in, int32_t in_is_f64, int64_t n_images, int32_t side,
+                    double* out, rdm_stream_t stream);
+
+/* RN:259-280 sparse_comparison_id (before its Lloyd call) + CP:201-216 split_matrix +
+ * the CP:308 resize that feeds them (RN:373, RN:386), for every 16x16 page of a
+ * (N,side,side) f32 map, side in {16,32,64,128}, P=(side/16)^2 pages in row-major order.
+ * raw_out: (N,P,256,64) f64.  parent_out (optional, may be NULL): (N,side/2,side/2) f64. */
+int rdm_pair_id_f64(const float* dn, int64_t n_images, int32_t side, double* raw_out,
+                    double* parent_out, rdm_stream_t stream);
+
+/* RN:259-280 with caller-supplied pages (the literal sparse_comparison_id(dn, dn_1) signature):
+ * pages (n,256) f32 = 16x16 pages, parents (n,64) f64 = their 8x8 parent pages (any values);
+ * raw_out (n,256,64) f64. */
+int rdm_pair_pages_f64(const float* pages, const double* parents, int64_t n_pages, double* raw_out,
+                       rdm_stream_t stream);
+
+/* CP:308-311 cp.resize for an arbitrary target size (network/module.py:68 resizes the 226x226
+ * ground truth to 128x128): torch bicubic, align_corners=False, A=-0.75, f64 out.
+ * in: (n,in_h,in_w) f32|f64; out: (n,out_h,out_w) f64. */
+int rdm_resize_bicubic_f64(const void* in, int32_t in_is_f64, int64_t n_maps, int32_t in_h,
+                           int32_t in_w, int32_t out_h, int32_t out_w, double* out,
+                           rdm_stream_t stream);
+
+/* CP:357-366 cp.upsample / cp.multi_upsample: `.double()` + nearest x2 applied `times` times.
+ * in: (n,side,side) f32|f64; out: (n, side<<times, side<<times) f64. */
+int rdm_upsample_nearest_f64(const void* in, int32_t in_is_f64, int64_t n_maps, int32_t side,
+                             int32_t times, double* out, rdm_stream_t stream);
+
+/* ------------------------------------------------------------------ stage 2: Lloyd quantisation */
+
+/* RN:286-311 Ordinal_Layer.LloydQuantization: bin = #{i<40 : x >= thr[i]} evaluated in the
+ * dtype of x (f32: thresholds rounded to f32 first), value = lvl[bin] rounded to that dtype.
+ * thr40/lvl41 are DEVICE f64 tables (RN:397-418 Quantization). values_out may alias x
+ * (the reference quantises in place); values_out and bins_out may each be NULL. */
+int rdm_lloyd_quantize_f32(const float* x, int64_t n, const double* thr40, const double* lvl41,
+                           float* values_out, uint8_t* bins_out, rdm_stream_t stream);
+int rdm_lloyd_quantize_f64(const double* x, int64_t n, const double* thr40, const double* lvl41,
+                           double* values_out, uint8_t* bins_out, rdm_stream_t stream);
+
+/* ------------------------------------------------------------------ stage 3 (+2 fused): ALS */
+
+enum {
+  RDM_SRC_RAW_F64 = 0, /* raw ratios f64 -> Lloyd (f64 compare) -> ALS   (pages, RN:376-378) */
+  RDM_SRC_RAW_F32 = 1, /* raw ratios f32 -> Lloyd (f32 compare) -> ALS   (8x8,   RN:362-364) */
+  RDM_SRC_VAL_F32 = 2, /* already quantised / arbitrary matrix, f32        (CP:38, CP:95)     */
+  RDM_SRC_VAL_F64 = 3, /* same, f64: `.float()` applied on load            (CP:40, CP:106)    */
+  RDM_SRC_MAP_F32 = 4  /* decoder map f32: pair build + Lloyd + ALS fused, the pair matrix is
+                          never written (rows=64: src=(N,64); rows=256: src=(N,side,side)) */
+};
+
+/* One relative decoder scale.  Matrices are (N, pages, rows, 64), rows = 64 (8x8 map, square
+ * case CP:38-85, limit 30) or 256 (16x16 page, CP:95-155, limit 100). */
+typedef struct rdm_als_scale {
+  const void* src;          /* see src_kind */
+  int32_t src_kind;
+  int32_t rows;             /* 64 or 256 */
+  int32_t pages;            /* P = 1 (side 8, 16) or (side/16)^2 */
+  int32_t side;             /* map side s */
+  int32_t limit;            /* ALS iterations (rows 64: <= 63, rows 256: <= 127) */
+  int32_t reserved;
+  const double* thresholds; /* device f64[40]; required for RAW_* and MAP_F32 */
+  const double* levels;     /* device f64[41]; required for RAW_* and MAP_F32 */
+  uint8_t* bins_out;        /* optional (N,P,rows,64) u8 Lloyd bins */
+  float* values_out;        /* optional (N,P,rows,64) f32 quantised matrix as ALS sees it */
+  float* pages_out;         /* optional (N,P,rows) f32: per-page ALS maps before re-tiling */
+  float* map_out;           /* optional (N,side,side) f32: CP:218-238 `reconstruct` re-tiling
+                               (bug-compatible: only pages 0..side/16-1 reach the map) */
+  float* ws;                /* REQUIRED workspace, N * rdm_als_ws_floats(rows, pages, limit) f32:
+                               per (image, page) the SSE record [limit+1] then p_1 [rows] */
+  float* record_out;        /* optional (N/group,P,limit+1) f32 rmse record (CP:53-61) */
+  int32_t* kstar_out;       /* optional (N/group,P) i32 selected iteration (CP:74, CP:143) */
+} rdm_als_scale_t;
+
+/* Lloyd + rank-1 ALS + geometric normalisation + page re-tiling for `n_scales` scales in a
+ * fixed number of launches.  Replaces Ordinal_Layer.forward (non-DORN branch, RN:358-396)
+ * minus the pair build (unless src_kind == RDM_SRC_MAP_F32), i.e. LloydQuantization,
+ * cp.quadratic_als, cp.alternating_least_squares, cp.als_step, cp.quick_gm, cp.reconstruct.
+ * `scales` is a HOST array.  n_images must be a multiple of group. */
+int rdm_als_fused(const rdm_als_scale_t* scales, int32_t n_scales, int64_t n_images,
+                  int32_t group, rdm_stream_t stream);
+/* f32 workspace elements per image for one scale (rdm_als_scale_t.ws) */
+int64_t rdm_als_ws_floats(int32_t rows, int32_t pages, int32_t limit);
+
+/* CP:175-193 cp.als_step: out[b,i] = (sum_j ratings[b,i,j] * fixed[b,j]) * (1/(|fixed_b|^2+reg)).
+ * ratings (B,rows,cols) f32, fixed (B,cols) f32, out (B,rows) f32. */
+int rdm_als_step_f32(const float* ratings, const float* fixed, int64_t batch, int32_t rows,
+                     int32_t cols, float reg, float* out, rdm_stream_t stream);
+
+/* ------------------------------------------------------------------ stage 4: decomposition */
+
+/* CP:244-255 cp.quick_gm over dim 1: out[b] = prod_i pow(t[b,i], 1/rc^2).
+ * dtype: 0 = f32, 1 = f64, 2 = i64 (computed in f32 like torch.pow(int64, float)). */
+int rdm_quick_gm(const void* t, int32_t dtype, int64_t batch, int64_t n, int32_t rc, void* out,
+                 rdm_stream_t stream);
+
+/* RN:117 / network/module.py:145-149: x / quick_gm(x.view(B,HW,1), H) for a (N,side,side) map.
+ * dtype as above; out is f32 for f32/i64 input and f64 for f64 input. */
+int rdm_gm_normalize(const void* x, int32_t dtype, int64_t n_images, int32_t side, void* out,
+                     rdm_stream_t stream);
+
+/* CP:368-392 cp.decompose_depth_map (+ callers' [::-1]): whole pyramid of a (N,side,side) map
+ * in one launch.  n = log2(side) levels, side <= 128.  pyramid_out: f64, LEVEL-MAJOR
+ * [D_0: (N,1), only if relative_map == 0] [F_1: (N,4)] [F_2: (N,16)] ... [F_n: (N,side^2)], so
+ * every component is a dense (N,1,2^k,2^k) tensor.  in_is_f64: 0 = f32 input, 1 = f64 input. */
+int rdm_decompose(const void* in, int32_t in_is_f64, int64_t n_images, int32_t side,
+                  int32_t relative_map, double* pyramid_out, rdm_stream_t stream);
+/* number of f64 values per image written by rdm_decompose (total = N times this) */
+int64_t rdm_pyramid_len(int32_t side, int32_t relative_map);
+/* backward of rdm_decompose (autograd through CP:368-392): grad_pyramid in the same level-major
+ * layout, grad_in (N,side,side) in the dtype of `in`. */
+int rdm_decompose_bwd(const void* in, int32_t in_is_f64, int64_t n_images, int32_t side,
+                      int32_t relative_map, const double* grad_pyramid, void* grad_in,
+                      rdm_stream_t stream);
+/* backward of rdm_quick_gm (grad_gm (B), optional) and/or rdm_gm_normalize (grad_norm (B,n),
+ * optional) for f32 (is_f64 = 0) or f64 x (B,n); all gradients in x's dtype. */
+int rdm_gm_bwd(const void* x, int32_t is_f64, int64_t batch, int64_t n, int32_t rc,
+               const void* grad_gm, const void* grad_norm, void* grad_x, rdm_stream_t stream);
+
+/* ------------------------------------------------------------------ stage 5: weighted reconstruction */
+
+/* CP:464-484 cp.make_matrix: out[b,k,:] = log(cand_k[b,:]) for K candidates of M values each.
+ * cands: HOST array of K device pointers to (B,M) f64. out (B,K,M) f64. */
+int rdm_log_stack_f64(const double* const* cands, int32_t K, int64_t batch, int64_t M, double* out,
+                      rdm_stream_t stream);
+
+/* backward of rdm_log_stack_f64: grad_cands[k][b,m] = grad_out[b,k,m] / cands[k][b,m]. */
+int rdm_log_stack_bwd(const double* const* cands, int32_t K, int64_t batch, int64_t M,
+                      const double* grad_out, double* const* grad_cands, rdm_stream_t stream);
+
+/* CP:512-528 cp.make_pred for one slot: out[b,m] = sum_k f32(A[b,k,m]) * w[k] (f32). */
+int rdm_make_pred_f32(const double* A, const float* w, int64_t batch, int32_t K, int64_t M,
+                      float* out, rdm_stream_t stream);
+/* backward of the above: grad_A (B,K,M) f64 (optional), grad_w (K) f32 (optional, overwritten). */
+int rdm_make_pred_bwd(const double* A, const float* w, const float* grad_out, int64_t batch,
+                      int32_t K, int64_t M, double* grad_A, float* grad_w, rdm_stream_t stream);
+
+/* CP:394-421 cp.recombination (+ CP:357-366 upsample/multi_upsample):
+ * out[b,y,x] = sum_i comp_i[b, y >> sh_i, x >> sh_i] in f64, out side = 2^n, summed in the
+ * reference's order (d_0 added last).  comps: HOST array of n_comps device pointers in list
+ * order: optional d_0 (side 1) then sides 2, 4, ... (any prefix); comp i is (B,side_i,side_i)
+ * f32 (comps_are_f64 = 0) or f64; sides[] HOST. */
+int rdm_recombination_f64(const void* const* comps, const int32_t* sides, int32_t n_comps,
+                          int32_t comps_are_f64, int64_t batch, int32_t n, double* out,
+                          rdm_stream_t stream);
+/* backward: grad_comp_i[b,u,v] = sum over the 2^sh x 2^sh block of grad_out, by successive 2x2
+ * pooling (what autograd does through the upsample chain).  Entries of grad_comps may be NULL.
+ * n <= 7. */
+int rdm_recombination_bwd(const double* grad_out, void* const* grad_comps, const int32_t* sides,
+                          int32_t n_comps, int32_t comps_are_f64, int64_t batch, int32_t n,
+                          rdm_stream_t stream);
+
+/* Fused stages 4+5 for the configuration RN:96-133 intends (decoder 1 + relative decoders):
+ *   f_d1 = decompose(x_d1 / gm(x_d1), 3); f_dk = decompose(rel_k, log2 side_k, relative);
+ *   A = relative_fine_detail_matrix; y_hat = make_pred(weights, A); depth = recombination(y_hat)
+ * x_d1: (N,64) i64; rel[k]: (N,side_k,side_k) f32, side_k <= 64, HOST array of device ptrs;
+ * weights: device f32, slots concatenated in slot order [d0 | f1 | ... ], within a slot in
+ * decoder order (decoder 1 first); weight count per slot is implied by `sides`.
+ * yhat_out (optional): (N, sum_{k<=kmax} 4^k) f32 packed by slot; depth_out: (N,128,128) f64;
+ * A_out (optional): HOST array of 8 device pointers (entries may be NULL), A_out[k] receives the
+ * slot-k fine-detail matrix (N, K_k, 4^k) f64 exactly as cp.relative_fine_detail_matrix builds it
+ * (what the backward needs). */
+int rdm_fuse_tail(const int64_t* x_d1, const float* const* rel, const int32_t* sides,
+                  int32_t n_rel, const float* weights, int64_t n_images, float* yhat_out,
+                  double* depth_out, double* const* A_out, rdm_stream_t stream);
+/* number of f32 weights rdm_fuse_tail expects for these relative decoder sides (-1 = bad sides) */
+int64_t rdm_fuse_tail_weight_count(const int32_t* sides, int32_t n_rel);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RDM_B200_H */

@@ -1,0 +1,91 @@
+"""Lloyd codebooks (40 thresholds + 41 levels per scale).
+
+Mirrors `Quantization` (reference network/RDM_Net.py:397-442): same attribute names
+(`depth_ratio_XXX_XXX_quant[_inv]`, numpy (40,1)/(41,1) float64), `get_with_id`,
+`get_size_id`.  The reference loads five MATLAB files from the current directory; the
+008 file is missing from its tree (`.MISSING_LARGE_BLOBS`), so the tables shipped here
+(md_rdm_b200/data/depth_ratio_codebooks.json, exact IEEE-754 hex, written by
+tools/import_codebooks.py) carry a DERIVED 008 table = table(016)**2.  `from_mat_dir`
+loads real .mat files instead when they are available.
+"""
+from __future__ import annotations
+
+import json
+import os
+from typing import Dict, Tuple
+
+import numpy as np
+import torch
+
+_DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "depth_ratio_codebooks.json")
+SCALES = (8, 16, 32, 64, 128)
+
+
+def _tag(scale: int) -> str:
+    return f"depth_ratio_{scale:03d}_{scale:03d}_quant"
+
+
+class Quantization:
+    """Drop-in for the reference class of the same name, plus device-resident tables."""
+
+    def __init__(self, path: str = _DATA):
+        with open(path) as f:
+            raw = json.load(f)
+        self.derived = {}
+        for key, tab in raw["tables"].items():
+            s = int(key)
+            q = np.array([float.fromhex(h) for h in tab["thresholds"]], dtype=np.float64).reshape(40, 1)
+            inv = np.array([float.fromhex(h) for h in tab["levels"]], dtype=np.float64).reshape(41, 1)
+            setattr(self, _tag(s), q)
+            setattr(self, _tag(s) + "_inv", inv)
+            self.derived[s] = bool(tab.get("derived", False))
+        self._dev: Dict[Tuple[int, str], Tuple[torch.Tensor, torch.Tensor]] = {}
+
+    @classmethod
+    def from_mat_dir(cls, directory: str) -> "Quantization":
+        """Load `depth_ratio_*_quant.mat` like RN:403-418 does (scipy needed); scales whose file
+        is absent keep the packaged table."""
+        import scipy.io
+        self = cls()
+        for s in SCALES:
+            p = os.path.join(directory, _tag(s) + ".mat")
+            if os.path.exists(p):
+                m = scipy.io.loadmat(p)
+                setattr(self, _tag(s), np.asarray(m[_tag(s)], dtype=np.float64).reshape(40, 1))
+                setattr(self, _tag(s) + "_inv", np.asarray(m[_tag(s) + "_inv"], dtype=np.float64).reshape(41, 1))
+                self.derived[s] = False
+        self._dev.clear()
+        return self
+
+    # ---- reference surface (RN:420-442)
+    def get_with_id(self, id):
+        if 3 <= id <= 7:
+            s = 1 << id
+            return getattr(self, _tag(s)), getattr(self, _tag(s) + "_inv")
+
+    def get_size_id(self, id):
+        if 3 <= id <= 7:
+            return 1 << id
+
+    # ---- device tables for the kernels
+    def device_tables(self, scale: int, device) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(thresholds[40], levels[41]) as f64 tensors on `device`, cached."""
+        device = torch.device(device)
+        key = (scale, str(device))
+        hit = self._dev.get(key)
+        if hit is None:
+            q = torch.from_numpy(getattr(self, _tag(scale)).reshape(-1).copy()).to(device)
+            inv = torch.from_numpy(getattr(self, _tag(scale) + "_inv").reshape(-1).copy()).to(device)
+            hit = (q, inv)
+            self._dev[key] = hit
+        return hit
+
+
+_default = None
+
+
+def default_quantization() -> Quantization:
+    global _default
+    if _default is None:
+        _default = Quantization()
+    return _default

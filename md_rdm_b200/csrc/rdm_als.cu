@@ -1,0 +1,556 @@
+// Stage 2+3 fused: Lloyd quantisation + rank-1 ALS + batch-wide arg-min + geometric
+// normalisation + page re-tiling (RN:286-311, RN:358-396, CP:38-85, CP:95-155, CP:175-193,
+// CP:218-238, CP:244-255), optionally with the pair build in front (RN:244-280) so the pair
+// matrix never exists in HBM.
+//
+// Work unit = one pair matrix = one (image, page).  rows = 256 (16x16 page against its 8x8
+// parent, 100 iterations) or rows = 64 (the 8x8 map against itself, 30 iterations); 64 columns
+// either way.  A unit is owned by rows threads, ONE MATRIX ROW PER THREAD HELD IN 64 REGISTERS,
+// so the 2*limit GEMVs of the alternating updates never touch shared memory for the matrix:
+//   p-update  p_i = (sum_c R[i][c] q_c) / (|q|^2 + lambda)              CP:186-192
+//   q-update  q_i = (sum_m Rflat[i*rows + m] p_m) / (|p|^2 + lambda)    CP:64 / CP:133: the
+//             reference passes R.view(B,W,H) - a reshape, not a transpose - so "row i" of the
+//             second operand is rows G*i .. G*i+G-1 of R laid end to end (G = rows/64).
+// Threads are mapped to rows so that a warp's 32 rows share r' = row % G; the p segment a
+// thread needs (p[64 r' .. 64 r'+63]) is then a warp-wide broadcast read.
+// Per iteration: 2 named barriers, 2 register GEMVs, 1-2 f64 warp reductions.
+//
+// rmse record (CP:53-61, CP:121-130): sum_j (p_i q_j - R_ij)^2 = |R_i|^2 + p_i (p_i |q|^2 - 2 s_i)
+// with s_i = R_i . q already known from the p-update, evaluated in f64 - O(1) per row instead of a
+// third pass over the matrix.  Per-unit SSE goes to the workspace; the arg-min is over the mean
+// of the whole reference batch ("group", CP:172-173), so phase 1 (second launch) sums the
+// group's records, picks the first minimum (CP:74, CP:143) and emits p_k*.  p_1 is checkpointed
+// by phase 0 (k* is 0 or 1 on every realistic input); for k* >= 2 phase 1 replays
+// k* iterations from the source.  No kernel waits on another: two plain launches.
+//
+// Bound: per unit 2*limit*rows*64 FMA against rows*64*(4..8) input bytes = 25..100 FMA/byte:
+// FP32-issue / dependency-latency bound, not HBM bound (DESIGN.md "K3").
+#include "rdm_common.cuh"
+
+namespace rdm {
+
+constexpr int kCols = 64;
+constexpr int kMaxScales = 8;
+constexpr float kLambda = 0.05f;   // CP:175 regularization_term
+constexpr int kAlsThreads = 256;
+constexpr int kTileFloats = 256 * 64;   // 64 KB matrix staging tile (dynamic shared memory)
+
+struct AlsScaleDev {
+  const void* src;
+  const double* thr;
+  const double* lvl;
+  uint8_t* bins;
+  float* values;
+  float* ws;          // per unit: [limit+1] SSE record, then [rows] p_1
+  float* pages_out;
+  float* map_out;
+  float* record_out;
+  int32_t* kstar_out;
+  int32_t kind, rows, pages, side, limit;
+  int32_t cta_begin;   // first blockIdx.x of this scale
+};
+
+struct AlsParams {
+  AlsScaleDev s[kMaxScales];
+  int64_t n_images;
+  int32_t n_scales;
+  int32_t group;
+};
+
+struct AlsSmem {
+  __align__(16) float p_s[256];       // p by row index (64-row units: 4 x 64)
+  __align__(16) float q_w[8][64];     // per-warp copy of q
+  __align__(16) float qpart[4][64];   // q partial sums (256-row: by r'; 64-row: by unit)
+  double part_e[8];
+  double part_pp[8];
+  double thr_d[kThrPad];
+  double inv_d[64];                   // 1/parent (pair build fused, 256-row units)
+  float thr_f[kThrPad];
+  float lvl_f[kLvl + 3];
+  float inv_f[4][64];                 // 1/d (pair build fused, 64-row units)
+  float rm[256];                      // group rmse record (phase 1)
+  int sorted;
+};
+
+__device__ __forceinline__ void unit_barrier(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__device__ __forceinline__ float dot64(const float (&R)[64], const float* __restrict__ v) {
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+  for (int c4 = 0; c4 < 16; ++c4) {
+    float4 x = *reinterpret_cast<const float4*>(v + 4 * c4);
+    a0 = fmaf(R[4 * c4 + 0], x.x, a0);
+    a1 = fmaf(R[4 * c4 + 1], x.y, a1);
+    a2 = fmaf(R[4 * c4 + 2], x.z, a2);
+    a3 = fmaf(R[4 * c4 + 3], x.w, a3);
+  }
+  return (a0 + a1) + (a2 + a3);
+}
+
+// Thread <-> row mapping of a unit.  lt = thread index inside the unit (0 .. 64G-1).
+template <int G>
+struct RowMap {
+  int lane, lw, rp, i, row;
+  __device__ __forceinline__ explicit RowMap(int lt) {
+    lane = lt & 31;
+    lw = lt >> 5;
+    rp = lw % G;
+    i = (lw / G) * 32 + lane;
+    row = G * i + rp;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Load (and, for RAW_* / MAP kinds, build + quantise) the unit's matrix row into registers.
+template <int G>
+__device__ __forceinline__ void load_unit(float (&R)[64], const AlsScaleDev& sc, AlsSmem& sm, float* tile,
+                                          int64_t unit_idx, int unit, int lt, bool emit) {
+  constexpr int NT = 64 * G;
+  constexpr int ROWS = 64 * G;
+  const RowMap<G> m(lt);
+  const int bar_id = (G == 4) ? 0 : 1 + unit;
+  const int sorted = sm.sorted;
+  uint8_t* bins = emit ? sc.bins : nullptr;
+  float* values = emit ? sc.values : nullptr;
+  const int64_t mat_off = unit_idx * (int64_t)(ROWS * kCols);
+
+  if (sc.kind == RDM_SRC_MAP_F32) {
+    // ---- pair build fused: nothing but the decoder map is read from HBM
+    if constexpr (G == 4) {
+      const int side = sc.side, ratio = side >> 4;
+      const int64_t img = unit_idx / sc.pages;
+      const int pg = (int)(unit_idx - img * sc.pages);
+      const int pi = pg / ratio, pj = pg - pi * ratio;
+      const float* map = reinterpret_cast<const float*>(sc.src) + img * (int64_t)side * side;
+      if (lt < 64) {
+        int y = 8 * pi + (lt >> 3), x = 8 * pj + (lt & 7);
+        double v = bicubic_half_at([&](int r, int c) { return (double)map[r * side + c]; }, y, x, side);
+        sm.inv_d[lt] = 1.0 / v;   // torch.pow(area,-1): IEEE reciprocal
+      }
+      const double d = (double)map[(16 * pi + (m.row >> 4)) * side + 16 * pj + (m.row & 15)];
+      unit_barrier(bar_id, NT);
+      const int r0 = min((m.row >> 4) >> 1, 5), c0 = min((m.row & 15) >> 1, 5);
+      const int bd = lloyd_bin<double>(d, sm.thr_d, sorted);   // the 55 columns outside the window
+      uint32_t pk = 0;
+#pragma unroll
+      for (int c = 0; c < 64; ++c) {
+        const bool win = (unsigned)((c >> 3) - r0) < 3u && (unsigned)((c & 7) - c0) < 3u;
+        int b = bd;
+        if (win) b = lloyd_bin<double>(__dmul_rn(d, sm.inv_d[c]), sm.thr_d, sorted);
+        R[c] = sm.lvl_f[b];
+        pk |= (uint32_t)b << (8 * (c & 3));
+        if ((c & 3) == 3) {
+          if (bins) *reinterpret_cast<uint32_t*>(bins + mat_off + m.row * 64 + (c - 3)) = pk;
+          pk = 0;
+        }
+      }
+    } else {
+      const float* map = reinterpret_cast<const float*>(sc.src) + unit_idx * 64;
+      const float dv = map[lt];
+      sm.inv_f[unit][lt] = __frcp_rn(dv);   // RN:248
+      unit_barrier(bar_id, NT);
+      uint32_t pk = 0;
+#pragma unroll
+      for (int c = 0; c < 64; ++c) {
+        int b = lloyd_bin<float>(__fmul_rn(dv, sm.inv_f[unit][c]), sm.thr_f, sorted);   // RN:252
+        R[c] = sm.lvl_f[b];
+        pk |= (uint32_t)b << (8 * (c & 3));
+        if ((c & 3) == 3) {
+          if (bins) *reinterpret_cast<uint32_t*>(bins + mat_off + m.row * 64 + (c - 3)) = pk;
+          pk = 0;
+        }
+      }
+    }
+    if (values) {
+#pragma unroll
+      for (int c4 = 0; c4 < 16; ++c4)
+        *reinterpret_cast<float4*>(values + mat_off + m.row * 64 + 4 * c4) =
+            make_float4(R[4 * c4], R[4 * c4 + 1], R[4 * c4 + 2], R[4 * c4 + 3]);
+    }
+    return;
+  }
+
+  // ---- matrix given in HBM: coalesced 128-bit loads, quantise on the fly, transpose through an
+  // XOR-swizzled shared tile into row-per-thread registers.
+  if (sc.kind == RDM_SRC_RAW_F64 || sc.kind == RDM_SRC_VAL_F64) {
+    const double* src = reinterpret_cast<const double*>(sc.src) + mat_off;
+    const bool quant = sc.kind == RDM_SRC_RAW_F64;
+    constexpr int ITERS = ROWS * 32 / NT;   // element pairs per thread
+#pragma unroll 8
+    for (int k = 0; k < ITERS; ++k) {
+      const int e2 = lt + NT * k;
+      const int r = e2 >> 5, cp = e2 & 31;
+      double2 x = ldg_stream_f64x2(src + 2 * e2);
+      float v0, v1;
+      if (quant) {
+        int b0 = lloyd_bin<double>(x.x, sm.thr_d, sorted), b1 = lloyd_bin<double>(x.y, sm.thr_d, sorted);
+        v0 = sm.lvl_f[b0];
+        v1 = sm.lvl_f[b1];
+        if (bins) *reinterpret_cast<uint16_t*>(bins + mat_off + 2 * e2) = (uint16_t)(b0 | (b1 << 8));
+      } else {
+        v0 = (float)x.x;   // `.float()` CP:40 / CP:106
+        v1 = (float)x.y;
+      }
+      if (values) *reinterpret_cast<float2*>(values + mat_off + 2 * e2) = make_float2(v0, v1);
+      const int swz = (r / G) & 7;
+      *reinterpret_cast<float2*>(tile + r * 64 + (((cp >> 1) ^ swz) << 2) + 2 * (cp & 1)) = make_float2(v0, v1);
+    }
+  } else {
+    const float* src = reinterpret_cast<const float*>(sc.src) + mat_off;
+    const bool quant = sc.kind == RDM_SRC_RAW_F32;
+    constexpr int ITERS = ROWS * 16 / NT;   // float4 chunks per thread
+#pragma unroll 8
+    for (int k = 0; k < ITERS; ++k) {
+      const int e4 = lt + NT * k;
+      const int r = e4 >> 4, c4 = e4 & 15;
+      float4 x = ldg_stream_f32x4(src + 4 * e4);
+      if (quant) {
+        int b0 = lloyd_bin<float>(x.x, sm.thr_f, sorted), b1 = lloyd_bin<float>(x.y, sm.thr_f, sorted);
+        int b2 = lloyd_bin<float>(x.z, sm.thr_f, sorted), b3 = lloyd_bin<float>(x.w, sm.thr_f, sorted);
+        x = make_float4(sm.lvl_f[b0], sm.lvl_f[b1], sm.lvl_f[b2], sm.lvl_f[b3]);
+        if (bins)
+          *reinterpret_cast<uint32_t*>(bins + mat_off + 4 * e4) = (uint32_t)(b0 | (b1 << 8) | (b2 << 16) | (b3 << 24));
+      }
+      if (values) *reinterpret_cast<float4*>(values + mat_off + 4 * e4) = x;
+      const int swz = (r / G) & 7;
+      *reinterpret_cast<float4*>(tile + r * 64 + ((c4 ^ swz) << 2)) = x;
+    }
+  }
+  unit_barrier(bar_id, NT);
+  {
+    const int swz = m.i & 7;
+    const float4* t4 = reinterpret_cast<const float4*>(tile) + m.row * 16;
+#pragma unroll
+    for (int c4 = 0; c4 < 16; ++c4) {
+      float4 x = t4[c4 ^ swz];
+      R[4 * c4 + 0] = x.x;
+      R[4 * c4 + 1] = x.y;
+      R[4 * c4 + 2] = x.z;
+      R[4 * c4 + 3] = x.w;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// n_iter alternating iterations; returns this thread's p_{n_iter}[row].  RECORD: write the SSE of
+// iterations 0..n_iter to rec[] and p_1 to p1_out[].
+template <int G, bool RECORD>
+__device__ __forceinline__ float als_iterate(const float (&R)[64], AlsSmem& sm, int unit, int lt, int n_iter,
+                                             float* __restrict__ rec, float* __restrict__ p1_out) {
+  constexpr int NW = 2 * G;
+  constexpr int NT = 64 * G;
+  const RowMap<G> m(lt);
+  const int gw = unit * NW + m.lw;
+  const int bar_id = (G == 4) ? 0 : 1 + unit;
+  const int qp_base = (G == 4) ? 0 : unit;
+  float* qw = sm.q_w[gw];
+  float* ps = sm.p_s + unit * 64;
+
+  // q_0 = 1: s = row sum.  |R_i|^2 in f64 for the record.
+  float s;
+  double r2 = 0.0;
+  {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+    for (int c = 0; c < 64; c += 4) {
+      a0 += R[c];
+      a1 += R[c + 1];
+      a2 += R[c + 2];
+      a3 += R[c + 3];
+    }
+    s = (a0 + a1) + (a2 + a3);
+    if (RECORD) {
+#pragma unroll
+      for (int c = 0; c < 64; ++c) r2 = fma((double)R[c], (double)R[c], r2);
+    }
+  }
+  double Q = 64.0;                               // |q|^2
+  float invA = 1.0f / (64.0f + kLambda);         // torch.inverse of the 1x1 matrix |q|^2 + lambda
+  if (RECORD) {
+    double e0 = warp_sum(r2 + 64.0 - 2.0 * (double)s);   // p = q = 1 (CP:55, CP:123)
+    if (m.lane == 0) sm.part_e[gw] = e0;
+    unit_barrier(bar_id, NT);
+    if (lt == 0) {
+      double t = 0.0;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) t += sm.part_e[unit * NW + w];
+      rec[0] = (float)fmax(t, 0.0);
+    }
+  }
+  float p = 1.0f;
+  for (int k = 1; k <= n_iter; ++k) {
+    p = s * invA;                                // (R q) @ inverse(A)
+    if (!RECORD && k == n_iter) break;
+    ps[m.row] = p;
+    if (RECORD && k == 1) p1_out[m.row] = p;
+    double pp = (double)p * (double)p;
+    double e = 0.0;
+    if (RECORD) e = r2 + (double)p * ((double)p * Q - 2.0 * (double)s);
+    unit_barrier(bar_id, NT);                    // A: p visible
+    const float u = dot64(R, ps + 64 * m.rp);
+    sm.qpart[qp_base + m.rp][m.i] = u;
+    pp = warp_sum(pp);
+    if (RECORD) e = warp_sum(e);
+    if (m.lane == 0) {
+      sm.part_pp[gw] = pp;
+      if (RECORD) sm.part_e[gw] = e;
+    }
+    unit_barrier(bar_id, NT);                    // B: q partials, |p|^2, SSE partials visible
+    if (RECORD && lt == 0) {
+      double t = 0.0;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) t += sm.part_e[unit * NW + w];
+      rec[k] = (float)fmax(t, 0.0);
+    }
+    if (k == n_iter) break;
+    // every warp finalises q for itself (no third barrier)
+    double npp = 0.0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) npp += sm.part_pp[unit * NW + w];
+    const float invB = 1.0f / ((float)npp + kLambda);
+    float u0 = 0.f, u1 = 0.f;
+#pragma unroll
+    for (int r = 0; r < G; ++r) {
+      u0 += sm.qpart[qp_base + r][m.lane];
+      u1 += sm.qpart[qp_base + r][m.lane + 32];
+    }
+    const float q0 = u0 * invB, q1 = u1 * invB;
+    Q = warp_sum(fma((double)q0, (double)q0, (double)q1 * (double)q1));
+    invA = 1.0f / ((float)Q + kLambda);
+    qw[m.lane] = q0;
+    qw[m.lane + 32] = q1;
+    __syncwarp();
+    s = dot64(R, qw);
+  }
+  return p;
+}
+
+// ---------------------------------------------------------------------------------------------
+template <int G, int PHASE>
+__device__ __forceinline__ void als_unit(const AlsParams& P, const AlsScaleDev& sc, AlsSmem& sm, float* tile,
+                                         int64_t unit_idx, int unit, int lt) {
+  constexpr int NT = 64 * G;
+  constexpr int ROWS = 64 * G;
+  const RowMap<G> m(lt);
+  const int bar_id = (G == 4) ? 0 : 1 + unit;
+  const int ws_stride = sc.limit + 1 + ROWS;
+  float* ws = sc.ws + unit_idx * ws_stride;
+  float R[64];
+
+  if constexpr (PHASE == 0) {
+    load_unit<G>(R, sc, sm, tile, unit_idx, unit, lt, true);
+    als_iterate<G, true>(R, sm, unit, lt, sc.limit, ws, ws + sc.limit + 1);
+    return;
+  } else {
+    // ---- batch-wide rmse record and first arg-min (CP:172-173, CP:74, CP:143)
+    const int64_t img = unit_idx / sc.pages;
+    const int pg = (int)(unit_idx - img * sc.pages);
+    const int64_t g0 = (img / P.group) * P.group;   // first image of the reference batch
+    float* rm = sm.rm + unit * 64;
+    const double inv_cnt = 1.0 / ((double)P.group * (double)(ROWS * kCols));
+    for (int k = lt; k <= sc.limit; k += NT) {
+      double t = 0.0;
+      for (int b = 0; b < P.group; ++b) t += (double)sc.ws[((g0 + b) * sc.pages + pg) * (int64_t)ws_stride + k];
+      rm[k] = (float)sqrt(t * inv_cnt);
+    }
+    unit_barrier(bar_id, NT);
+    int kstar = 0;
+    float best = rm[0];
+    for (int k = 1; k <= sc.limit; ++k) {
+      float v = rm[k];
+      if (v < best) {
+        best = v;
+        kstar = k;
+      }
+    }
+    if (img == g0) {
+      const int64_t gp = (img / P.group) * sc.pages + pg;
+      if (sc.record_out)
+        for (int k = lt; k <= sc.limit; k += NT) sc.record_out[gp * (sc.limit + 1) + k] = rm[k];
+      if (sc.kstar_out && lt == 0) sc.kstar_out[gp] = kstar;
+    }
+    float p;
+    if (kstar == 0) {
+      p = 1.0f;
+    } else if (kstar == 1) {
+      p = ws[sc.limit + 1 + m.row];
+    } else {   // rare: replay k* iterations from the source
+      load_unit<G>(R, sc, sm, tile, unit_idx, unit, lt, false);
+      p = als_iterate<G, false>(R, sm, unit, lt, kstar, nullptr, nullptr);
+    }
+    // ---- quick_gm(p, H) with H = rows: prod_i p_i^(1/H^2)  (CP:76, CP:146, CP:244-255)
+    const float pw = (float)pow((double)p, 1.0 / ((double)ROWS * (double)ROWS));
+    float prod = warp_prod(pw);
+    unit_barrier(bar_id, NT);   // rm[] no longer needed; reuse p_s as scratch
+    float* scratch = sm.p_s + unit * 64;
+    if (m.lane == 0) scratch[m.lw] = prod;
+    unit_barrier(bar_id, NT);
+    float gm = scratch[0];
+#pragma unroll
+    for (int w = 1; w < 2 * G; ++w) gm *= scratch[w];
+    const float out = p / gm;
+    if (sc.pages_out) sc.pages_out[unit_idx * ROWS + m.row] = out;
+    if (sc.map_out) {
+      if constexpr (G == 1) {
+        sc.map_out[img * 64 + m.row] = out;
+      } else {
+        const int side = sc.side, ratio = side >> 4;
+        float* mp = sc.map_out + img * (int64_t)side * side;
+        // CP:218-238 as written: block-row j of every block-column holds page j (< ratio)
+        if (pg < ratio)
+          for (int bc = 0; bc < ratio; ++bc) mp[(16 * pg + (m.row >> 4)) * side + 16 * bc + (m.row & 15)] = out;
+      }
+    }
+  }
+}
+
+template <int PHASE>
+__global__ void __launch_bounds__(kAlsThreads, 2) als_kernel(const __grid_constant__ AlsParams P) {
+  extern __shared__ __align__(16) float tile[];
+  __shared__ AlsSmem sm;
+  int si = 0;
+#pragma unroll 1
+  for (int k = 1; k < P.n_scales; ++k)
+    if ((int)blockIdx.x >= P.s[k].cta_begin) si = k;
+  const AlsScaleDev& sc = P.s[si];
+  const int tid = threadIdx.x;
+  if (sc.thr) {
+    if (tid == 0) sm.sorted = 1;
+    __syncthreads();
+    if (tid < kThrPad) {
+      double t = (tid < kThr) ? sc.thr[tid] : (double)NAN;
+      sm.thr_d[tid] = t;
+      sm.thr_f[tid] = (float)t;
+    }
+    if (tid < kLvl) sm.lvl_f[tid] = (float)sc.lvl[tid];
+    __syncthreads();
+    // the branch-free search needs non-decreasing thresholds in BOTH dtypes
+    if (tid < kThr - 1 && (!(sm.thr_d[tid] <= sm.thr_d[tid + 1]) || !(sm.thr_f[tid] <= sm.thr_f[tid + 1]))) sm.sorted = 0;
+  }
+  __syncthreads();
+  const int64_t n_units = P.n_images * sc.pages;
+  const int local_cta = (int)blockIdx.x - sc.cta_begin;
+  if (sc.rows == 256) {
+    const int64_t unit_idx = local_cta;
+    if (unit_idx < n_units) als_unit<4, PHASE>(P, sc, sm, tile, unit_idx, 0, tid);
+  } else {
+    const int unit = tid >> 6;
+    const int64_t unit_idx = (int64_t)local_cta * 4 + unit;
+    if (unit_idx < n_units) als_unit<1, PHASE>(P, sc, sm, tile + unit * (64 * 64), unit_idx, unit, tid & 63);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// CP:175-193 als_step as a stand-alone op: one warp per output row.
+__global__ void __launch_bounds__(256) als_step_kernel(const float* __restrict__ ratings, const float* __restrict__ fixed,
+                                                       int64_t batch, int rows, int cols, float reg, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t o = warp; o < batch * rows; o += nwarps) {
+    const int64_t b = o / rows;
+    const float* r = ratings + o * cols;
+    const float* f = fixed + b * cols;
+    float acc = 0.f;
+    double nn = 0.0;
+    for (int c = lane; c < cols; c += 32) {
+      float fv = f[c];
+      acc = fmaf(r[c], fv, acc);
+      nn = fma((double)fv, (double)fv, nn);
+    }
+    acc = warp_sum(acc);
+    nn = warp_sum(nn);
+    if (lane == 0) out[o] = acc * (1.0f / ((float)nn + reg));
+  }
+}
+
+}  // namespace rdm
+
+using namespace rdm;
+
+extern "C" int64_t rdm_als_ws_floats(int32_t rows, int32_t pages, int32_t limit) {
+  return (int64_t)pages * ((int64_t)limit + 1 + rows);
+}
+
+extern "C" int rdm_als_fused(const rdm_als_scale_t* scales, int32_t n_scales, int64_t n_images, int32_t group,
+                             rdm_stream_t stream) {
+  RDM_REQUIRE(scales, "rdm_als_fused: null scales");
+  RDM_REQUIRE(n_scales >= 1 && n_scales <= kMaxScales, "rdm_als_fused: n_scales must be 1..%d (got %d)", kMaxScales, n_scales);
+  RDM_REQUIRE(n_images >= 0, "rdm_als_fused: negative n_images");
+  RDM_REQUIRE(group >= 1, "rdm_als_fused: group must be >= 1");
+  RDM_REQUIRE(n_images % group == 0, "rdm_als_fused: n_images (%lld) must be a multiple of group (%d)", (long long)n_images, group);
+  if (n_images == 0) return 0;
+  AlsParams P;
+  P.n_scales = n_scales;
+  P.group = group;
+  P.n_images = n_images;
+  int64_t ctas = 0;
+  for (int k = 0; k < n_scales; ++k) {
+    const rdm_als_scale_t& h = scales[k];
+    RDM_REQUIRE(h.src && h.ws, "rdm_als_fused: scale %d: src and ws are required", k);
+    RDM_REQUIRE(h.rows == 64 || h.rows == 256, "rdm_als_fused: scale %d: rows must be 64 or 256 (got %d)", k, h.rows);
+    RDM_REQUIRE(h.src_kind >= RDM_SRC_RAW_F64 && h.src_kind <= RDM_SRC_MAP_F32, "rdm_als_fused: scale %d: bad src_kind %d", k, h.src_kind);
+    RDM_REQUIRE(h.limit >= 0 && h.limit <= (h.rows == 64 ? 63 : 127), "rdm_als_fused: scale %d: limit %d out of range", k, h.limit);
+    RDM_REQUIRE(h.pages >= 1, "rdm_als_fused: scale %d: pages must be >= 1", k);
+    const bool needs_side = h.src_kind == RDM_SRC_MAP_F32 || h.map_out;
+    if (needs_side) {
+      if (h.rows == 64)
+        RDM_REQUIRE(h.side == 8 && h.pages == 1, "rdm_als_fused: scale %d: rows=64 maps are 8x8, one page", k);
+      else
+        RDM_REQUIRE(is_pow2(h.side) && h.side >= 16 && h.side <= 128 && h.pages == (h.side / 16) * (h.side / 16),
+                    "rdm_als_fused: scale %d: side %d / pages %d inconsistent", k, h.side, h.pages);
+    }
+    const bool quant = h.src_kind == RDM_SRC_RAW_F64 || h.src_kind == RDM_SRC_RAW_F32 || h.src_kind == RDM_SRC_MAP_F32;
+    RDM_REQUIRE(!quant || (h.thresholds && h.levels), "rdm_als_fused: scale %d: codebook required for this src_kind", k);
+    RDM_REQUIRE(quant || !h.bins_out, "rdm_als_fused: scale %d: bins_out needs a quantising src_kind", k);
+    RDM_REQUIRE(h.src_kind == RDM_SRC_MAP_F32 || aligned16(h.src), "rdm_als_fused: scale %d: src must be 16-byte aligned", k);
+    RDM_REQUIRE((!h.values_out || aligned16(h.values_out)) && (!h.bins_out || (reinterpret_cast<uintptr_t>(h.bins_out) & 3u) == 0),
+                "rdm_als_fused: scale %d: values_out must be 16-byte and bins_out 4-byte aligned", k);
+    AlsScaleDev& d = P.s[k];
+    d.src = h.src;
+    d.thr = quant ? h.thresholds : nullptr;
+    d.lvl = quant ? h.levels : nullptr;
+    d.bins = h.bins_out;
+    d.values = h.values_out;
+    d.ws = h.ws;
+    d.pages_out = h.pages_out;
+    d.map_out = h.map_out;
+    d.record_out = h.record_out;
+    d.kstar_out = h.kstar_out;
+    d.kind = h.src_kind;
+    d.rows = h.rows;
+    d.pages = h.pages;
+    d.side = h.side;
+    d.limit = h.limit;
+    d.cta_begin = (int32_t)ctas;
+    const int64_t units = n_images * h.pages;
+    ctas += (h.rows == 256) ? units : (units + 3) / 4;
+    RDM_REQUIRE(ctas < (1ll << 30), "rdm_als_fused: too many work units");
+  }
+  const size_t dyn = kTileFloats * sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(als_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(als_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+  if (e != cudaSuccess) {
+    set_error("rdm_als_fused: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    return (int)e;
+  }
+  als_kernel<0><<<(unsigned)ctas, kAlsThreads, dyn, (cudaStream_t)stream>>>(P);
+  int rc = launch_status("als_kernel<iterate>");
+  if (rc) return rc;
+  als_kernel<1><<<(unsigned)ctas, kAlsThreads, dyn, (cudaStream_t)stream>>>(P);
+  return launch_status("als_kernel<select>");
+}
+
+extern "C" int rdm_als_step_f32(const float* ratings, const float* fixed, int64_t batch, int32_t rows, int32_t cols,
+                                float reg, float* out, rdm_stream_t stream) {
+  RDM_REQUIRE(ratings && fixed && out, "rdm_als_step_f32: null pointer");
+  RDM_REQUIRE(batch >= 0 && rows >= 1 && cols >= 1, "rdm_als_step_f32: bad shape");
+  if (batch == 0) return 0;
+  int64_t warps = batch * rows;
+  int64_t blocks = (warps + 7) / 8;
+  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  als_step_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(ratings, fixed, batch, rows, cols, reg, out);
+  return launch_status("als_step_kernel");
+}

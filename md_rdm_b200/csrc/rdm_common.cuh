@@ -1,0 +1,154 @@
+// Shared device/host helpers for librdm_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdarg>
+#include <cmath>
+
+#include "../../include/rdm_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "librdm_b200 is written for sm_100a (B200) only"
+#endif
+
+namespace rdm {
+
+// ---- error plumbing (no exceptions cross the ABI) --------------------------------------
+void set_error(const char* fmt, ...);
+int launch_status(const char* what);   // cudaGetLastError -> return code + message
+
+#define RDM_REQUIRE(cond, ...)            \
+  do {                                    \
+    if (!(cond)) {                        \
+      ::rdm::set_error(__VA_ARGS__);      \
+      return -1;                          \
+    }                                     \
+  } while (0)
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+inline int ilog2(int v) { int n = 0; while ((1 << n) < v) ++n; return n; }
+
+constexpr int kNumSMs = 148;          // B200
+constexpr int kThr = 40;              // Lloyd thresholds (RN:290)
+constexpr int kLvl = 41;              // Lloyd levels
+constexpr int kThrPad = 64;           // padded table for the branch-free search (NaN fill)
+
+// ---- warp helpers -------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_prod(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v *= __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_prod(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v *= __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// streaming 128-bit accesses (data touched once: keep it out of L1)
+__device__ __forceinline__ double2 ldg_stream_f64x2(const double* p) {
+  double2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float4 ldg_stream_f32x4(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float2 ldg_stream_f32x2(const float* p) {
+  float2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg_stream_f64x2(double* p, double a, double b) {
+  asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(a), "d"(b) : "memory");
+}
+__device__ __forceinline__ void stg_stream_f32x4(float* p, float4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+// ---- Lloyd bin search (RN:286-311) --------------------------------------------------------
+// Table of kThrPad entries: thresholds 0..39 then NaN.  For a non-decreasing table the count
+// of thresholds <= x equals the branch-free upper-bound position below; NaN x (and NaN
+// padding) compare false, so NaN / negatives / 0 land in bin 0 and +inf in bin 40 exactly
+// as the reference's 40 compares do.  `sorted == 0` falls back to the literal 40 compares.
+template <typename T>
+__device__ __forceinline__ int lloyd_bin(T x, const T* __restrict__ tab, int sorted) {
+  if (sorted) {
+    int pos = 0;
+#pragma unroll
+    for (int step = 32; step >= 1; step >>= 1) pos += (x >= tab[pos + step - 1]) ? step : 0;
+    return pos;
+  }
+  int c = 0;
+#pragma unroll 8
+  for (int i = 0; i < kThr; ++i) c += (x >= tab[i]) ? 1 : 0;
+  return c;
+}
+
+// Fill shared copies of one codebook.  thr_s: kThrPad entries of T; lvl_s: kLvl entries of T.
+// Returns (through *sorted_s, an int in shared memory) whether the thresholds are non-decreasing.
+template <typename T>
+__device__ __forceinline__ void load_codebook(const double* __restrict__ thr, const double* __restrict__ lvl,
+                                              T* thr_s, T* lvl_s, int* sorted_s, int tid, int nthreads) {
+  if (tid == 0) *sorted_s = 1;
+  __syncthreads();
+  for (int i = tid; i < kThrPad; i += nthreads)
+    thr_s[i] = (i < kThr) ? static_cast<T>(thr[i]) : static_cast<T>(NAN);
+  for (int i = tid; i < kLvl; i += nthreads) lvl_s[i] = static_cast<T>(lvl[i]);
+  __syncthreads();
+  for (int i = tid; i < kThr - 1; i += nthreads)
+    if (!(thr_s[i] <= thr_s[i + 1])) *sorted_s = 0;
+  __syncthreads();
+}
+
+// Bicubic (A = -0.75) weights at t = 0.5: the only ones an exact halving needs (CP:308-311).
+#define RDM_W0 (-0.09375)
+#define RDM_W1 (0.59375)
+
+// One output pixel of the stride-2 4-tap separable filter; `at(r, c)` returns the f64 source
+// value, indices are clamped here.  Horizontal taps are summed first, then vertical ones.
+template <typename F>
+__device__ __forceinline__ double bicubic_half_at(F at, int y, int x, int side) {
+  const double w[4] = {RDM_W0, RDM_W1, RDM_W1, RDM_W0};
+  double acc = 0.0;
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    int r = min(max(2 * y - 1 + a, 0), side - 1);
+    double inner = 0.0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      int c = min(max(2 * x - 1 + b, 0), side - 1);
+      double v = at(r, c);
+      inner = (b == 0) ? __dmul_rn(v, w[0]) : fma(v, w[b], inner);
+    }
+    acc = (a == 0) ? __dmul_rn(inner, w[0]) : fma(inner, w[a], acc);
+  }
+  return acc;
+}
+
+// RN:266-273 + CP:269-295: is column `col` (parent pixel col/8, col%8) inside the 3x3 window of
+// page row `row` (pixel row/16, row%16)?  The window is anchored top-left at (min(r/2,5), min(c/2,5)).
+__device__ __forceinline__ bool in_window(int row, int col) {
+  int r0 = min((row >> 4) >> 1, 5), c0 = min((row & 15) >> 1, 5);
+  int dr = (col >> 3) - r0, dc = (col & 7) - c0;
+  return (unsigned)dr < 3u && (unsigned)dc < 3u;
+}
+
+}  // namespace rdm

@@ -1,0 +1,802 @@
+// Stage 4 (multi-scale decomposition, also the ground-truth path) and stage 5 (log-space
+// weighted combination + recombination), as stand-alone ops mirroring the reference functions
+// one to one, plus rdm_fuse_tail which does stages 4+5 for one batch in a single launch.
+//
+// All of these are streaming kernels bounded by HBM bandwidth (O(1) flop per byte); the pyramids
+// are tiny (<= 64x64 f64 = 32 KB per decoder) and live in shared memory, so each input is read
+// once and each output written once.
+//   quick_gm / gm_normalize : CP:244-255, RN:117, network/module.py:145-149
+//   decompose               : CP:368-392 (+ CP:308-311 resize, CP:357-360 upsample)
+//   log_stack               : CP:464-484 make_matrix
+//   make_pred (+bwd)        : CP:512-528
+//   recombination (+bwd)    : CP:394-421 (+ CP:362-366 multi_upsample)
+//   fuse_tail               : RN:117-133 + network/module.py:132
+#include "rdm_common.cuh"
+
+namespace rdm {
+
+constexpr int kMaxPtrs = 16;
+constexpr int kPyrDoubles = 5461;   // levels 0..6: (4^7 - 1) / 3
+
+__host__ __device__ __forceinline__ int off_level(int k) { return ((1 << (2 * k)) - 1) / 3; }   // levels 0..k-1
+__host__ __device__ __forceinline__ int off_fine(int k) { return ((1 << (2 * k)) - 4) / 3; }    // F_1..F_{k-1}
+
+struct PtrList {
+  const void* p[kMaxPtrs];
+  int32_t side[kMaxPtrs];
+};
+struct MutPtrList {
+  void* p[kMaxPtrs];
+  int32_t side[kMaxPtrs];
+};
+
+template <typename T>
+__device__ __forceinline__ T block_prod(T v, T* scratch /* >= 32 */) {
+  v = warp_prod(v);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if (lane == 0) scratch[w] = v;
+  __syncthreads();
+  T r = scratch[0];
+  for (int i = 1; i < nw; ++i) r *= scratch[i];
+  return r;
+}
+
+// torch.pow(t, 1/rc^2) keeps t's dtype (int64 -> default f32); evaluated through f64 and rounded
+// so the f32 result is the correctly rounded power.
+template <typename TAcc>
+__device__ __forceinline__ TAcc pow_as(TAcc v, double e) {
+  return (TAcc)pow((double)v, e);
+}
+
+// one CTA per batch row: gm[b] = prod_i pow(t[b,i], e);  optional normalised copy x / gm
+template <typename TIn, typename TAcc>
+__global__ void __launch_bounds__(256) gm_kernel(const TIn* __restrict__ t, int64_t n, double e, TAcc* __restrict__ gm_out,
+                                                 TAcc* __restrict__ norm_out) {
+  __shared__ TAcc scratch[32];
+  const int64_t b = blockIdx.x;
+  const TIn* row = t + b * n;
+  TAcc prod = (TAcc)1;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) prod *= pow_as<TAcc>((TAcc)row[i], e);
+  const TAcc gm = block_prod<TAcc>(prod, scratch);
+  if (gm_out && threadIdx.x == 0) gm_out[b] = gm;
+  if (norm_out)
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) norm_out[b * n + i] = (TAcc)row[i] / gm;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pyramid of one map held in shared memory D[] (level k at off_level(k)), level `top` filled by
+// the caller.  emit(k, idx, F) is called for every fine-detail value F_k[idx], k = top..1.
+template <typename Emit>
+__device__ __forceinline__ void pyramid_down(double* D, int top, Emit emit) {
+  for (int k = top; k >= 1; --k) {
+    const int side = 1 << k, half = side >> 1;
+    const double* cur = D + off_level(k);
+    double* nxt = D + off_level(k - 1);
+    for (int idx = threadIdx.x; idx < half * half; idx += blockDim.x) {
+      int y = idx / half, x = idx - y * half;
+      nxt[idx] = bicubic_half_at([&](int r, int c) { return cur[r * side + c]; }, y, x, side);
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < side * side; idx += blockDim.x) {
+      int y = idx >> k, x = idx & (side - 1);
+      emit(k, idx, cur[idx] / nxt[(y >> 1) * half + (x >> 1)]);   // CP:389 torch.div(dn, upsample(dn_1))
+    }
+  }
+}
+
+// Output is LEVEL-MAJOR: [D_0 of all images (unless relative)] [F_1 of all images] ... so every
+// component is a dense (N,1,2^k,2^k) tensor for the caller.
+template <typename TIn>
+__global__ void __launch_bounds__(256) decompose_kernel(const TIn* __restrict__ in, int side, int n, int relative,
+                                                        double* __restrict__ out, int64_t n_images) {
+  extern __shared__ __align__(16) double D[];
+  const int64_t img = blockIdx.x;
+  const TIn* src = in + img * (int64_t)side * side;
+  const int base = relative ? 0 : 1;
+  auto fine = [&](int k) { return out + n_images * (base + off_fine(k)) + img * ((int64_t)1 << (2 * k)); };
+  int top = n;
+  if (n == 7) {   // D_7 stays in HBM/L2: it is read twice (D_6 taps, then the F_7 division)
+    double* d6 = D + off_level(6);
+    for (int idx = threadIdx.x; idx < 4096; idx += blockDim.x)
+      d6[idx] = bicubic_half_at([&](int r, int c) { return (double)src[r * 128 + c]; }, idx >> 6, idx & 63, 128);
+    __syncthreads();
+    double* f7 = fine(7);
+    for (int idx = threadIdx.x; idx < 16384; idx += blockDim.x)
+      f7[idx] = (double)src[idx] / d6[((idx >> 7) >> 1) * 64 + ((idx & 127) >> 1)];
+    top = 6;
+  } else {
+    double* dn = D + off_level(n);
+    for (int idx = threadIdx.x; idx < side * side; idx += blockDim.x) dn[idx] = (double)src[idx];
+    __syncthreads();
+  }
+  pyramid_down(D, top, [&](int k, int idx, double f) { fine(k)[idx] = f; });
+  __syncthreads();
+  if (!relative && threadIdx.x == 0) out[img] = D[0];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Backward of decompose.  With D_{k-1} = H(D_k) (H = the linear stride-2 bicubic filter) and
+// F_k = D_k / U(D_{k-1}), the total gradient G_j = dL/dD_j obeys
+//   G_j = [j >= 1] gF_j / U(D_{j-1})  -  [j < n] pool2x2(gF_{j+1} * D_{j+1}) / D_j^2
+//         + [j >= 1] H^T G_{j-1}  + [j == 0] gD_0
+// evaluated bottom-up; G_n is the input gradient.  H^T is applied as a deterministic gather.
+__device__ __forceinline__ int adj_taps(int r, int side, int (&ys)[3], double (&ws)[3]) {
+  const double w[4] = {RDM_W0, RDM_W1, RDM_W1, RDM_W0};
+  const int half = side >> 1;
+  int cnt = 0;
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    int t = r + 1 - a;
+    if (t >= 0 && !(t & 1) && (t >> 1) < half) {
+      ys[cnt] = t >> 1;
+      ws[cnt] = w[a];
+      ++cnt;
+    }
+  }
+  if (r == 0) {            // tap index -1 clamps to 0
+    ys[cnt] = 0;
+    ws[cnt] = w[0];
+    ++cnt;
+  }
+  if (r == side - 1) {     // tap index `side` clamps to side-1
+    ys[cnt] = half - 1;
+    ws[cnt] = w[3];
+    ++cnt;
+  }
+  return cnt;
+}
+
+__device__ __forceinline__ double adj_bicubic_at(const double* g, int r, int c, int side) {
+  const int half = side >> 1;
+  int ys[3], xs[3];
+  double wy[3], wx[3];
+  const int ny = adj_taps(r, side, ys, wy), nx = adj_taps(c, side, xs, wx);
+  double acc = 0.0;
+  for (int i = 0; i < ny; ++i) {
+    double inner = 0.0;
+    for (int j = 0; j < nx; ++j) inner = fma(g[ys[i] * half + xs[j]], wx[j], inner);
+    acc = fma(inner, wy[i], acc);
+  }
+  return acc;
+}
+
+template <typename TIn>
+__global__ void __launch_bounds__(256) decompose_bwd_kernel(const TIn* __restrict__ in, int side, int n, int relative,
+                                                            const double* __restrict__ gpyr, int64_t n_images, TIn* __restrict__ gin) {
+  extern __shared__ __align__(16) double sm[];
+  double* D = sm;
+  double* G = sm + kPyrDoubles;
+  const int64_t img = blockIdx.x;
+  const TIn* src = in + img * (int64_t)side * side;
+  const int base = relative ? 0 : 1;
+  auto gfine = [&](int k) { return gpyr + n_images * (base + off_fine(k)) + img * ((int64_t)1 << (2 * k)); };
+  // ---- forward levels
+  int top = n;
+  if (n == 7) {
+    double* d6 = D + off_level(6);
+    for (int idx = threadIdx.x; idx < 4096; idx += blockDim.x)
+      d6[idx] = bicubic_half_at([&](int r, int c) { return (double)src[r * 128 + c]; }, idx >> 6, idx & 63, 128);
+    top = 6;
+  } else {
+    double* dn = D + off_level(n);
+    for (int idx = threadIdx.x; idx < side * side; idx += blockDim.x) dn[idx] = (double)src[idx];
+  }
+  __syncthreads();
+  for (int k = top; k >= 1; --k) {
+    const int sd = 1 << k, half = sd >> 1;
+    const double* cur = D + off_level(k);
+    double* nxt = D + off_level(k - 1);
+    for (int idx = threadIdx.x; idx < half * half; idx += blockDim.x)
+      nxt[idx] = bicubic_half_at([&](int r, int c) { return cur[r * sd + c]; }, idx / half, idx % half, sd);
+    __syncthreads();
+  }
+  // ---- gradients, bottom-up
+  for (int j = 0; j <= n; ++j) {
+    const int sd = 1 << j;
+    const bool in_smem = j <= 6;
+    for (int idx = threadIdx.x; idx < sd * sd; idx += blockDim.x) {
+      const int y = idx >> j, x = idx & (sd - 1);
+      const double dj = in_smem ? D[off_level(j) + idx] : (double)src[idx];
+      double g = 0.0;
+      if (j == 0 && !relative) g = gpyr[img];
+      if (j >= 1) {
+        const int hs = sd >> 1;
+        g += gfine(j)[idx] / D[off_level(j - 1) + (y >> 1) * hs + (x >> 1)];
+        g += adj_bicubic_at(G + off_level(j - 1), y, x, sd);
+      }
+      if (j < n) {
+        const int us = sd << 1;
+        const double* gf = gfine(j + 1);
+        double pool = 0.0;
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+          for (int dx = 0; dx < 2; ++dx) {
+            const int u = (2 * y + dy) * us + 2 * x + dx;
+            const double du = (j + 1 <= 6) ? D[off_level(j + 1) + u] : (double)src[u];
+            pool = fma(gf[u], du, pool);
+          }
+        g -= pool / (dj * dj);
+      }
+      if (j == n)
+        gin[img * (int64_t)side * side + idx] = (TIn)g;
+      else
+        G[off_level(j) + idx] = g;
+    }
+    __syncthreads();
+  }
+}
+
+// backward of log_stack: grad_cand_k[b,m] = g[b,k,m] / cand_k[b,m]
+__global__ void __launch_bounds__(256) log_stack_bwd_kernel(PtrList cands, MutPtrList gc, int K, int64_t batch, int64_t M,
+                                                            const double* __restrict__ g) {
+  const int64_t total = batch * K * M;
+  for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
+    int64_t m = o % M;
+    int64_t bk = o / M;
+    int k = (int)(bk % K);
+    int64_t b = bk / K;
+    reinterpret_cast<double*>(gc.p[k])[b * M + m] = g[o] / reinterpret_cast<const double*>(cands.p[k])[b * M + m];
+  }
+}
+
+// backward of gm_normalize / quick_gm for one batch row per CTA (x f32 or f64):
+//   y_i = x_i / gm, gm = prod_j x_j^e  ->  dL/dx_j = gy_j / gm - (e / x_j) sum_i gy_i y_i  (+ ggm * e * gm / x_j)
+template <typename T>
+__global__ void __launch_bounds__(256) gm_bwd_kernel(const T* __restrict__ x, int64_t n, double e, const T* __restrict__ g_gm,
+                                                     const T* __restrict__ g_norm, T* __restrict__ gx) {
+  __shared__ double scratch[32];
+  __shared__ double part[8];
+  const int64_t b = blockIdx.x;
+  const T* row = x + b * n;
+  double prod = 1.0, dot = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    prod *= pow((double)row[i], e);
+    if (g_norm) dot = fma((double)g_norm[b * n + i], (double)row[i], dot);
+  }
+  const double gm = block_prod<double>(prod, scratch);
+  dot = warp_sum(dot);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = dot;
+  __syncthreads();
+  double S = 0.0;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) S += part[i];
+  S /= gm;   // sum_i gy_i y_i
+  const double gg = g_gm ? (double)g_gm[b] : 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    double v = (gg * gm - S) * e / (double)row[i];
+    if (g_norm) v += (double)g_norm[b * n + i] / gm;
+    gx[b * n + i] = (T)v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) log_stack_kernel(PtrList cands, int K, int64_t batch, int64_t M, double* __restrict__ out) {
+  const int64_t total = batch * K * M;
+  for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
+    int64_t m = o % M;
+    int64_t bk = o / M;
+    int k = (int)(bk % K);
+    int64_t b = bk / K;
+    out[o] = log(reinterpret_cast<const double*>(cands.p[k])[b * M + m]);
+  }
+}
+
+__global__ void __launch_bounds__(256) make_pred_kernel(const double* __restrict__ A, const float* __restrict__ w, int64_t batch,
+                                                        int K, int64_t M, float* __restrict__ out) {
+  const int64_t total = batch * M;
+  for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
+    int64_t b = o / M, m = o - b * M;
+    const double* a = A + b * K * M + m;
+    float acc = 0.f;
+    for (int k = 0; k < K; ++k) acc = fmaf((float)a[k * M], w[k], acc);   // A[b].T.float() @ w.float()
+    out[o] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(256) make_pred_bwd_a_kernel(const float* __restrict__ w, const float* __restrict__ g, int64_t batch,
+                                                              int K, int64_t M, double* __restrict__ grad_A) {
+  const int64_t total = batch * K * M;
+  for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
+    int64_t m = o % M;
+    int64_t bk = o / M;
+    int k = (int)(bk % K);
+    int64_t b = bk / K;
+    grad_A[o] = (double)(w[k] * g[b * M + m]);
+  }
+}
+
+// one CTA per weight: grad_w[k] = sum_b sum_m f32(A[b,k,m]) * g[b,m]
+__global__ void __launch_bounds__(512) make_pred_bwd_w_kernel(const double* __restrict__ A, const float* __restrict__ g, int64_t batch,
+                                                              int K, int64_t M, float* __restrict__ grad_w) {
+  __shared__ double part[16];
+  const int k = blockIdx.x;
+  double acc = 0.0;
+  for (int64_t o = threadIdx.x; o < batch * M; o += blockDim.x) {
+    int64_t b = o / M, m = o - b * M;
+    acc = fma((double)(float)A[(b * K + k) * M + m], (double)g[o], acc);
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += part[i];
+    grad_w[k] = (float)t;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// recombination: comps (in list order) d0? then sides 2,4,...; out side S = 2^n.
+template <typename TC>
+__global__ void __launch_bounds__(256) recombination_kernel(PtrList comps, int n_comps, int has_d0, int n, int64_t batch,
+                                                            double* __restrict__ out) {
+  const int S = 1 << n;
+  const int64_t per = (int64_t)S * S / 2;   // two horizontally adjacent pixels per thread
+  const int64_t total = batch * per;
+  for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = o / per;
+    const int rem = (int)(o - b * per);
+    const int y = rem / (S / 2), x = (rem - y * (S / 2)) * 2;
+    double a0 = 0.0, a1 = 0.0;
+    for (int j = has_d0; j < n_comps; ++j) {
+      const int cs = comps.side[j];
+      const int sh = n - (31 - __clz(cs));
+      const TC* c = reinterpret_cast<const TC*>(comps.p[j]) + b * (int64_t)cs * cs + (y >> sh) * cs;
+      const double v0 = (double)c[x >> sh], v1 = (double)c[(x + 1) >> sh];
+      if (j == has_d0) {
+        a0 = v0;
+        a1 = v1;
+      } else {
+        a0 += v0;
+        a1 += v1;
+      }
+    }
+    if (has_d0) {
+      const double d0 = (double)reinterpret_cast<const TC*>(comps.p[0])[b];
+      a0 = d0 + a0;
+      a1 = d0 + a1;
+    }
+    stg_stream_f64x2(out + b * (int64_t)S * S + (int64_t)y * S + x, a0, a1);
+  }
+}
+
+// backward: successive 2x2 sum pooling of grad_out (exactly what autograd does through the
+// chain of nearest x2 upsamples); component of side 2^k receives pooled level k.
+template <typename TC>
+__global__ void __launch_bounds__(256) recombination_bwd_kernel(const double* __restrict__ grad_out, MutPtrList gc, int n_comps, int n,
+                                                                int64_t batch) {
+  extern __shared__ __align__(16) double D[];
+  const int64_t b = blockIdx.x;
+  const int S = 1 << n;
+  const double* g = grad_out + b * (int64_t)S * S;
+  auto emit = [&](int k, const double* lvl) {
+    for (int j = 0; j < n_comps; ++j)
+      if (gc.side[j] == (1 << k) && gc.p[j]) {
+        TC* dst = reinterpret_cast<TC*>(gc.p[j]) + b * (int64_t)(1 << (2 * k));
+        for (int idx = threadIdx.x; idx < (1 << (2 * k)); idx += blockDim.x) dst[idx] = (TC)lvl[idx];
+      }
+  };
+  // level n straight from global
+  for (int j = 0; j < n_comps; ++j)
+    if (gc.side[j] == S && gc.p[j]) {
+      TC* dst = reinterpret_cast<TC*>(gc.p[j]) + b * (int64_t)S * S;
+      for (int idx = threadIdx.x; idx < S * S; idx += blockDim.x) dst[idx] = (TC)g[idx];
+    }
+  if (n == 0) return;
+  {
+    const int half = S >> 1;
+    double* nxt = D + off_level(n - 1);
+    for (int idx = threadIdx.x; idx < half * half; idx += blockDim.x) {
+      int y = idx / half, x = idx - y * half;
+      const double* r0 = g + (2 * y) * S + 2 * x;
+      nxt[idx] = (r0[0] + r0[1]) + (r0[S] + r0[S + 1]);
+    }
+    __syncthreads();
+    emit(n - 1, nxt);
+  }
+  for (int k = n - 1; k >= 1; --k) {
+    const int side = 1 << k, half = side >> 1;
+    const double* cur = D + off_level(k);
+    double* nxt = D + off_level(k - 1);
+    for (int idx = threadIdx.x; idx < half * half; idx += blockDim.x) {
+      int y = idx / half, x = idx - y * half;
+      const double* r0 = cur + (2 * y) * side + 2 * x;
+      nxt[idx] = (r0[0] + r0[1]) + (r0[side] + r0[side + 1]);
+    }
+    __syncthreads();
+    emit(k - 1, nxt);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused tail.  Grid = n_images * bands; every CTA rebuilds the (tiny) pyramids of its image in
+// shared memory and writes one horizontal band of the 128x128 f64 log-depth map, so the 128 KB
+// per image output - the only significant HBM traffic of stages 4+5 - is spread over the chip.
+constexpr int kMaxRel = 6;
+struct TailParams {
+  const int64_t* x_d1;
+  const float* rel[kMaxRel];
+  const float* w;
+  float* yhat_out;
+  double* depth_out;
+  double* A_out[8];
+  int32_t side[kMaxRel];
+  int32_t n_rel;
+  int32_t w_off[8];         // first weight of slot k
+  int32_t K[8];             // candidates in slot k
+  int32_t cand[kMaxRel + 1][8];   // candidate index of decoder d in slot k
+  int32_t kmax;
+  int32_t bands;
+};
+
+__global__ void __launch_bounds__(256) fuse_tail_kernel(const __grid_constant__ TailParams P) {
+  extern __shared__ __align__(16) double D[];               // kPyrDoubles
+  float* yh = reinterpret_cast<float*>(D + kPyrDoubles);     // kPyrDoubles floats, slot k at off_level(k)
+  __shared__ float scratch[32];
+  const int64_t img = blockIdx.x / P.bands;
+  const int band = blockIdx.x - (int)(img * P.bands);
+  const bool lead = band == 0;
+  const int tid = threadIdx.x;
+  const int ylen = off_level(P.kmax + 1);
+  for (int i = tid; i < ylen; i += blockDim.x) yh[i] = 0.f;
+
+  auto level_emit = [&](int dec) {
+    return [&, dec](int k, int idx, double f) {
+      const int cand = P.cand[dec][k];
+      const int64_t M = 1 << (2 * k);
+      const double lg = log(f);                                      // CP:478-480
+      if (lead && P.A_out[k]) P.A_out[k][(img * P.K[k] + cand) * M + idx] = lg;
+      float* y = yh + off_level(k) + idx;
+      *y = fmaf((float)lg, P.w[P.w_off[k] + cand], *y);               // CP:521 / CP:526
+    };
+  };
+
+  // ---- decoder 1 (ordinary map): x / gm(x) in f32 (RN:117), then 3 levels + D_0
+  {
+    float v = 1.f, pw = 1.f;
+    if (tid < 64) {
+      v = (float)P.x_d1[img * 64 + tid];
+      pw = (float)pow((double)v, 1.0 / 64.0);
+    }
+    const float gm = block_prod<float>(pw, scratch);
+    if (tid < 64) D[off_level(3) + tid] = (double)(v / gm);
+    __syncthreads();
+    pyramid_down(D, 3, level_emit(0));
+    __syncthreads();
+    if (tid == 0) {
+      const double d0 = D[0];
+      const double lg = log(d0);
+      if (lead && P.A_out[0]) P.A_out[0][img] = lg;
+      yh[0] = fmaf((float)lg, P.w[P.w_off[0]], yh[0]);
+    }
+  }
+  // ---- relative decoders
+  for (int r = 0; r < P.n_rel; ++r) {
+    const int side = P.side[r], n = 31 - __clz(side);
+    const float* src = P.rel[r] + img * (int64_t)side * side;
+    __syncthreads();
+    double* dn = D + off_level(n);
+    for (int idx = tid; idx < side * side; idx += blockDim.x) dn[idx] = (double)src[idx];
+    __syncthreads();
+    pyramid_down(D, n, level_emit(r + 1));
+  }
+  __syncthreads();
+  if (lead && P.yhat_out)
+    for (int i = tid; i < ylen; i += blockDim.x) P.yhat_out[img * ylen + i] = yh[i];
+  // ---- recombination of this CTA's band (CP:394-421): d0 + ((f1 + f2) + ... + f_kmax)
+  const int rows = 128 / P.bands;
+  double* out = P.depth_out + img * 16384 + (int64_t)band * rows * 128;
+  const double d0 = (double)yh[0];
+  for (int o = tid; o < rows * 64; o += blockDim.x) {
+    const int y = band * rows + (o >> 6), x = (o & 63) * 2;
+    double a0 = 0.0, a1 = 0.0;
+    for (int k = 1; k <= P.kmax; ++k) {
+      const int sh = 7 - k, cs = 1 << k;
+      const float* c = yh + off_level(k) + (y >> sh) * cs;
+      const double v0 = (double)c[x >> sh], v1 = (double)c[(x + 1) >> sh];
+      if (k == 1) {
+        a0 = v0;
+        a1 = v1;
+      } else {
+        a0 += v0;
+        a1 += v1;
+      }
+    }
+    stg_stream_f64x2(out + (o >> 6) * 128 + x, d0 + a0, d0 + a1);
+  }
+}
+
+static int grid_cap(int64_t items, int per_block) {
+  int64_t blocks = (items + per_block - 1) / per_block;
+  if (blocks > (int64_t)kNumSMs * 8) blocks = (int64_t)kNumSMs * 8;
+  return blocks < 1 ? 1 : (int)blocks;
+}
+
+}  // namespace rdm
+
+using namespace rdm;
+
+extern "C" int64_t rdm_pyramid_len(int32_t side, int32_t relative_map) {
+  if (!is_pow2(side)) return -1;
+  int n = ilog2(side);
+  return (relative_map ? 0 : 1) + (((int64_t)1 << (2 * (n + 1))) - 4) / 3;
+}
+
+template <typename TIn, typename TAcc>
+static int gm_launch(const void* t, int64_t batch, int64_t n, double e, void* gm_out, void* norm_out, rdm_stream_t stream) {
+  gm_kernel<TIn, TAcc><<<(unsigned)batch, 256, 0, (cudaStream_t)stream>>>((const TIn*)t, n, e, (TAcc*)gm_out, (TAcc*)norm_out);
+  return launch_status("gm_kernel");
+}
+
+static int gm_dispatch(const char* name, const void* t, int32_t dtype, int64_t batch, int64_t n, int32_t rc, void* gm_out,
+                       void* norm_out, rdm_stream_t stream) {
+  RDM_REQUIRE(t && (gm_out || norm_out), "%s: null pointer", name);
+  RDM_REQUIRE(dtype >= 0 && dtype <= 2, "%s: dtype must be 0 (f32), 1 (f64) or 2 (i64)", name);
+  RDM_REQUIRE(batch >= 0 && n >= 1 && rc >= 1, "%s: bad shape", name);
+  RDM_REQUIRE(batch < (1ll << 31), "%s: batch too large", name);
+  if (batch == 0) return 0;
+  const double e = 1.0 / ((double)rc * (double)rc);
+  if (dtype == 0) return gm_launch<float, float>(t, batch, n, e, gm_out, norm_out, stream);
+  if (dtype == 1) return gm_launch<double, double>(t, batch, n, e, gm_out, norm_out, stream);
+  return gm_launch<int64_t, float>(t, batch, n, e, gm_out, norm_out, stream);
+}
+
+extern "C" int rdm_quick_gm(const void* t, int32_t dtype, int64_t batch, int64_t n, int32_t rc, void* out, rdm_stream_t stream) {
+  return gm_dispatch("rdm_quick_gm", t, dtype, batch, n, rc, out, nullptr, stream);
+}
+
+extern "C" int rdm_gm_normalize(const void* x, int32_t dtype, int64_t n_images, int32_t side, void* out, rdm_stream_t stream) {
+  RDM_REQUIRE(side >= 1, "rdm_gm_normalize: bad side");
+  return gm_dispatch("rdm_gm_normalize", x, dtype, n_images, (int64_t)side * side, side, nullptr, out, stream);
+}
+
+extern "C" int rdm_decompose(const void* in, int32_t in_is_f64, int64_t n_images, int32_t side, int32_t relative_map,
+                             double* pyramid_out, rdm_stream_t stream) {
+  RDM_REQUIRE(in && pyramid_out, "rdm_decompose: null pointer");
+  RDM_REQUIRE(is_pow2(side) && side <= 128, "rdm_decompose: side must be a power of two <= 128 (got %d)", side);
+  RDM_REQUIRE(n_images >= 0 && n_images < (1ll << 31), "rdm_decompose: bad n_images");
+  if (n_images == 0) return 0;
+  const int n = ilog2(side);
+  const int64_t len = rdm_pyramid_len(side, relative_map);
+  if (len == 0) return 0;
+  const size_t smem = kPyrDoubles * sizeof(double);
+  cudaError_t e;
+  if (in_is_f64) {
+    e = cudaFuncSetAttribute(decompose_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess)
+      decompose_kernel<double><<<(unsigned)n_images, 256, smem, (cudaStream_t)stream>>>((const double*)in, side, n, relative_map, pyramid_out, n_images);
+  } else {
+    e = cudaFuncSetAttribute(decompose_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess)
+      decompose_kernel<float><<<(unsigned)n_images, 256, smem, (cudaStream_t)stream>>>((const float*)in, side, n, relative_map, pyramid_out, n_images);
+  }
+  if (e != cudaSuccess) {
+    set_error("rdm_decompose: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    return (int)e;
+  }
+  return launch_status("decompose_kernel");
+}
+
+extern "C" int rdm_decompose_bwd(const void* in, int32_t in_is_f64, int64_t n_images, int32_t side, int32_t relative_map,
+                                 const double* grad_pyramid, void* grad_in, rdm_stream_t stream) {
+  RDM_REQUIRE(in && grad_pyramid && grad_in, "rdm_decompose_bwd: null pointer");
+  RDM_REQUIRE(is_pow2(side) && side >= 2 && side <= 128, "rdm_decompose_bwd: side must be a power of two in 2..128 (got %d)", side);
+  RDM_REQUIRE(n_images >= 0 && n_images < (1ll << 31), "rdm_decompose_bwd: bad n_images");
+  if (n_images == 0) return 0;
+  const int n = ilog2(side);
+  const size_t smem = 2 * kPyrDoubles * sizeof(double);
+  cudaError_t e;
+  if (in_is_f64) {
+    e = cudaFuncSetAttribute(decompose_bwd_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess)
+      decompose_bwd_kernel<double><<<(unsigned)n_images, 256, smem, (cudaStream_t)stream>>>((const double*)in, side, n, relative_map, grad_pyramid, n_images, (double*)grad_in);
+  } else {
+    e = cudaFuncSetAttribute(decompose_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess)
+      decompose_bwd_kernel<float><<<(unsigned)n_images, 256, smem, (cudaStream_t)stream>>>((const float*)in, side, n, relative_map, grad_pyramid, n_images, (float*)grad_in);
+  }
+  if (e != cudaSuccess) {
+    set_error("rdm_decompose_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    return (int)e;
+  }
+  return launch_status("decompose_bwd_kernel");
+}
+
+extern "C" int rdm_gm_bwd(const void* x, int32_t is_f64, int64_t batch, int64_t n, int32_t rc, const void* grad_gm,
+                          const void* grad_norm, void* grad_x, rdm_stream_t stream) {
+  RDM_REQUIRE(x && grad_x && (grad_gm || grad_norm), "rdm_gm_bwd: null pointer");
+  RDM_REQUIRE(batch >= 0 && batch < (1ll << 31) && n >= 1 && rc >= 1, "rdm_gm_bwd: bad shape");
+  if (batch == 0) return 0;
+  const double e = 1.0 / ((double)rc * (double)rc);
+  if (is_f64)
+    gm_bwd_kernel<double><<<(unsigned)batch, 256, 0, (cudaStream_t)stream>>>((const double*)x, n, e, (const double*)grad_gm, (const double*)grad_norm, (double*)grad_x);
+  else
+    gm_bwd_kernel<float><<<(unsigned)batch, 256, 0, (cudaStream_t)stream>>>((const float*)x, n, e, (const float*)grad_gm, (const float*)grad_norm, (float*)grad_x);
+  return launch_status("gm_bwd_kernel");
+}
+
+extern "C" int rdm_log_stack_bwd(const double* const* cands, int32_t K, int64_t batch, int64_t M, const double* grad_out,
+                                 double* const* grad_cands, rdm_stream_t stream) {
+  RDM_REQUIRE(cands && grad_out && grad_cands, "rdm_log_stack_bwd: null pointer");
+  RDM_REQUIRE(K >= 1 && K <= kMaxPtrs, "rdm_log_stack_bwd: K must be 1..%d (got %d)", kMaxPtrs, K);
+  RDM_REQUIRE(batch >= 0 && M >= 1, "rdm_log_stack_bwd: bad shape");
+  if (batch == 0) return 0;
+  PtrList pl{};
+  MutPtrList gl{};
+  for (int k = 0; k < K; ++k) {
+    RDM_REQUIRE(cands[k] && grad_cands[k], "rdm_log_stack_bwd: candidate %d is null", k);
+    pl.p[k] = cands[k];
+    gl.p[k] = grad_cands[k];
+  }
+  log_stack_bwd_kernel<<<grid_cap(batch * K * M, 256), 256, 0, (cudaStream_t)stream>>>(pl, gl, K, batch, M, grad_out);
+  return launch_status("log_stack_bwd_kernel");
+}
+
+extern "C" int rdm_log_stack_f64(const double* const* cands, int32_t K, int64_t batch, int64_t M, double* out, rdm_stream_t stream) {
+  RDM_REQUIRE(cands && out, "rdm_log_stack_f64: null pointer");
+  RDM_REQUIRE(K >= 1 && K <= kMaxPtrs, "rdm_log_stack_f64: K must be 1..%d (got %d)", kMaxPtrs, K);
+  RDM_REQUIRE(batch >= 0 && M >= 1, "rdm_log_stack_f64: bad shape");
+  if (batch == 0) return 0;
+  PtrList pl{};
+  for (int k = 0; k < K; ++k) {
+    RDM_REQUIRE(cands[k], "rdm_log_stack_f64: candidate %d is null", k);
+    pl.p[k] = cands[k];
+  }
+  log_stack_kernel<<<grid_cap(batch * K * M, 256), 256, 0, (cudaStream_t)stream>>>(pl, K, batch, M, out);
+  return launch_status("log_stack_kernel");
+}
+
+extern "C" int rdm_make_pred_f32(const double* A, const float* w, int64_t batch, int32_t K, int64_t M, float* out, rdm_stream_t stream) {
+  RDM_REQUIRE(A && w && out, "rdm_make_pred_f32: null pointer");
+  RDM_REQUIRE(batch >= 0 && K >= 1 && M >= 1, "rdm_make_pred_f32: bad shape");
+  if (batch == 0) return 0;
+  make_pred_kernel<<<grid_cap(batch * M, 256), 256, 0, (cudaStream_t)stream>>>(A, w, batch, K, M, out);
+  return launch_status("make_pred_kernel");
+}
+
+extern "C" int rdm_make_pred_bwd(const double* A, const float* w, const float* grad_out, int64_t batch, int32_t K, int64_t M,
+                                 double* grad_A, float* grad_w, rdm_stream_t stream) {
+  RDM_REQUIRE(grad_out && (grad_A || grad_w), "rdm_make_pred_bwd: null pointer");
+  RDM_REQUIRE((!grad_A || w) && (!grad_w || A), "rdm_make_pred_bwd: grad_A needs w, grad_w needs A");
+  RDM_REQUIRE(batch >= 0 && K >= 1 && M >= 1, "rdm_make_pred_bwd: bad shape");
+  if (batch == 0) {
+    if (grad_w) cudaMemsetAsync(grad_w, 0, sizeof(float) * K, (cudaStream_t)stream);
+    return launch_status("rdm_make_pred_bwd memset");
+  }
+  if (grad_A) {
+    make_pred_bwd_a_kernel<<<grid_cap(batch * K * M, 256), 256, 0, (cudaStream_t)stream>>>(w, grad_out, batch, K, M, grad_A);
+    int rc = launch_status("make_pred_bwd_a_kernel");
+    if (rc) return rc;
+  }
+  if (grad_w) {
+    make_pred_bwd_w_kernel<<<(unsigned)K, 512, 0, (cudaStream_t)stream>>>(A, grad_out, batch, K, M, grad_w);
+    return launch_status("make_pred_bwd_w_kernel");
+  }
+  return 0;
+}
+
+static int check_comp_sides(const char* name, const int32_t* sides, int32_t n_comps, int32_t n, int* has_d0) {
+  RDM_REQUIRE(n_comps >= 1 && n_comps <= kMaxPtrs, "%s: n_comps must be 1..%d (got %d)", name, kMaxPtrs, n_comps);
+  RDM_REQUIRE(n >= 1 && n <= 12, "%s: n must be 1..12 (got %d)", name, n);
+  *has_d0 = sides[0] == 1;
+  RDM_REQUIRE(n_comps > *has_d0, "%s: need at least one component besides d_0", name);
+  // CP:405-418 upsamples the j-th remaining component n-1-j times: its side must be 2^(j+1)
+  for (int j = *has_d0; j < n_comps; ++j) {
+    int want = 2 << (j - *has_d0);
+    RDM_REQUIRE(sides[j] == want && want <= (1 << n), "%s: component %d has side %d, expected %d (<= %d)", name, j, sides[j], want, 1 << n);
+  }
+  return 0;
+}
+
+extern "C" int rdm_recombination_f64(const void* const* comps, const int32_t* sides, int32_t n_comps, int32_t comps_are_f64,
+                                     int64_t batch, int32_t n, double* out, rdm_stream_t stream) {
+  RDM_REQUIRE(comps && sides && out, "rdm_recombination_f64: null pointer");
+  int has_d0 = 0;
+  if (check_comp_sides("rdm_recombination_f64", sides, n_comps, n, &has_d0)) return -1;
+  RDM_REQUIRE(aligned16(out), "rdm_recombination_f64: out must be 16-byte aligned");
+  RDM_REQUIRE(batch >= 0, "rdm_recombination_f64: bad batch");
+  if (batch == 0) return 0;
+  PtrList pl{};
+  for (int j = 0; j < n_comps; ++j) {
+    RDM_REQUIRE(comps[j], "rdm_recombination_f64: component %d is null", j);
+    pl.p[j] = comps[j];
+    pl.side[j] = sides[j];
+  }
+  const int64_t items = batch * ((int64_t)1 << (2 * n)) / 2;
+  if (comps_are_f64)
+    recombination_kernel<double><<<grid_cap(items, 256), 256, 0, (cudaStream_t)stream>>>(pl, n_comps, has_d0, n, batch, out);
+  else
+    recombination_kernel<float><<<grid_cap(items, 256), 256, 0, (cudaStream_t)stream>>>(pl, n_comps, has_d0, n, batch, out);
+  return launch_status("recombination_kernel");
+}
+
+extern "C" int rdm_recombination_bwd(const double* grad_out, void* const* grad_comps, const int32_t* sides, int32_t n_comps,
+                                     int32_t comps_are_f64, int64_t batch, int32_t n, rdm_stream_t stream) {
+  RDM_REQUIRE(grad_out && grad_comps && sides, "rdm_recombination_bwd: null pointer");
+  int has_d0 = 0;
+  if (check_comp_sides("rdm_recombination_bwd", sides, n_comps, n, &has_d0)) return -1;
+  RDM_REQUIRE(n <= 7, "rdm_recombination_bwd: n must be <= 7 (got %d)", n);
+  RDM_REQUIRE(batch >= 0 && batch < (1ll << 31), "rdm_recombination_bwd: bad batch");
+  if (batch == 0) return 0;
+  MutPtrList pl{};
+  for (int j = 0; j < n_comps; ++j) {
+    pl.p[j] = grad_comps[j];
+    pl.side[j] = sides[j];
+  }
+  const size_t smem = kPyrDoubles * sizeof(double);
+  cudaError_t e;
+  if (comps_are_f64) {
+    e = cudaFuncSetAttribute(recombination_bwd_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess)
+      recombination_bwd_kernel<double><<<(unsigned)batch, 256, smem, (cudaStream_t)stream>>>(grad_out, pl, n_comps, n, batch);
+  } else {
+    e = cudaFuncSetAttribute(recombination_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess)
+      recombination_bwd_kernel<float><<<(unsigned)batch, 256, smem, (cudaStream_t)stream>>>(grad_out, pl, n_comps, n, batch);
+  }
+  if (e != cudaSuccess) {
+    set_error("rdm_recombination_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    return (int)e;
+  }
+  return launch_status("recombination_bwd_kernel");
+}
+
+extern "C" int64_t rdm_fuse_tail_weight_count(const int32_t* sides, int32_t n_rel) {
+  if (n_rel < 0 || n_rel > kMaxRel) return -1;
+  int64_t total = 4;   // decoder 1: d0, f1, f2, f3
+  for (int r = 0; r < n_rel; ++r) {
+    if (!is_pow2(sides[r]) || sides[r] < 2 || sides[r] > 64) return -1;
+    total += ilog2(sides[r]);
+  }
+  return total;
+}
+
+extern "C" int rdm_fuse_tail(const int64_t* x_d1, const float* const* rel, const int32_t* sides, int32_t n_rel,
+                             const float* weights, int64_t n_images, float* yhat_out, double* depth_out,
+                             double* const* A_out, rdm_stream_t stream) {
+  RDM_REQUIRE(x_d1 && weights && depth_out, "rdm_fuse_tail: null pointer");
+  RDM_REQUIRE(n_rel >= 0 && n_rel <= kMaxRel, "rdm_fuse_tail: n_rel must be 0..%d (got %d)", kMaxRel, n_rel);
+  RDM_REQUIRE(n_rel == 0 || (rel && sides), "rdm_fuse_tail: rel/sides required");
+  RDM_REQUIRE(aligned16(depth_out), "rdm_fuse_tail: depth_out must be 16-byte aligned");
+  RDM_REQUIRE(n_images >= 0, "rdm_fuse_tail: bad n_images");
+  if (n_images == 0) return 0;
+  TailParams P{};
+  P.x_d1 = x_d1;
+  P.w = weights;
+  P.yhat_out = yhat_out;
+  P.depth_out = depth_out;
+  P.n_rel = n_rel;
+  P.kmax = 3;
+  for (int k = 0; k < 8; ++k) {
+    P.K[k] = (k <= 3) ? 1 : 0;
+    P.cand[0][k] = 0;
+  }
+  for (int r = 0; r < n_rel; ++r) {
+    RDM_REQUIRE(rel[r], "rdm_fuse_tail: rel[%d] is null", r);
+    RDM_REQUIRE(is_pow2(sides[r]) && sides[r] >= 2 && sides[r] <= 64, "rdm_fuse_tail: rel side must be a power of two in 2..64 (got %d)", sides[r]);
+    P.rel[r] = rel[r];
+    P.side[r] = sides[r];
+    const int n = ilog2(sides[r]);
+    if (n > P.kmax) P.kmax = n;
+    for (int k = 1; k <= n; ++k) P.cand[r + 1][k] = P.K[k]++;
+  }
+  int woff = 0;
+  for (int k = 0; k < 8; ++k) {
+    P.w_off[k] = woff;
+    woff += P.K[k];
+    P.A_out[k] = (A_out && k <= P.kmax) ? A_out[k] : nullptr;
+  }
+  int bands = 1;
+  while (bands < 16 && n_images * bands < kNumSMs) bands <<= 1;
+  P.bands = bands;
+  RDM_REQUIRE(n_images * bands < (1ll << 31), "rdm_fuse_tail: too many images");
+  const size_t smem = kPyrDoubles * (sizeof(double) + sizeof(float));
+  cudaError_t e = cudaFuncSetAttribute(fuse_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) {
+    set_error("rdm_fuse_tail: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    return (int)e;
+  }
+  fuse_tail_kernel<<<(unsigned)(n_images * bands), 256, smem, (cudaStream_t)stream>>>(P);
+  return launch_status("fuse_tail_kernel");
+}

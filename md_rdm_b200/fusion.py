@@ -1,0 +1,211 @@
+"""Batched fast entry point of the fusion path: all relative decoder scales of one batch in
+THREE launches (ALS iterate, ALS select/normalise/re-tile, fused decompose+combine+recombine),
+with every buffer preallocated, optional CUDA-graph replay and a pinned-host end-to-end call.
+
+This sits beside the drop-in names (md_rdm_b200.computations / rdm_net) and computes exactly
+what RN:103-133 + network/module.py:132 compute for decoder 1 plus relative decoders at
+`scales`: it is what `bench.py` times.
+
+source = "map": inputs are the decoder maps; pair build + Lloyd + ALS are fused and the pair
+                matrices never exist in HBM (the call a user of RDM_Net makes).
+source = "raw": inputs are materialised raw pair matrices (f32 64x64 for scale 8, f64
+                P x 256 x 64 for scales >= 16), as BASELINE.json's standalone fusion config
+                states it: quantize + ALS + decompose + reconstruct.
+"""
+from __future__ import annotations
+
+from ctypes import c_void_p
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import _cabi
+from ._cabi import AlsScale, check, i32_array, load, ptr_array
+from .codebooks import Quantization, default_quantization
+from .ops import split_yhat, tail_layout
+
+LIMIT_8 = 30
+LIMIT_PAGE = 100
+
+
+class FusionPlan:
+    def __init__(self, n_images: int, scales: Sequence[int] = (8, 16, 32), source: str = "map", group: Optional[int] = None,
+                 device="cuda", quant: Optional[Quantization] = None, want_bins: bool = True, want_values: bool = False,
+                 want_A: bool = False, limit_8: int = LIMIT_8, limit_page: int = LIMIT_PAGE):
+        if source not in ("map", "raw"):
+            raise ValueError("source must be 'map' or 'raw'")
+        self.lib = load()                      # raises if librdm_b200.so is missing: no fallback
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("FusionPlan needs a CUDA device (md_rdm_b200 has no CPU path)")
+        self.N = int(n_images)
+        self.group = int(group) if group else self.N
+        if self.N % self.group:
+            raise ValueError("n_images must be a multiple of group")
+        self.scales = tuple(int(s) for s in scales)
+        if any(s not in (8, 16, 32, 64) for s in self.scales):
+            raise ValueError("relative decoder scales must be in {8,16,32,64}")
+        self.source = source
+        self.quant = quant or default_quantization()
+        dev, N = self.device, self.N
+        f32, f64 = torch.float32, torch.float64
+        K, w_off, kmax, n_w = tail_layout(self.scales)
+        self.K, self.w_off, self.kmax, self.n_weights = K, w_off, kmax, n_w
+
+        # ---- inputs (static buffers: copy into them, then run())
+        self.x_d1 = torch.ones((N, 1, 8, 8), dtype=torch.int64, device=dev)
+        self.weights = torch.ones((n_w,), dtype=f32, device=dev)
+        self.src: Dict[int, torch.Tensor] = {}
+        # ---- outputs
+        self.rel: Dict[int, torch.Tensor] = {}
+        self.pages: Dict[int, torch.Tensor] = {}
+        self.bins: Dict[int, torch.Tensor] = {}
+        self.values: Dict[int, torch.Tensor] = {}
+        self.record: Dict[int, torch.Tensor] = {}
+        self.kstar: Dict[int, torch.Tensor] = {}
+        self._ws: Dict[int, torch.Tensor] = {}
+        self._tables = {}
+        G = N // self.group
+        descs = (AlsScale * len(self.scales))()
+        for i, s in enumerate(self.scales):
+            rows = 64 if s == 8 else 256
+            P = 1 if s == 8 else (s // 16) ** 2
+            limit = limit_8 if s == 8 else limit_page
+            if source == "map":
+                self.src[s] = torch.ones((N, 1, s, s), dtype=f32, device=dev)
+                kind = _cabi.SRC_MAP_F32
+            elif s == 8:
+                self.src[s] = torch.ones((N, 64, 64), dtype=f32, device=dev)
+                kind = _cabi.SRC_RAW_F32
+            else:
+                self.src[s] = torch.ones((N, P, 256, 64), dtype=f64, device=dev)
+                kind = _cabi.SRC_RAW_F64
+            thr, lvl = self.quant.device_tables(s, dev)
+            self._tables[s] = (thr, lvl)
+            self.rel[s] = torch.empty((N, 1, s, s), dtype=f32, device=dev)
+            self.pages[s] = torch.empty((N, P, rows), dtype=f32, device=dev)
+            self.record[s] = torch.empty((G, P, limit + 1), dtype=f32, device=dev)
+            self.kstar[s] = torch.empty((G, P), dtype=torch.int32, device=dev)
+            self._ws[s] = torch.empty((N * self.lib.rdm_als_ws_floats(rows, P, limit),), dtype=f32, device=dev)
+            if want_bins:
+                self.bins[s] = torch.empty((N, P, rows, 64), dtype=torch.uint8, device=dev)
+            if want_values:
+                self.values[s] = torch.empty((N, P, rows, 64), dtype=f32, device=dev)
+            d = descs[i]
+            d.src, d.src_kind, d.rows, d.pages, d.side, d.limit = self.src[s].data_ptr(), kind, rows, P, s, limit
+            d.thresholds, d.levels = thr.data_ptr(), lvl.data_ptr()
+            d.bins_out = self.bins[s].data_ptr() if want_bins else None
+            d.values_out = self.values[s].data_ptr() if want_values else None
+            d.pages_out, d.map_out, d.ws = self.pages[s].data_ptr(), self.rel[s].data_ptr(), self._ws[s].data_ptr()
+            d.record_out, d.kstar_out = self.record[s].data_ptr(), self.kstar[s].data_ptr()
+        self._descs = descs
+        self.yhat = torch.empty((N, (4 ** (kmax + 1) - 1) // 3), dtype=f32, device=dev)
+        self.depth = torch.empty((N, 1, 128, 128), dtype=f64, device=dev)
+        self.A: List[torch.Tensor] = [torch.empty((N, K[k], 4 ** k), dtype=f64, device=dev) for k in range(kmax + 1)] if want_A else []
+        self._rel_ptrs = ptr_array([self.rel[s].data_ptr() for s in self.scales])
+        self._sides = i32_array(list(self.scales))
+        self._a_ptrs = ptr_array([self.A[k].data_ptr() if (want_A and k <= kmax) else None for k in range(8)])
+        self._graph: Optional[torch.cuda.CUDAGraph] = None
+        self._pinned = None
+        self.launches_per_run = 3   # als_kernel<0>, als_kernel<1>, fuse_tail_kernel
+
+    # ------------------------------------------------------------------ device path
+    def run(self) -> torch.Tensor:
+        """Enqueue the whole path on the current stream; returns the (N,1,128,128) f64 log-depth buffer."""
+        st = c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        lib = self.lib
+        if self.scales:
+            check(lib.rdm_als_fused(self._descs, len(self.scales), self.N, self.group, st), "rdm_als_fused")
+        check(lib.rdm_fuse_tail(c_void_p(self.x_d1.data_ptr()), self._rel_ptrs, self._sides, len(self.scales),
+                                c_void_p(self.weights.data_ptr()), self.N, c_void_p(self.yhat.data_ptr()),
+                                c_void_p(self.depth.data_ptr()), self._a_ptrs, st), "rdm_fuse_tail")
+        return self.depth
+
+    def capture(self) -> None:
+        """Record run() into a CUDA graph (the library does no host sync and no allocation)."""
+        with torch.cuda.device(self.device):
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                self.run()                      # warm-up outside capture (function attributes, module load)
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.run()
+            self._graph = g
+
+    def replay(self) -> torch.Tensor:
+        if self._graph is None:
+            self.capture()
+        self._graph.replay()
+        return self.depth
+
+    # ------------------------------------------------------------------ inputs
+    def load_inputs(self, x_d1: torch.Tensor, srcs: Sequence[torch.Tensor], weights: Optional[torch.Tensor] = None) -> None:
+        self.x_d1.copy_(x_d1.reshape(self.x_d1.shape), non_blocking=True)
+        for s, t in zip(self.scales, srcs):
+            self.src[s].copy_(t.reshape(self.src[s].shape), non_blocking=True)
+        if weights is not None:
+            self.weights.copy_(weights.reshape(-1), non_blocking=True)
+
+    def yhat_list(self) -> List[torch.Tensor]:
+        """The reference's y_hat: list of (N,1,2^k,2^k) f32 views, k = 0..kmax."""
+        return split_yhat(self.yhat, self.kmax)
+
+    # ------------------------------------------------------------------ host end-to-end
+    def _host_buffers(self):
+        if self._pinned is None:
+            pin = lambda t: torch.empty(t.shape, dtype=t.dtype).pin_memory()
+            self._pinned = dict(x_d1=pin(self.x_d1), src={s: pin(self.src[s]) for s in self.scales}, depth=pin(self.depth))
+        return self._pinned
+
+    def h2d_bytes(self) -> int:
+        return self.x_d1.numel() * 8 + sum(t.numel() * t.element_size() for t in self.src.values())
+
+    def d2h_bytes(self) -> int:
+        return self.depth.numel() * 8
+
+    def run_host(self, x_d1: torch.Tensor, srcs: Sequence[torch.Tensor], use_graph: bool = True) -> torch.Tensor:
+        """Host tensors in -> host (pinned) log-depth out, synchronous: H2D copies, the three
+        launches (graph replay), D2H copy, stream sync."""
+        hb = self._host_buffers()
+        hb["x_d1"].copy_(x_d1.reshape(hb["x_d1"].shape))
+        for s, t in zip(self.scales, srcs):
+            hb["src"][s].copy_(t.reshape(hb["src"][s].shape))
+        return self.run_pinned(use_graph)
+
+    def run_pinned(self, use_graph: bool = True) -> torch.Tensor:
+        """Same, with the inputs already staged in this plan's pinned host buffers."""
+        hb = self._host_buffers()
+        self.x_d1.copy_(hb["x_d1"], non_blocking=True)
+        for s in self.scales:
+            self.src[s].copy_(hb["src"][s], non_blocking=True)
+        if use_graph:
+            self.replay()
+        else:
+            self.run()
+        hb["depth"].copy_(self.depth, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return hb["depth"]
+
+
+_plans: Dict[tuple, FusionPlan] = {}
+
+
+def fuse_maps(x_d1: torch.Tensor, rel_maps: Sequence[torch.Tensor], weights: Sequence[torch.Tensor] | torch.Tensor,
+              quant: Optional[Quantization] = None):
+    """Functional form: decoder outputs in, (depth (B,1,128,128) f64, y_hat list, filled relative maps) out.
+    x_d1 (B,1,8,8) int64 DORN counts, rel_maps[i] (B,1,s_i,s_i) f32; weights: the `Weights.weight_list`
+    (list of (K,1)) or a flat tensor.  One arg-min group = the whole call, like one reference forward."""
+    B = x_d1.shape[0]
+    scales = tuple(int(r.shape[2]) for r in rel_maps)
+    key = (B, scales, str(x_d1.device), id(quant))
+    plan = _plans.get(key)
+    if plan is None:
+        plan = _plans[key] = FusionPlan(B, scales, "map", device=x_d1.device, quant=quant, want_bins=False)
+    if not torch.is_tensor(weights):
+        weights = torch.cat([w.reshape(-1) for w in weights if w.numel()])
+    plan.load_inputs(x_d1, rel_maps, weights.float())
+    plan.run()
+    return plan.depth.clone(), [y.clone() for y in plan.yhat_list()], [plan.rel[s].clone() for s in scales]

@@ -1,0 +1,80 @@
+"""CPU: the C-ABI library builds, loads, exports every symbol include/rdm_b200.h declares, and
+rejects bad arguments with the documented error convention (no compute calls: no GPU here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+from md_rdm_b200 import _cabi
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "rdm_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(rdm_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_exported(lib):
+    syms = _declared_symbols()
+    assert len(syms) >= 20
+    raw = ctypes.CDLL(_cabi.LIB_PATH)
+    for s in syms:
+        assert hasattr(raw, s), f"{s} declared in include/rdm_b200.h but not exported"
+    assert set(syms) == set(_cabi.PROTOTYPES), "ctypes prototypes and header disagree"
+
+
+def test_abi_version_and_sizes(lib):
+    assert lib.rdm_abi_version() == _cabi.ABI_VERSION
+    assert lib.rdm_pyramid_len(128, 0) == 21845
+    assert lib.rdm_pyramid_len(8, 1) == 84
+    assert lib.rdm_pyramid_len(12, 0) == -1
+    assert lib.rdm_als_ws_floats(256, 4, 100) == 4 * (101 + 256)
+    sides = (ctypes.c_int32 * 3)(8, 16, 32)
+    assert lib.rdm_fuse_tail_weight_count(sides, 3) == 4 + 3 + 4 + 5
+    assert ctypes.sizeof(_cabi.AlsScale) == 8 + 6 * 4 + 9 * 8
+
+
+def test_argument_errors_do_not_launch(lib):
+    null = ctypes.c_void_p(0)
+    rc = lib.rdm_pair_v1_f32(null, 4, null, null)
+    assert rc < 0 and b"null pointer" in lib.rdm_last_error()
+    one = ctypes.c_void_p(16)
+    rc = lib.rdm_pair_id_f64(one, 1, 24, one, null, null)
+    assert rc < 0 and b"side must be" in lib.rdm_last_error()
+    rc = lib.rdm_decompose(one, 0, 1, 100, 0, one, null)
+    assert rc < 0 and b"power of two" in lib.rdm_last_error()
+    sc = _cabi.AlsScale(src=16, src_kind=_cabi.SRC_VAL_F32, rows=128, pages=1, side=16, limit=10, ws=16)
+    rc = lib.rdm_als_fused(sc, 1, 4, 4, null)
+    assert rc < 0 and b"rows must be 64 or 256" in lib.rdm_last_error()
+    sc.rows = 256
+    rc = lib.rdm_als_fused(sc, 1, 6, 4, null)
+    assert rc < 0 and b"multiple of group" in lib.rdm_last_error()
+    # empty batches are a no-op, not an error
+    assert lib.rdm_pair_v1_f32(one, 0, one, null) == 0
+    assert lib.rdm_als_fused(sc, 1, 0, 4, null) == 0
+
+
+def test_ops_refuse_cpu_tensors():
+    import torch
+    import md_rdm_b200.computations as cp
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        cp.quick_gm(torch.ones(2, 4, 1), 2)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        cp.decompose_depth_map([], torch.ones(1, 1, 8, 8), 3)
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(_cabi, "_lib", None)
+    monkeypatch.setattr(_cabi, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_cabi.RdmError, match="no CPU or PyTorch fallback"):
+        _cabi.load()
+
+
+def test_product_does_not_import_oracle():
+    for root, _, files in os.walk(os.path.join(ROOT, "md_rdm_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(root, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f

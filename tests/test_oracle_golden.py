@@ -1,0 +1,102 @@
+"""CPU: the oracle restatement against the golden vectors generated from the unmodified
+reference (tools/make_golden.py).  This is what pins the oracle (tests/golden/README.md)."""
+import numpy as np
+import torch
+
+from conftest import load_golden
+from oracle import fusion_ref as fr
+
+
+def _eq_nan(a, b):
+    return torch.equal(torch.nan_to_num(a, nan=-7.0), torch.nan_to_num(b, nan=-7.0))
+
+
+def test_codebook_relations(books):
+    # codebook(s) == codebook(2s)**2, thresholds are geometric means of adjacent levels
+    for s in (16, 32, 64):
+        q, lv = books[s]
+        q2, lv2 = books[2 * s]
+        assert torch.allclose(q, q2 ** 2, rtol=1e-13, atol=0)
+        assert torch.allclose(lv, lv2 ** 2, rtol=1e-13, atol=0)
+    q, lv = books[16]
+    assert torch.allclose(q, torch.sqrt(lv[:-1] * lv[1:]), rtol=1e-15, atol=0)
+    assert lv[20].item() == 1.0
+    assert torch.all(q[1:] > q[:-1])
+
+
+def test_lloyd_edges(books):
+    g = load_golden("lloyd_edges.npz")
+    for s in (8, 16, 32):
+        q, lv = books[s]
+        for name in ("f32", "f64"):
+            x = torch.from_numpy(g[f"x_{s}_{name}"])
+            v, b = fr.lloyd(x, q, lv)
+            assert _eq_nan(v, torch.from_numpy(g[f"values_{s}_{name}"]))
+            assert torch.equal(b, torch.from_numpy(g[f"bins_{s}_{name}"]))
+
+
+def test_relative_tails(books):
+    g = load_golden("relative_tails_b2.npz")
+    for s in (8, 16, 32):
+        x = torch.from_numpy(g[f"x_{s}"])
+        out, inter = fr.relative_decoder_tail(x, books, want_intermediates=True)
+        assert (out - torch.from_numpy(g[f"map_{s}"])).abs().max().item() <= 1e-6
+        for pi, it in enumerate(inter):
+            assert torch.equal(it["bins"], torch.from_numpy(g[f"bins_{s}_p{pi}"]))
+            assert it["kstar"] == int(g[f"kstar_{s}_p{pi}"])
+
+
+def test_als(books):
+    g = load_golden("als.npz")
+    for name, lim in (("page", 100), ("sq", 30)):
+        m, rec, k = fr.als_rank1(torch.from_numpy(g[f"Rq_{name}"]), lim)
+        assert k == int(g[f"kstar_{name}"])
+        assert (m - torch.from_numpy(g[f"map_{name}"])).abs().max().item() <= 1e-6
+        assert np.allclose(np.array(rec, dtype=np.float32), g[f"record_{name}"], rtol=1e-5)
+        assert int(g[f"const_kstar_{name}"]) == 0
+
+
+def test_full_path(books):
+    g = load_golden("full_path_b2.npz")
+    scales = (8, 16, 32)
+    x_d1 = torch.from_numpy(g["x_d1"])
+    rel = [torch.from_numpy(g[f"rel_in_{s}"]) for s in scales]
+    weights = [torch.from_numpy(g[f"w_{i}"]) for i in range(6)]
+    o = fr.fusion_forward(x_d1, rel, weights, books)
+    for s, r in zip(scales, o["rel"]):
+        assert (r - torch.from_numpy(g[f"rel_out_{s}"])).abs().max().item() <= 1e-6
+    for i, a in enumerate(o["A"]):
+        assert torch.allclose(a, torch.from_numpy(g[f"A_{i}"]), rtol=0, atol=1e-6)
+    assert (o["depth"] - torch.from_numpy(g["depth"])).abs().max().item() <= 1e-5
+
+
+def test_gt_decompose():
+    g = load_golden("gt_decompose_b2.npz")
+    comps = fr.gt_components(torch.from_numpy(g["y_masked"]))
+    assert len(comps) == 8
+    for i, c in enumerate(comps):
+        ref = torch.from_numpy(g[f"comp_{i}"])
+        assert torch.allclose(c, ref, rtol=1e-12, atol=0), i
+
+
+def test_resize_half_explicit_matches_aten():
+    g = torch.Generator().manual_seed(3)
+    for n in (2, 4, 8, 16, 32, 64, 128):
+        x = (torch.rand(2, 1, n, n, generator=g) + 0.5)
+        assert torch.equal(fr.resize_half(x), fr.resize_half_explicit(x))          # f32-valued: bit-equal
+        xd = torch.rand(2, 1, n, n, generator=g, dtype=torch.float64) + 0.5
+        a, b = fr.resize_half(xd), fr.resize_half_explicit(xd)
+        assert ((a - b).abs() / a.abs()).max().item() < 1e-15
+
+
+def test_properties():
+    g = torch.Generator().manual_seed(9)
+    d = torch.exp(0.3 * torch.randn(2, 1, 128, 128, generator=g, dtype=torch.float64))
+    comps = fr.decompose(d, 7)
+    rt = fr.recombination([torch.log(c) for c in comps])
+    assert (rt - torch.log(d)).abs().max().item() < 1e-12          # SURVEY 4.1 round trip
+    # retile bug: only the first `ratio` pages reach the map
+    pages = [torch.full((1, 1, 16, 16), float(i)) for i in range(4)]
+    m = fr.retile_pages(pages)
+    assert m.shape == (1, 1, 32, 32) and set(m.unique().tolist()) == {0.0, 1.0}
+    assert torch.equal(m[0, 0, :16, :16], pages[0][0, 0]) and torch.equal(m[0, 0, 16:, 16:], pages[1][0, 0])
