@@ -1,0 +1,414 @@
+#!/usr/bin/env python
+"""Benchmark of the MD_RDM depth-map fusion path (BASELINE.json metric: fused depth maps/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+ours      : BASELINE.json configs[1] - standalone fusion path on B200, batch 16, scales 8/16/32:
+            inputs (ordinary map + raw pair matrices: 1 f32 64x64 + 5 f64 256x64 per image)
+            resident in HBM, one step = quantize + ALS + decompose + weighted reconstruction of one
+            batch (3 kernel launches replayed from a CUDA graph).  Steps rotate over a ring of
+            resident batches larger than L2 and over a few streams (batches in flight).
+            e2e = the public host API (FusionPlan.run_pinned: decoder maps in pinned host memory
+            -> fused 128x128 log-depth maps in pinned host memory), H2D and D2H copies inside
+            the timed region, pair build fused in front.
+reference : the reference's own CPU algorithm for the same path (oracle/literal.py: the
+            loop-for-loop restatement of the reference, which is Python and cannot travel to
+            the GPU box), one image per step, all host threads.
+One JSON line on stdout (rank 0).  Weak scaling: every rank runs K steps on its own batches;
+no collective on the data path (torch.distributed is used for the barrier and the max only).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "fused_depth_maps_per_sec"
+UNIT = "maps/s"
+BATCH = 16
+SCALES = (8, 16, 32)
+
+
+# ----------------------------------------------------------------------------- workload arithmetic
+def algorithmic_bytes(scales=SCALES):
+    """Per-image stage contract bytes (SURVEY.md 8d / DESIGN.md 'Algorithmic bytes')."""
+    import math
+    E = {s: (64 * 64 if s == 8 else (s // 16) ** 2 * 256 * 64) for s in scales}
+    raw = {s: E[s] * (4 if s == 8 else 8) for s in scales}
+    Rq = {s: 4 * E[s] for s in scales}
+    bins = {s: E[s] for s in scales}
+    mp = {s: 4 * s * s for s in scales}
+    comp = {s: 8 * sum(4 ** k for k in range(1, int(math.log2(s)) + 1)) for s in scales}
+    comp_d1 = 8 * 85
+    kmax = max([3] + [int(math.log2(s)) for s in scales])
+    yhat = 4 * sum(4 ** k for k in range(kmax + 1))
+    out = {
+        "pair": sum(mp[s] + (8 * (s // 2) ** 2 if s > 8 else 0) + raw[s] for s in scales),
+        "quantize": sum(raw[s] + Rq[s] + bins[s] for s in scales),
+        "als": sum(Rq[s] + mp[s] for s in scales),
+        "decompose": sum(mp[s] for s in scales) + 512 + sum(comp[s] for s in scales) + comp_d1,
+        "reconstruct": sum(comp[s] for s in scales) + comp_d1 + yhat + 131072,
+    }
+    out["path"] = out["quantize"] + out["als"] + out["decompose"] + out["reconstruct"]
+    # the dominant kernel (als_kernel<0>) covers the quantize stage and the ALS stage's matrix read
+    out["als_iterate_kernel"] = out["quantize"] + sum(Rq[s] for s in scales)
+    out["als_select_kernel"] = sum(mp[s] for s in scales)
+    out["tail_kernel"] = out["decompose"] + out["reconstruct"]
+    return out
+
+
+def synthetic_batch(B: int, scales, seed: int):
+    """SURVEY 8d synthetic decoder outputs: x_d1 = randint(1,90) DORN counts, relative maps
+    exp(0.3 randn), weights abs(randn(K,1)) as network/RDM_Net.py:449-465 initialises them."""
+    import math
+    g = torch.Generator().manual_seed(seed)
+    x_d1 = torch.randint(1, 90, (B, 1, 8, 8), generator=g, dtype=torch.int64)
+    rel = [torch.exp(0.3 * torch.randn(B, 1, s, s, generator=g)) for s in scales]
+    K = [1, 1, 1, 1, 0, 0, 0, 0]
+    for s in scales:
+        for k in range(1, int(math.log2(s)) + 1):
+            K[k] += 1
+    weights = [torch.abs(torch.randn(k, 1, generator=g)) for k in K if k > 0]
+    return x_d1, rel, weights
+
+
+def batch_seed(rank: int, batch_idx: int) -> int:
+    """seed of the synthetic batch `batch_idx` of GPU `rank`."""
+    return 1234 + 1000 * rank + batch_idx
+
+
+def dist_env():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+def dist_max(value: float, device=None) -> float:
+    """Max over ranks (identity when not distributed)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return value
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def dist_barrier():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        dist.barrier()
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML while the GPU is busy."""
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x10: "sync_boost",
+               0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, cuda_index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            try:   # CUDA and NVML orderings differ under CUDA_VISIBLE_DEVICES: go through the UUID
+                self._h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(torch.cuda.get_device_properties(cuda_index).uuid)).encode())
+            except Exception:
+                self._h = pynvml.nvmlDeviceGetHandleByIndex(cuda_index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:  # pragma: no cover - NVML missing
+            self._nv, self.error = None, repr(e)
+
+    def _loop(self):
+        nv = self._nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
+                for bit, name in self.REASONS.items():
+                    if mask & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def __enter__(self):
+        if self._nv is not None:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join(timeout=2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": "no NVML samples"}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ----------------------------------------------------------------------------- ours
+def build_ring(dev, rank, n_plans, source):
+    """`n_plans` resident batches (each its own buffers + CUDA graph), inputs generated per SURVEY 8d."""
+    import md_rdm_b200.ops  # noqa: F401
+    from md_rdm_b200.fusion import FusionPlan
+    R = torch.ops.rdm
+    ring = []
+    for b in range(n_plans):
+        x_d1, rel, weights = synthetic_batch(BATCH, SCALES, seed=batch_seed(rank, b))
+        plan = FusionPlan(BATCH, SCALES, source, device=dev, want_bins=True)
+        rel_d = [r.to(dev) for r in rel]
+        if source == "raw":   # raw pair matrices derived from the maps with the pair-build kernels (not timed)
+            srcs = [R.pair_v1(r) if r.shape[2] == 8 else R.pair_id(r)[0] for r in rel_d]
+        else:
+            srcs = rel_d
+        plan.load_inputs(x_d1.to(dev), srcs, torch.cat([w.reshape(-1) for w in weights]).to(dev))
+        plan.host_inputs = (x_d1, rel)
+        plan.capture()
+        ring.append(plan)
+    torch.cuda.synchronize()
+    return ring
+
+
+def timed_steps(ring, streams, steps, fn):
+    """Run `steps` steps, step i on stream i % S with plan i % len(ring); device time by CUDA events
+    recorded on the current stream around fork/join of the side streams."""
+    cur = torch.cuda.current_stream()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    start.record(cur)
+    for s in streams:
+        s.wait_event(start)
+    for i in range(steps):
+        with torch.cuda.stream(streams[i % len(streams)]):
+            fn(ring[i % len(ring)])
+    for s in streams:
+        ev = torch.cuda.Event()
+        ev.record(s)
+        cur.wait_event(ev)
+    end.record(cur)
+    torch.cuda.synchronize()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    return start.elapsed_time(end), wall_ms
+
+
+def time_serial(fns, reps):
+    """Average duration of the launches issued by `fns` (one per ring entry) back to back on ONE stream."""
+    cur = torch.cuda.current_stream()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for f in fns[:4]:
+        f()
+    torch.cuda.synchronize()
+    start.record(cur)
+    for i in range(reps):
+        fns[i % len(fns)]()
+    end.record(cur)
+    torch.cuda.synchronize()
+    return start.elapsed_time(end) / reps * 1e-3   # seconds per launch
+
+
+def cpu_baseline_port(images: int):
+    """The reference's CPU algorithm (literal port) on a bounded sample of the same workload."""
+    from oracle import fusion_ref as fr
+    from oracle import literal as lit
+    books = fr.load_codebooks()
+    x_d1, rel, weights = fr.synthetic_batch(images, SCALES, seed=batch_seed(0, 0))
+    t0 = time.perf_counter()
+    lit.fusion_forward_literal(x_d1, rel, weights, books)
+    dt = time.perf_counter() - t0
+    # vectorised restatement (same arithmetic, Python loops removed): the "best-effort CPU" figure
+    x16 = fr.synthetic_batch(BATCH, SCALES, seed=batch_seed(0, 0))
+    fr.fusion_forward(*x16, books)
+    t1 = time.perf_counter()
+    nb = 5
+    for _ in range(nb):
+        fr.fusion_forward(*x16, books)
+    dv = time.perf_counter() - t1
+    return images / dt, (nb * BATCH) / dv, dt
+
+
+def run_ours(args):
+    rank, local_rank, world = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from md_rdm_b200 import _cabi
+    _cabi.load()   # fail loudly before anything is timed
+
+    ab = algorithmic_bytes()
+    n_plans = args.ring
+    ring = build_ring(dev, rank, n_plans, "raw")
+    ring_in_bytes = sum(p.h2d_bytes() for p in ring)
+    streams = [torch.cuda.Stream() for _ in range(args.streams)]
+    K, W = args.steps, args.warmup
+    replay = lambda p: p.replay()   # noqa: E731
+
+    with ClockSampler(local_rank) as clk:
+        # warm-up: at least W steps, and long enough for NVML to see the clocks under load
+        timed_steps(ring, streams, max(W, 3), replay)
+        t_end = time.perf_counter() + 0.4
+        while time.perf_counter() < t_end:
+            timed_steps(ring, streams, 200, replay)
+        dist_barrier()
+        dev_ms, wall_ms = timed_steps(ring, streams, K, replay)
+        dist_barrier()
+        dev_ms = dist_max(dev_ms, dev)
+
+        # single-stream latency of one step, and per-kernel launch durations (one stream, back to back)
+        lat_ms, _ = timed_steps(ring, streams[:1], max(K, 50), replay)
+        lat_ms /= max(K, 50)
+        reps = max(K, 100)
+        t_iter = time_serial([(lambda p=p: p.run_als_phase(1)) for p in ring], reps)
+        t_sel = time_serial([(lambda p=p: p.run_als_phase(2)) for p in ring], reps)
+        t_tail = time_serial([(lambda p=p: p.run_tail()) for p in ring], reps)
+
+        # end-to-end through the public host API: pinned host maps -> pinned host log-depth
+        e2e_ring = build_ring(dev, rank, max(args.streams, 4), "map")
+        for p in e2e_ring:
+            hb = p._host_buffers()
+            hb["x_d1"].copy_(p.host_inputs[0])
+            for s, t in zip(p.scales, p.host_inputs[1]):
+                hb["src"][s].copy_(t)
+
+        def e2e_step(p):
+            hb = p._pinned
+            p.x_d1.copy_(hb["x_d1"], non_blocking=True)
+            for s in p.scales:
+                p.src[s].copy_(hb["src"][s], non_blocking=True)
+            p.replay()
+            hb["depth"].copy_(p.depth, non_blocking=True)
+
+        e2e_streams = streams[:len(e2e_ring)]
+        timed_steps(e2e_ring, e2e_streams, max(W, 3), e2e_step)
+        dist_barrier()
+        e_dev_ms, e_wall_ms = timed_steps(e2e_ring, e2e_streams, K, e2e_step)
+        dist_barrier()
+        e_ms = dist_max(max(e_dev_ms, e_wall_ms), dev)
+    clocks = clk.summary()
+
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("als_kernel_iterate_dram_bytes_per_launch")
+    achieved = ab["als_iterate_kernel"] * BATCH / t_iter / 1e9
+
+    out = {
+        "metric": METRIC, "value": world * K * BATCH / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 (ALS) + f64 (Lloyd compare, decomposition, recombination)", "data": "synthetic",
+        "config": {
+            "workload": "BASELINE configs[1]: standalone fusion path, batch 16, scales 8/16/32; inputs = ordinary 8x8 map + raw pair "
+                        "matrices (1 f32 64x64 + 5 f64 256x64 per image) resident in HBM; quantize + ALS + decompose + weighted "
+                        "reconstruction -> bins, relative maps, y_hat, 128x128 f64 log-depth",
+            "batch": BATCH, "scales": list(SCALES), "images_per_step_per_gpu": BATCH,
+            "l2_policy": f"inputs larger than L2: ring of {n_plans} resident batches = {ring_in_bytes / 1e6:.0f} MB of inputs (L2 126 MB)",
+            "batches_in_flight": args.streams, "cuda_graph": True, "launches_per_step": 3,
+            "single_stream_ms_per_step": lat_ms,
+            "algorithmic_bytes_per_image": ab,
+            "kernel_ms": {"als_iterate": t_iter * 1e3, "als_select": t_sel * 1e3, "fuse_tail": t_tail * 1e3},
+            "kernel_gbs": {"als_iterate": achieved, "als_select": ab["als_select_kernel"] * BATCH / t_sel / 1e9,
+                           "fuse_tail": ab["tail_kernel"] * BATCH / t_tail / 1e9},
+            "path_gbs_at_value": ab["path"] * BATCH * K / (dev_ms * 1e-3) / 1e9,
+        },
+        "clocks": clocks,
+        "e2e": {"value": world * K * BATCH / (e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": e2e_ring[0].h2d_bytes(),
+                "d2h_bytes_per_step": e2e_ring[0].d2h_bytes(),
+                "api": "FusionPlan (source='map'): pinned host decoder maps -> pinned host log-depth; pair build fused in front"},
+        "gpu_launches": K * 3,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                     "kernel": "als_kernel<0> (Lloyd + ALS iterations; FP32-issue/latency bound, see DESIGN.md)",
+                     "algorithmic_bytes_per_launch": ab["als_iterate_kernel"] * BATCH, "launch_seconds": t_iter, "peak_source": peak_src},
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        lit_rate, vec_rate, dt = cpu_baseline_port(args.cpu_images)
+        out["cpu_baseline"] = {"value": lit_rate, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                               "sample": f"{args.cpu_images} images (one call) of the batch-16 workload through oracle/literal.py, "
+                                         f"the loop-for-loop restatement of the reference ({dt:.1f} s)",
+                               "vectorised_port_value": vec_rate, "host_cpus": os.cpu_count()}
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    from oracle import fusion_ref as fr
+    from oracle import literal as lit
+    torch.set_num_threads(os.cpu_count() or 1)
+    books = fr.load_codebooks()
+    K, W = args.steps, args.warmup
+    per_step = 1   # images per step: a bounded sample of the batch-16 workload
+    batches = [fr.synthetic_batch(per_step, SCALES, seed=batch_seed(0, i)) for i in range(4)]
+    for i in range(W):
+        lit.fusion_forward_literal(*batches[i % 4], books)
+    t0 = time.perf_counter()
+    for i in range(K):
+        lit.fusion_forward_literal(*batches[i % 4], books)
+    dt = time.perf_counter() - t0
+    val = K * per_step / dt
+    sample = f"{per_step} image per step of the batch-16 scales-8/16/32 workload, oracle/literal.py (loop-for-loop port of the reference)"
+    out = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
+        "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 (ALS) + f64 (Lloyd compare, decomposition, recombination)", "data": "synthetic",
+        "config": {"workload": "BASELINE configs[1] on the host CPU: decoder maps -> pair build + Lloyd + ALS + decompose + weighted "
+                               "reconstruction, reference algorithm", "batch": per_step, "scales": list(SCALES)},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--streams", type=int, default=4, help="batches in flight (CUDA streams)")
+    ap.add_argument("--ring", type=int, default=16, help="resident input batches (ring > L2)")
+    ap.add_argument("--cpu-images", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        args.steps = 20 if args.steps is None else args.steps
+        args.warmup = 3 if args.warmup is None else max(args.warmup, 1)
+        run_reference(args)
+    else:
+        args.steps = 2000 if args.steps is None else args.steps
+        args.warmup = 20 if args.warmup is None else max(args.warmup, 3)
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -125,6 +125,12 @@ typedef struct rdm_als_scale {
  * `scales` is a HOST array.  n_images must be a multiple of group. */
 int rdm_als_fused(const rdm_als_scale_t* scales, int32_t n_scales, int64_t n_images,
                   int32_t group, rdm_stream_t stream);
+/* The same, launching only the selected phases: bit 0 = iterate (Lloyd + ALS iterations, SSE
+ * record and p_1 checkpoint into ws), bit 1 = select (batch-wide arg-min, normalise, re-tile;
+ * needs ws from a previous iterate phase).  For profiling and for callers that want to overlap
+ * other work between the two launches. */
+int rdm_als_fused_phases(const rdm_als_scale_t* scales, int32_t n_scales, int64_t n_images,
+                         int32_t group, int32_t phase_mask, rdm_stream_t stream);
 /* f32 workspace elements per image for one scale (rdm_als_scale_t.ws) */
 int64_t rdm_als_ws_floats(int32_t rows, int32_t pages, int32_t limit);
 

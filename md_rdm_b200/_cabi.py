@@ -44,6 +44,7 @@ PROTOTYPES = {
     "rdm_lloyd_quantize_f32": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "rdm_lloyd_quantize_f64": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "rdm_als_fused": (c_int, [POINTER(AlsScale), c_int32, c_int64, c_int32, c_void_p]),
+    "rdm_als_fused_phases": (c_int, [POINTER(AlsScale), c_int32, c_int64, c_int32, c_int32, c_void_p]),
     "rdm_als_ws_floats": (c_int64, [c_int32, c_int32, c_int32]),
     "rdm_als_step_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_float, c_void_p, c_void_p]),
     "rdm_quick_gm": (c_int, [c_void_p, c_int32, c_int64, c_int64, c_int32, c_void_p, c_void_p]),

@@ -61,8 +61,7 @@ struct AlsSmem {
   __align__(16) float p_s[256];       // p by row index (64-row units: 4 x 64)
   __align__(16) float q_w[8][64];     // per-warp copy of q
   __align__(16) float qpart[4][64];   // q partial sums (256-row: by r'; 64-row: by unit)
-  double part_e[8];
-  double part_pp[8];
+  __align__(16) float part_pp[8];     // |p|^2 per warp
   double thr_d[kThrPad];
   double inv_d[64];                   // 1/parent (pair build fused, 256-row units)
   float thr_f[kThrPad];
@@ -234,23 +233,55 @@ __device__ __forceinline__ void load_unit(float (&R)[64], const AlsScaleDev& sc,
 }
 
 // ---------------------------------------------------------------------------------------------
+// Direct residual of one row: sum_j (p q_j - R_ij)^2 in f32 (what CP:172-173 evaluates).
+__device__ __forceinline__ float sse_row(const float (&R)[64], const float* __restrict__ q, float p) {
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+  for (int c4 = 0; c4 < 16; ++c4) {
+    float4 x = *reinterpret_cast<const float4*>(q + 4 * c4);
+    // fl(fl(p q_j) - R_ij): the outer product is rounded before the subtraction in the reference
+    // (matmul, then sub); a fused multiply-subtract would differ when the fit is nearly exact
+    float t0 = __fsub_rn(__fmul_rn(p, x.x), R[4 * c4 + 0]), t1 = __fsub_rn(__fmul_rn(p, x.y), R[4 * c4 + 1]);
+    float t2 = __fsub_rn(__fmul_rn(p, x.z), R[4 * c4 + 2]), t3 = __fsub_rn(__fmul_rn(p, x.w), R[4 * c4 + 3]);
+    a0 = fmaf(t0, t0, a0);
+    a1 = fmaf(t1, t1, a1);
+    a2 = fmaf(t2, t2, a2);
+    a3 = fmaf(t3, t3, a3);
+  }
+  return (a0 + a1) + (a2 + a3);
+}
+
+// Record (CP:53-61, CP:121-130).  Row i's residual sum_j (p_i q_j - R_ij)^2 equals
+// |R_i|^2 + p_i (p_i |q|^2 - 2 s_i) with s_i = R_i . q a by-product of the p-update; evaluated
+// in f64 its absolute error is ~1e-7 |R_i|^2 (s_i and |q|^2 are f32).  That is used when the
+// row's residual is a sizeable part of its energy; rows fitted almost exactly (below kDirectFrac
+// of |R_i|^2 - near-constant or nearly rank-1 rows, where arg-min ties could flip k*) are
+// evaluated directly with sse_row(), the third pass the reference always makes.  The decision is
+// per row, so no cross-thread dependency exists: each thread parks its row's value for iteration
+// k in shared memory E[k][thread] and the unit reduces all iterations once, after the loop.
+constexpr double kDirectFrac = 0.005;
+
 // n_iter alternating iterations; returns this thread's p_{n_iter}[row].  RECORD: write the SSE of
-// iterations 0..n_iter to rec[] and p_1 to p1_out[].
+// iterations 0..n_iter to rec[] and p_1 to p1_out[].  E: shared scratch, (n_iter+1) x (NT+1) floats.
 template <int G, bool RECORD>
-__device__ __forceinline__ float als_iterate(const float (&R)[64], AlsSmem& sm, int unit, int lt, int n_iter,
+__device__ __forceinline__ float als_iterate(const float (&R)[64], AlsSmem& sm, float* __restrict__ E, int unit, int lt, int n_iter,
                                              float* __restrict__ rec, float* __restrict__ p1_out) {
   constexpr int NW = 2 * G;
   constexpr int NT = 64 * G;
+  constexpr int ES = NT + 1;                     // odd stride: the final column sums are conflict-free
   const RowMap<G> m(lt);
   const int gw = unit * NW + m.lw;
   const int bar_id = (G == 4) ? 0 : 1 + unit;
   const int qp_base = (G == 4) ? 0 : unit;
   float* qw = sm.q_w[gw];
   float* ps = sm.p_s + unit * 64;
+  const float* pp_part = sm.part_pp + unit * NW;
 
-  // q_0 = 1: s = row sum.  |R_i|^2 in f64 for the record.
+  // q_0 = 1: s = row sum.
+  qw[m.lane] = 1.0f;
+  qw[m.lane + 32] = 1.0f;
+  __syncwarp();
   float s;
-  double r2 = 0.0;
   {
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
@@ -261,23 +292,16 @@ __device__ __forceinline__ float als_iterate(const float (&R)[64], AlsSmem& sm, 
       a3 += R[c + 3];
     }
     s = (a0 + a1) + (a2 + a3);
-    if (RECORD) {
-#pragma unroll
-      for (int c = 0; c < 64; ++c) r2 = fma((double)R[c], (double)R[c], r2);
-    }
   }
-  double Q = 64.0;                               // |q|^2
+  float Q = 64.0f;                               // |q|^2
   float invA = 1.0f / (64.0f + kLambda);         // torch.inverse of the 1x1 matrix |q|^2 + lambda
+  double r2 = 0.0, direct_below = 0.0;
   if (RECORD) {
-    double e0 = warp_sum(r2 + 64.0 - 2.0 * (double)s);   // p = q = 1 (CP:55, CP:123)
-    if (m.lane == 0) sm.part_e[gw] = e0;
-    unit_barrier(bar_id, NT);
-    if (lt == 0) {
-      double t = 0.0;
 #pragma unroll
-      for (int w = 0; w < NW; ++w) t += sm.part_e[unit * NW + w];
-      rec[0] = (float)fmax(t, 0.0);
-    }
+    for (int c = 0; c < 64; ++c) r2 = fma((double)R[c], (double)R[c], r2);
+    direct_below = kDirectFrac * r2;
+    unit_barrier(bar_id, NT);                    // the staging tile (aliased by E) is dead from here on
+    E[lt] = sse_row(R, qw, 1.0f);                // k = 0: p = q = 1 (CP:55, CP:123)
   }
   float p = 1.0f;
   for (int k = 1; k <= n_iter; ++k) {
@@ -285,51 +309,66 @@ __device__ __forceinline__ float als_iterate(const float (&R)[64], AlsSmem& sm, 
     if (!RECORD && k == n_iter) break;
     ps[m.row] = p;
     if (RECORD && k == 1) p1_out[m.row] = p;
-    double pp = (double)p * (double)p;
-    double e = 0.0;
-    if (RECORD) e = r2 + (double)p * ((double)p * Q - 2.0 * (double)s);
     unit_barrier(bar_id, NT);                    // A: p visible
     const float u = dot64(R, ps + 64 * m.rp);
+    const float pp = warp_sum(p * p);
+    if (RECORD) {
+      const double e = r2 + (double)p * ((double)p * (double)Q - 2.0 * (double)s);
+      float ef = fmaxf((float)e, 0.f);
+      if (e < direct_below) ef = sse_row(R, qw, p);   // qw still holds q_{k-1}
+      E[k * ES + lt] = ef;
+    }
     sm.qpart[qp_base + m.rp][m.i] = u;
-    pp = warp_sum(pp);
-    if (RECORD) e = warp_sum(e);
-    if (m.lane == 0) {
-      sm.part_pp[gw] = pp;
-      if (RECORD) sm.part_e[gw] = e;
-    }
-    unit_barrier(bar_id, NT);                    // B: q partials, |p|^2, SSE partials visible
-    if (RECORD && lt == 0) {
-      double t = 0.0;
-#pragma unroll
-      for (int w = 0; w < NW; ++w) t += sm.part_e[unit * NW + w];
-      rec[k] = (float)fmax(t, 0.0);
-    }
+    if (m.lane == 0) sm.part_pp[gw] = pp;
+    unit_barrier(bar_id, NT);                    // B: q partials and |p|^2 partials visible
     if (k == n_iter) break;
-    // every warp finalises q for itself (no third barrier)
-    double npp = 0.0;
-#pragma unroll
-    for (int w = 0; w < NW; ++w) npp += sm.part_pp[unit * NW + w];
-    const float invB = 1.0f / ((float)npp + kLambda);
-    float u0 = 0.f, u1 = 0.f;
-#pragma unroll
-    for (int r = 0; r < G; ++r) {
-      u0 += sm.qpart[qp_base + r][m.lane];
-      u1 += sm.qpart[qp_base + r][m.lane + 32];
+    // every warp finalises q for itself (no further barrier)
+    float npp;
+    if constexpr (G == 4) {
+      const float4 a = *reinterpret_cast<const float4*>(pp_part), b = *reinterpret_cast<const float4*>(pp_part + 4);
+      npp = ((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w));
+    } else {
+      npp = pp_part[0] + pp_part[1];
+    }
+    const float invB = 1.0f / (npp + kLambda);
+    float u0, u1;
+    if constexpr (G == 4) {
+      u0 = (sm.qpart[0][m.lane] + sm.qpart[1][m.lane]) + (sm.qpart[2][m.lane] + sm.qpart[3][m.lane]);
+      u1 = (sm.qpart[0][m.lane + 32] + sm.qpart[1][m.lane + 32]) + (sm.qpart[2][m.lane + 32] + sm.qpart[3][m.lane + 32]);
+    } else {
+      u0 = sm.qpart[unit][m.lane];
+      u1 = sm.qpart[unit][m.lane + 32];
     }
     const float q0 = u0 * invB, q1 = u1 * invB;
-    Q = warp_sum(fma((double)q0, (double)q0, (double)q1 * (double)q1));
-    invA = 1.0f / ((float)Q + kLambda);
+    __syncwarp();
     qw[m.lane] = q0;
     qw[m.lane + 32] = q1;
     __syncwarp();
     s = dot64(R, qw);
+    Q = warp_sum(fmaf(q0, q0, q1 * q1));
+    invA = 1.0f / (Q + kLambda);
+  }
+  if (RECORD) {
+    unit_barrier(bar_id, NT);
+    for (int k = lt; k <= n_iter; k += NT) {
+      const float* col = E + k * ES;
+      double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+#pragma unroll 4
+      for (int j = 0; j < NT; j += 4) {
+        t0 += (double)col[j];
+        t1 += (double)col[j + 1];
+        t2 += (double)col[j + 2];
+        t3 += (double)col[j + 3];
+      }
+      rec[k] = (float)((t0 + t1) + (t2 + t3));
+    }
   }
   return p;
 }
 
 // ---------------------------------------------------------------------------------------------
 template <int G, int PHASE>
-__device__ __forceinline__ void als_unit(const AlsParams& P, const AlsScaleDev& sc, AlsSmem& sm, float* tile,
+__device__ __forceinline__ void als_unit(const AlsParams& P, const AlsScaleDev& sc, AlsSmem& sm, float* tile, float* E,
                                          int64_t unit_idx, int unit, int lt) {
   constexpr int NT = 64 * G;
   constexpr int ROWS = 64 * G;
@@ -341,7 +380,7 @@ __device__ __forceinline__ void als_unit(const AlsParams& P, const AlsScaleDev& 
 
   if constexpr (PHASE == 0) {
     load_unit<G>(R, sc, sm, tile, unit_idx, unit, lt, true);
-    als_iterate<G, true>(R, sm, unit, lt, sc.limit, ws, ws + sc.limit + 1);
+    als_iterate<G, true>(R, sm, E, unit, lt, sc.limit, ws, ws + sc.limit + 1);
     return;
   } else {
     // ---- batch-wide rmse record and first arg-min (CP:172-173, CP:74, CP:143)
@@ -378,7 +417,7 @@ __device__ __forceinline__ void als_unit(const AlsParams& P, const AlsScaleDev& 
       p = ws[sc.limit + 1 + m.row];
     } else {   // rare: replay k* iterations from the source
       load_unit<G>(R, sc, sm, tile, unit_idx, unit, lt, false);
-      p = als_iterate<G, false>(R, sm, unit, lt, kstar, nullptr, nullptr);
+      p = als_iterate<G, false>(R, sm, nullptr, unit, lt, kstar, nullptr, nullptr);
     }
     // ---- quick_gm(p, H) with H = rows: prod_i p_i^(1/H^2)  (CP:76, CP:146, CP:244-255)
     const float pw = (float)pow((double)p, 1.0 / ((double)ROWS * (double)ROWS));
@@ -434,11 +473,14 @@ __global__ void __launch_bounds__(kAlsThreads, 2) als_kernel(const __grid_consta
   const int local_cta = (int)blockIdx.x - sc.cta_begin;
   if (sc.rows == 256) {
     const int64_t unit_idx = local_cta;
-    if (unit_idx < n_units) als_unit<4, PHASE>(P, sc, sm, tile, unit_idx, 0, tid);
+    // 256-row unit: the record scratch E aliases the staging tile (dead once the rows are in registers)
+    if (unit_idx < n_units) als_unit<4, PHASE>(P, sc, sm, tile, tile, unit_idx, 0, tid);
   } else {
     const int unit = tid >> 6;
     const int64_t unit_idx = (int64_t)local_cta * 4 + unit;
-    if (unit_idx < n_units) als_unit<1, PHASE>(P, sc, sm, tile + unit * (64 * 64), unit_idx, unit, tid & 63);
+    // 64-row units: four independent units per CTA, so E lives behind the four staging tiles
+    if (unit_idx < n_units)
+      als_unit<1, PHASE>(P, sc, sm, tile + unit * (64 * 64), tile + kTileFloats + unit * ((sc.limit + 1) * 65), unit_idx, unit, tid & 63);
   }
 }
 
@@ -470,13 +512,21 @@ __global__ void __launch_bounds__(256) als_step_kernel(const float* __restrict__
 
 using namespace rdm;
 
+extern "C" int rdm_als_fused_phases(const rdm_als_scale_t*, int32_t, int64_t, int32_t, int32_t, rdm_stream_t);
+
 extern "C" int64_t rdm_als_ws_floats(int32_t rows, int32_t pages, int32_t limit) {
   return (int64_t)pages * ((int64_t)limit + 1 + rows);
 }
 
 extern "C" int rdm_als_fused(const rdm_als_scale_t* scales, int32_t n_scales, int64_t n_images, int32_t group,
                              rdm_stream_t stream) {
+  return rdm_als_fused_phases(scales, n_scales, n_images, group, 3, stream);
+}
+
+extern "C" int rdm_als_fused_phases(const rdm_als_scale_t* scales, int32_t n_scales, int64_t n_images, int32_t group,
+                                    int32_t phase_mask, rdm_stream_t stream) {
   RDM_REQUIRE(scales, "rdm_als_fused: null scales");
+  RDM_REQUIRE(phase_mask >= 1 && phase_mask <= 3, "rdm_als_fused_phases: phase_mask must be 1, 2 or 3");
   RDM_REQUIRE(n_scales >= 1 && n_scales <= kMaxScales, "rdm_als_fused: n_scales must be 1..%d (got %d)", kMaxScales, n_scales);
   RDM_REQUIRE(n_images >= 0, "rdm_als_fused: negative n_images");
   RDM_REQUIRE(group >= 1, "rdm_als_fused: group must be >= 1");
@@ -529,18 +579,29 @@ extern "C" int rdm_als_fused(const rdm_als_scale_t* scales, int32_t n_scales, in
     ctas += (h.rows == 256) ? units : (units + 3) / 4;
     RDM_REQUIRE(ctas < (1ll << 30), "rdm_als_fused: too many work units");
   }
-  const size_t dyn = kTileFloats * sizeof(float);
+  // dynamic shared memory: staging tile, plus the record scratch E of phase 0
+  size_t dyn1 = kTileFloats * sizeof(float), dyn = dyn1;
+  for (int k = 0; k < n_scales; ++k) {
+    const size_t need = (scales[k].rows == 256) ? (size_t)(scales[k].limit + 1) * 257 * sizeof(float)
+                                                : dyn1 + (size_t)4 * (scales[k].limit + 1) * 65 * sizeof(float);
+    if (need > dyn) dyn = need;
+  }
   cudaError_t e = cudaFuncSetAttribute(als_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(als_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(als_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn1);
   if (e != cudaSuccess) {
     set_error("rdm_als_fused: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     return (int)e;
   }
-  als_kernel<0><<<(unsigned)ctas, kAlsThreads, dyn, (cudaStream_t)stream>>>(P);
-  int rc = launch_status("als_kernel<iterate>");
-  if (rc) return rc;
-  als_kernel<1><<<(unsigned)ctas, kAlsThreads, dyn, (cudaStream_t)stream>>>(P);
-  return launch_status("als_kernel<select>");
+  if (phase_mask & 1) {
+    als_kernel<0><<<(unsigned)ctas, kAlsThreads, dyn, (cudaStream_t)stream>>>(P);
+    int rc = launch_status("als_kernel<iterate>");
+    if (rc) return rc;
+  }
+  if (phase_mask & 2) {
+    als_kernel<1><<<(unsigned)ctas, kAlsThreads, dyn1, (cudaStream_t)stream>>>(P);
+    return launch_status("als_kernel<select>");
+  }
+  return 0;
 }
 
 extern "C" int rdm_als_step_f32(const float* ratings, const float* fixed, int64_t batch, int32_t rows, int32_t cols,

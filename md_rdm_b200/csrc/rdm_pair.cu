@@ -328,8 +328,9 @@ extern "C" int rdm_resize_bicubic_f64(const void* in, int32_t in_is_f64, int64_t
 template <typename T>
 static int lloyd_launch(const T* x, int64_t n, const double* thr, const double* lvl, T* values, uint8_t* bins,
                         rdm_stream_t stream, const char* name) {
-  RDM_REQUIRE(x && thr && lvl, "%s: null pointer", name);
   RDM_REQUIRE(n >= 0, "%s: negative n", name);
+  if (n == 0) return 0;
+  RDM_REQUIRE(x && thr && lvl, "%s: null pointer", name);
   RDM_REQUIRE(aligned16(x) && (!values || aligned16(values)) && (!bins || (reinterpret_cast<uintptr_t>(bins) & 3u) == 0),
               "%s: x/values must be 16-byte aligned and bins 4-byte aligned", name);
   if (n == 0) return 0;

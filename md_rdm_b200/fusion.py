@@ -121,6 +121,18 @@ class FusionPlan:
                                 c_void_p(self.depth.data_ptr()), self._a_ptrs, st), "rdm_fuse_tail")
         return self.depth
 
+    def run_als_phase(self, phase_mask: int) -> None:
+        """Only the ALS launches selected by phase_mask (1 = iterate, 2 = select): used by bench.py to
+        time the dominant kernel alone."""
+        st = c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        check(self.lib.rdm_als_fused_phases(self._descs, len(self.scales), self.N, self.group, phase_mask, st), "rdm_als_fused_phases")
+
+    def run_tail(self) -> None:
+        st = c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        check(self.lib.rdm_fuse_tail(c_void_p(self.x_d1.data_ptr()), self._rel_ptrs, self._sides, len(self.scales),
+                                     c_void_p(self.weights.data_ptr()), self.N, c_void_p(self.yhat.data_ptr()),
+                                     c_void_p(self.depth.data_ptr()), self._a_ptrs, st), "rdm_fuse_tail")
+
     def capture(self) -> None:
         """Record run() into a CUDA graph (the library does no host sync and no allocation)."""
         with torch.cuda.device(self.device):
