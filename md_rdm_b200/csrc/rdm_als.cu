@@ -75,17 +75,40 @@ __device__ __forceinline__ void unit_barrier(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-__device__ __forceinline__ float dot64(const float (&R)[64], const float* __restrict__ v) {
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+// ---- packed f32x2 arithmetic (sm_100a FFMA2): the matrix row lives in 32 register PAIRS, a
+// 64-term dot product is 32 FFMA2 in 4 independent pair-chains (8 scalar chains, depth 8).
+using u64 = unsigned long long;
+__device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) {
+  u64 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ u64 as_u64(float2 v) { return *reinterpret_cast<u64*>(&v); }
+__device__ __forceinline__ float2 as_f2(u64 v) { return *reinterpret_cast<float2*>(&v); }
+__device__ __forceinline__ float hsum4(u64 a, u64 b, u64 c, u64 d) {
+  const float2 fa = as_f2(a), fb = as_f2(b), fc = as_f2(c), fd = as_f2(d);
+  return ((fa.x + fa.y) + (fb.x + fb.y)) + ((fc.x + fc.y) + (fd.x + fd.y));
+}
+
+// dot = R_row . v[0..63] and nrm = |v|^2, both from the same 16 LDS.128 (v is a warp-wide
+// broadcast read): no shuffle reduction is needed for the norms of p and q.
+__device__ __forceinline__ void dot_norm(const float2 (&R)[32], const float* __restrict__ v, float& dot, float& nrm) {
+  u64 a0 = 0, a1 = 0, a2 = 0, a3 = 0, n0 = 0, n1 = 0, n2 = 0, n3 = 0;   // all-zero bits = (0.f, 0.f)
 #pragma unroll
-  for (int c4 = 0; c4 < 16; ++c4) {
-    float4 x = *reinterpret_cast<const float4*>(v + 4 * c4);
-    a0 = fmaf(R[4 * c4 + 0], x.x, a0);
-    a1 = fmaf(R[4 * c4 + 1], x.y, a1);
-    a2 = fmaf(R[4 * c4 + 2], x.z, a2);
-    a3 = fmaf(R[4 * c4 + 3], x.w, a3);
+  for (int c4 = 0; c4 < 16; c4 += 2) {
+    const ulonglong2 x = *reinterpret_cast<const ulonglong2*>(v + 4 * c4);
+    const ulonglong2 y = *reinterpret_cast<const ulonglong2*>(v + 4 * c4 + 4);
+    a0 = ffma2(as_u64(R[2 * c4 + 0]), x.x, a0);
+    a1 = ffma2(as_u64(R[2 * c4 + 1]), x.y, a1);
+    a2 = ffma2(as_u64(R[2 * c4 + 2]), y.x, a2);
+    a3 = ffma2(as_u64(R[2 * c4 + 3]), y.y, a3);
+    n0 = ffma2(x.x, x.x, n0);
+    n1 = ffma2(x.y, x.y, n1);
+    n2 = ffma2(y.x, y.x, n2);
+    n3 = ffma2(y.y, y.y, n3);
   }
-  return (a0 + a1) + (a2 + a3);
+  dot = hsum4(a0, a1, a2, a3);
+  nrm = hsum4(n0, n1, n2, n3);
 }
 
 // Thread <-> row mapping of a unit.  lt = thread index inside the unit (0 .. 64G-1).
@@ -104,7 +127,7 @@ struct RowMap {
 // ---------------------------------------------------------------------------------------------
 // Load (and, for RAW_* / MAP kinds, build + quantise) the unit's matrix row into registers.
 template <int G>
-__device__ __forceinline__ void load_unit(float (&R)[64], const AlsScaleDev& sc, AlsSmem& sm, float* tile,
+__device__ __forceinline__ void load_unit(float2 (&R)[32], const AlsScaleDev& sc, AlsSmem& sm, float* tile,
                                           int64_t unit_idx, int unit, int lt, bool emit) {
   constexpr int NT = 64 * G;
   constexpr int ROWS = 64 * G;
@@ -138,7 +161,7 @@ __device__ __forceinline__ void load_unit(float (&R)[64], const AlsScaleDev& sc,
         const bool win = (unsigned)((c >> 3) - r0) < 3u && (unsigned)((c & 7) - c0) < 3u;
         int b = bd;
         if (win) b = lloyd_bin<double>(__dmul_rn(d, sm.inv_d[c]), sm.thr_d, sorted);
-        R[c] = sm.lvl_f[b];
+        if (c & 1) R[c >> 1].y = sm.lvl_f[b]; else R[c >> 1].x = sm.lvl_f[b];
         pk |= (uint32_t)b << (8 * (c & 3));
         if ((c & 3) == 3) {
           if (bins) *reinterpret_cast<uint32_t*>(bins + mat_off + m.row * 64 + (c - 3)) = pk;
@@ -154,7 +177,7 @@ __device__ __forceinline__ void load_unit(float (&R)[64], const AlsScaleDev& sc,
 #pragma unroll
       for (int c = 0; c < 64; ++c) {
         int b = lloyd_bin<float>(__fmul_rn(dv, sm.inv_f[unit][c]), sm.thr_f, sorted);   // RN:252
-        R[c] = sm.lvl_f[b];
+        if (c & 1) R[c >> 1].y = sm.lvl_f[b]; else R[c >> 1].x = sm.lvl_f[b];
         pk |= (uint32_t)b << (8 * (c & 3));
         if ((c & 3) == 3) {
           if (bins) *reinterpret_cast<uint32_t*>(bins + mat_off + m.row * 64 + (c - 3)) = pk;
@@ -166,7 +189,7 @@ __device__ __forceinline__ void load_unit(float (&R)[64], const AlsScaleDev& sc,
 #pragma unroll
       for (int c4 = 0; c4 < 16; ++c4)
         *reinterpret_cast<float4*>(values + mat_off + m.row * 64 + 4 * c4) =
-            make_float4(R[4 * c4], R[4 * c4 + 1], R[4 * c4 + 2], R[4 * c4 + 3]);
+            make_float4(R[2 * c4].x, R[2 * c4].y, R[2 * c4 + 1].x, R[2 * c4 + 1].y);
     }
     return;
   }
@@ -224,25 +247,23 @@ __device__ __forceinline__ void load_unit(float (&R)[64], const AlsScaleDev& sc,
 #pragma unroll
     for (int c4 = 0; c4 < 16; ++c4) {
       float4 x = t4[c4 ^ swz];
-      R[4 * c4 + 0] = x.x;
-      R[4 * c4 + 1] = x.y;
-      R[4 * c4 + 2] = x.z;
-      R[4 * c4 + 3] = x.w;
+      R[2 * c4] = make_float2(x.x, x.y);
+      R[2 * c4 + 1] = make_float2(x.z, x.w);
     }
   }
 }
 
 // ---------------------------------------------------------------------------------------------
 // Direct residual of one row: sum_j (p q_j - R_ij)^2 in f32 (what CP:172-173 evaluates).
-__device__ __forceinline__ float sse_row(const float (&R)[64], const float* __restrict__ q, float p) {
+__device__ __forceinline__ float sse_row(const float2 (&R)[32], const float* __restrict__ q, float p) {
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
   for (int c4 = 0; c4 < 16; ++c4) {
     float4 x = *reinterpret_cast<const float4*>(q + 4 * c4);
     // fl(fl(p q_j) - R_ij): the outer product is rounded before the subtraction in the reference
     // (matmul, then sub); a fused multiply-subtract would differ when the fit is nearly exact
-    float t0 = __fsub_rn(__fmul_rn(p, x.x), R[4 * c4 + 0]), t1 = __fsub_rn(__fmul_rn(p, x.y), R[4 * c4 + 1]);
-    float t2 = __fsub_rn(__fmul_rn(p, x.z), R[4 * c4 + 2]), t3 = __fsub_rn(__fmul_rn(p, x.w), R[4 * c4 + 3]);
+    float t0 = __fsub_rn(__fmul_rn(p, x.x), R[2 * c4].x), t1 = __fsub_rn(__fmul_rn(p, x.y), R[2 * c4].y);
+    float t2 = __fsub_rn(__fmul_rn(p, x.z), R[2 * c4 + 1].x), t3 = __fsub_rn(__fmul_rn(p, x.w), R[2 * c4 + 1].y);
     a0 = fmaf(t0, t0, a0);
     a1 = fmaf(t1, t1, a1);
     a2 = fmaf(t2, t2, a2);
@@ -264,7 +285,7 @@ constexpr double kDirectFrac = 0.005;
 // n_iter alternating iterations; returns this thread's p_{n_iter}[row].  RECORD: write the SSE of
 // iterations 0..n_iter to rec[] and p_1 to p1_out[].  E: shared scratch, (n_iter+1) x (NT+1) floats.
 template <int G, bool RECORD>
-__device__ __forceinline__ float als_iterate(const float (&R)[64], AlsSmem& sm, float* __restrict__ E, int unit, int lt, int n_iter,
+__device__ __forceinline__ float als_iterate(const float2 (&R)[32], AlsSmem& sm, float* __restrict__ E, int unit, int lt, int n_iter,
                                              float* __restrict__ rec, float* __restrict__ p1_out) {
   constexpr int NW = 2 * G;
   constexpr int NT = 64 * G;
@@ -275,30 +296,18 @@ __device__ __forceinline__ float als_iterate(const float (&R)[64], AlsSmem& sm, 
   const int qp_base = (G == 4) ? 0 : unit;
   float* qw = sm.q_w[gw];
   float* ps = sm.p_s + unit * 64;
-  const float* pp_part = sm.part_pp + unit * NW;
 
-  // q_0 = 1: s = row sum.
+  // q_0 = 1: s = row sum, |q|^2 = 64.
   qw[m.lane] = 1.0f;
   qw[m.lane + 32] = 1.0f;
   __syncwarp();
-  float s;
-  {
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-    for (int c = 0; c < 64; c += 4) {
-      a0 += R[c];
-      a1 += R[c + 1];
-      a2 += R[c + 2];
-      a3 += R[c + 3];
-    }
-    s = (a0 + a1) + (a2 + a3);
-  }
-  float Q = 64.0f;                               // |q|^2
-  float invA = 1.0f / (64.0f + kLambda);         // torch.inverse of the 1x1 matrix |q|^2 + lambda
+  float s, Q;
+  dot_norm(R, qw, s, Q);
+  float invA = 1.0f / (Q + kLambda);             // torch.inverse of the 1x1 matrix |q|^2 + lambda
   double r2 = 0.0, direct_below = 0.0;
   if (RECORD) {
 #pragma unroll
-    for (int c = 0; c < 64; ++c) r2 = fma((double)R[c], (double)R[c], r2);
+    for (int c = 0; c < 32; ++c) r2 = fma((double)R[c].y, (double)R[c].y, fma((double)R[c].x, (double)R[c].x, r2));
     direct_below = kDirectFrac * r2;
     unit_barrier(bar_id, NT);                    // the staging tile (aliased by E) is dead from here on
     E[lt] = sse_row(R, qw, 1.0f);                // k = 0: p = q = 1 (CP:55, CP:123)
@@ -310,42 +319,40 @@ __device__ __forceinline__ float als_iterate(const float (&R)[64], AlsSmem& sm, 
     ps[m.row] = p;
     if (RECORD && k == 1) p1_out[m.row] = p;
     unit_barrier(bar_id, NT);                    // A: p visible
-    const float u = dot64(R, ps + 64 * m.rp);
-    const float pp = warp_sum(p * p);
+    float u, pseg;
+    dot_norm(R, ps + 64 * m.rp, u, pseg);        // q partial and |p segment|^2 from the same loads
     if (RECORD) {
       const double e = r2 + (double)p * ((double)p * (double)Q - 2.0 * (double)s);
       float ef = fmaxf((float)e, 0.f);
       if (e < direct_below) ef = sse_row(R, qw, p);   // qw still holds q_{k-1}
       E[k * ES + lt] = ef;
     }
-    sm.qpart[qp_base + m.rp][m.i] = u;
-    if (m.lane == 0) sm.part_pp[gw] = pp;
-    unit_barrier(bar_id, NT);                    // B: q partials and |p|^2 partials visible
+    float npp = pseg;
+    if constexpr (G == 4) {
+      sm.qpart[m.rp][m.i] = u;
+      if (m.lw < 4 && m.lane == 0) sm.part_pp[m.rp] = pseg;
+    } else {
+      sm.qpart[qp_base][m.i] = u;
+    }
+    unit_barrier(bar_id, NT);                    // B: q partials (and |p|^2 segments) visible
     if (k == n_iter) break;
     // every warp finalises q for itself (no further barrier)
-    float npp;
-    if constexpr (G == 4) {
-      const float4 a = *reinterpret_cast<const float4*>(pp_part), b = *reinterpret_cast<const float4*>(pp_part + 4);
-      npp = ((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w));
-    } else {
-      npp = pp_part[0] + pp_part[1];
-    }
-    const float invB = 1.0f / (npp + kLambda);
     float u0, u1;
     if constexpr (G == 4) {
+      const float4 a = *reinterpret_cast<const float4*>(sm.part_pp);
+      npp = (a.x + a.y) + (a.z + a.w);
       u0 = (sm.qpart[0][m.lane] + sm.qpart[1][m.lane]) + (sm.qpart[2][m.lane] + sm.qpart[3][m.lane]);
       u1 = (sm.qpart[0][m.lane + 32] + sm.qpart[1][m.lane + 32]) + (sm.qpart[2][m.lane + 32] + sm.qpart[3][m.lane + 32]);
     } else {
-      u0 = sm.qpart[unit][m.lane];
-      u1 = sm.qpart[unit][m.lane + 32];
+      u0 = sm.qpart[qp_base][m.lane];
+      u1 = sm.qpart[qp_base][m.lane + 32];
     }
-    const float q0 = u0 * invB, q1 = u1 * invB;
+    const float invB = 1.0f / (npp + kLambda);
     __syncwarp();
-    qw[m.lane] = q0;
-    qw[m.lane + 32] = q1;
+    qw[m.lane] = u0 * invB;
+    qw[m.lane + 32] = u1 * invB;
     __syncwarp();
-    s = dot64(R, qw);
-    Q = warp_sum(fmaf(q0, q0, q1 * q1));
+    dot_norm(R, qw, s, Q);
     invA = 1.0f / (Q + kLambda);
   }
   if (RECORD) {
@@ -376,7 +383,7 @@ __device__ __forceinline__ void als_unit(const AlsParams& P, const AlsScaleDev& 
   const int bar_id = (G == 4) ? 0 : 1 + unit;
   const int ws_stride = sc.limit + 1 + ROWS;
   float* ws = sc.ws + unit_idx * ws_stride;
-  float R[64];
+  float2 R[32];
 
   if constexpr (PHASE == 0) {
     load_unit<G>(R, sc, sm, tile, unit_idx, unit, lt, true);

@@ -227,7 +227,14 @@ def test_group_argmin_is_batch_wide(dev, books):
     for gi in range(2):
         ref, inter = fr.relative_decoder_tail(x[2 * gi:2 * gi + 2], books, want_intermediates=True)
         assert _rel_err(m[2 * gi:2 * gi + 2].cpu(), ref) < REL_MAP
-        assert np.allclose(rec[gi, 0].cpu().numpy(), np.array(inter[0]["record"], dtype=np.float32), rtol=1e-5, atol=1e-7)
+        # Constant maps leave a residual of ~8e-4 on values of 1: there one f32 ulp of |p|^2 (summation
+        # order inside the reference's own matmul) moves the rmse by ~1e-3 relative, so only rec[0] == 0
+        # exactly (hence k* = 0) and rough agreement are meaningful for that group.
+        rtol = 1e-5 if gi == 0 else 5e-3
+        ours_rec = rec[gi, 0].cpu().numpy()
+        assert np.allclose(ours_rec, np.array(inter[0]["record"], dtype=np.float32), rtol=rtol, atol=1e-7)
+        if gi == 1:
+            assert ours_rec[0] == 0.0 and (ours_rec[1:] > 0).all()
 
 
 # ============================================================================ stage 4
