@@ -11,7 +11,8 @@ import os
 from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_uint8, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librdm_b200.so")
+# RDM_B200_LIB selects an experimental build of the same ABI (tools/als_variants.py); default = the product
+LIB_PATH = os.environ.get("RDM_B200_LIB") or os.path.join(_HERE, "librdm_b200.so")
 ABI_VERSION = 1
 
 # rdm_als_scale_t.src_kind

@@ -44,17 +44,18 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, defines=(), out: str = LIB) -> str:
+    """`defines` / `out` build an experimental variant (tools/als_variants.py); the product is the default."""
+    if not force and out == LIB and not needs_build():
         return LIB
     nvcc = _nvcc()
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build", os.path.basename(out).replace(".so", ""))
     os.makedirs(objdir, exist_ok=True)
     objs = []
     procs = []
     for src in SOURCES:
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-I", INCLUDE, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-I", INCLUDE, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), flush=True)
@@ -62,18 +63,18 @@ def build(force: bool = False, verbose: bool = False) -> str:
         objs.append(obj)
     failed = False
     for src, p in procs:
-        out, _ = p.communicate()
+        log, _ = p.communicate()
         if p.returncode != 0 or verbose:
-            print(f"--- {src}\n{out}", flush=True)
+            print(f"--- {src}\n{log}", flush=True)
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed (see output above)")
-    tmp = LIB + ".tmp"
+    tmp = out + ".tmp"
     # static cudart: the library is self-contained and shares the primary context (and therefore
     # torch's streams) with whatever runtime the host process already uses
     subprocess.check_call([nvcc, "-shared", "-o", tmp, *objs, "-cudart", "static"])
-    os.replace(tmp, LIB)
-    return LIB
+    os.replace(tmp, out)
+    return out
 
 
 if __name__ == "__main__":

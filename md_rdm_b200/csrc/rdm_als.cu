@@ -3,25 +3,30 @@
 // CP:218-238, CP:244-255), optionally with the pair build in front (RN:244-280) so the pair
 // matrix never exists in HBM.
 //
-// Work unit = one pair matrix = one (image, page).  rows = 256 (16x16 page against its 8x8
-// parent, 100 iterations) or rows = 64 (the 8x8 map against itself, 30 iterations); 64 columns
-// either way.  A unit is owned by rows threads, ONE MATRIX ROW PER THREAD HELD IN 64 REGISTERS,
-// so the 2*limit GEMVs of the alternating updates never touch shared memory for the matrix:
+// Work unit = one pair matrix = one (image, page): rows x 64 with rows = 256 (16x16 page against
+// its 8x8 parent, 100 iterations) or rows = 64 (the 8x8 map against itself, 30 iterations).  A
+// unit is owned by `rows` threads and the whole matrix lives in REGISTERS for all iterations:
+// every thread holds a 4-row x 16-column tile (64 values as 32 FFMA2 register pairs).  The four
+// lanes cb = 0..3 of a lane group share the same four rows and split the 64 columns.
 //   p-update  p_i = (sum_c R[i][c] q_c) / (|q|^2 + lambda)              CP:186-192
 //   q-update  q_i = (sum_m Rflat[i*rows + m] p_m) / (|p|^2 + lambda)    CP:64 / CP:133: the
 //             reference passes R.view(B,W,H) - a reshape, not a transpose - so "row i" of the
-//             second operand is rows G*i .. G*i+G-1 of R laid end to end (G = rows/64).
-// Threads are mapped to rows so that a warp's 32 rows share r' = row % G; the p segment a
-// thread needs (p[64 r' .. 64 r'+63]) is then a warp-wide broadcast read.
-// Per iteration: 2 named barriers, 2 register GEMVs, 1-2 f64 warp reductions.
+//             second operand is rows G*i .. G*i+G-1 of R laid end to end (G = rows/64), i.e.
+//             q_i = sum_{r'<G} sum_c R[G i + r'][c] p[64 r' + c].
+// A warp's 32 rows share r' = row % G, so both GEMVs read a 16-float operand slice per lane
+// (4 LDS.128, four distinct addresses per warp), do 64 FMAs (32 FFMA2), and finish with a 2-level
+// reduce-scatter over the lane group (3 SHFL) that leaves each lane with the full sum of ONE
+// row.  The operand norms |q|^2 and |p segment|^2 come from the same loaded slice (8 FFMA2 + 2
+// SHFL levels).  Measured on B200 the earlier row-per-thread layout (16 broadcast LDS.128 per
+// GEMV) was bound by shared-memory operand delivery, not by FMA issue (profiles/README.md).
+// Per iteration: 2 named barriers.
 //
-// rmse record (CP:53-61, CP:121-130): sum_j (p_i q_j - R_ij)^2 = |R_i|^2 + p_i (p_i |q|^2 - 2 s_i)
-// with s_i = R_i . q already known from the p-update, evaluated in f64 - O(1) per row instead of a
-// third pass over the matrix.  Per-unit SSE goes to the workspace; the arg-min is over the mean
-// of the whole reference batch ("group", CP:172-173), so phase 1 (second launch) sums the
-// group's records, picks the first minimum (CP:74, CP:143) and emits p_k*.  p_1 is checkpointed
-// by phase 0 (k* is 0 or 1 on every realistic input); for k* >= 2 phase 1 replays
-// k* iterations from the source.  No kernel waits on another: two plain launches.
+// rmse record (CP:53-61, CP:121-130): see the comment above kDirectFrac.  Per-unit SSE goes to
+// the workspace; the arg-min is over the mean of the whole reference batch ("group",
+// CP:172-173), so phase 1 (second launch) sums the group's records, picks the first minimum
+// (CP:74, CP:143) and emits p_k*.  p_1 is checkpointed by phase 0 (k* is 0 or 1 on every
+// realistic input); for k* >= 2 phase 1 replays k* iterations from the source.
+// No kernel waits on another: two plain launches.
 //
 // Bound: per unit 2*limit*rows*64 FMA against rows*64*(4..8) input bytes = 25..100 FMA/byte:
 // FP32-issue / dependency-latency bound, not HBM bound (DESIGN.md "K3").
@@ -61,22 +66,38 @@ struct AlsSmem {
   __align__(16) float p_s[256];       // p by row index (64-row units: 4 x 64)
   __align__(16) float q_w[8][64];     // per-warp copy of q
   __align__(16) float qpart[4][64];   // q partial sums (256-row: by r'; 64-row: by unit)
-  __align__(16) float part_pp[8];     // |p|^2 per warp
+  __align__(16) float part_pp[8];     // |p segment|^2 by r'
   double thr_d[kThrPad];
   double inv_d[64];                   // 1/parent (pair build fused, 256-row units)
   float thr_f[kThrPad];
   float lvl_f[kLvl + 3];
   float inv_f[4][64];                 // 1/d (pair build fused, 64-row units)
   float rm[256];                      // group rmse record (phase 1)
+  int cell_s[kThr];
   int sorted;
+  LloydLut lut;                       // bin lookup table in the dtype this CTA compares in
+};
+
+// Bin look-up context held in registers for the duration of a load (USE_LUT is hoisted out of
+// the element loops so that the look-ups are straight-line code and interleave).
+template <typename T, bool USE_LUT>
+struct BinCtx {
+  const T* tab;
+  const uint8_t* lut;
+  int base, ncell, sorted;
+  T thr0;
+  __device__ __forceinline__ BinCtx(const AlsSmem& sm, const T* t) : tab(t), lut(sm.lut.lut), base(sm.lut.base), ncell(sm.lut.ncell), sorted(sm.sorted), thr0(t[0]) {}
+  __device__ __forceinline__ int operator()(T x) const {
+    if constexpr (USE_LUT) return lloyd_bin_lut<T>(x, tab, lut, base, ncell, thr0);
+    else return lloyd_bin<T>(x, tab, sorted);
+  }
 };
 
 __device__ __forceinline__ void unit_barrier(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// ---- packed f32x2 arithmetic (sm_100a FFMA2): the matrix row lives in 32 register PAIRS, a
-// 64-term dot product is 32 FFMA2 in 4 independent pair-chains (8 scalar chains, depth 8).
+// ---- packed f32x2 arithmetic (sm_100a FFMA2)
 using u64 = unsigned long long;
 __device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) {
   u64 d;
@@ -85,129 +106,189 @@ __device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) {
 }
 __device__ __forceinline__ u64 as_u64(float2 v) { return *reinterpret_cast<u64*>(&v); }
 __device__ __forceinline__ float2 as_f2(u64 v) { return *reinterpret_cast<float2*>(&v); }
-__device__ __forceinline__ float hsum4(u64 a, u64 b, u64 c, u64 d) {
-  const float2 fa = as_f2(a), fb = as_f2(b), fc = as_f2(c), fd = as_f2(d);
-  return ((fa.x + fa.y) + (fb.x + fb.y)) + ((fc.x + fc.y) + (fd.x + fd.y));
+__device__ __forceinline__ float hsum2(u64 a, u64 b) {
+  const float2 fa = as_f2(a), fb = as_f2(b);
+  return (fa.x + fa.y) + (fb.x + fb.y);
 }
 
-// dot = R_row . v[0..63] and nrm = |v|^2, both from the same 16 LDS.128 (v is a warp-wide
-// broadcast read): no shuffle reduction is needed for the norms of p and q.
-__device__ __forceinline__ void dot_norm(const float2 (&R)[32], const float* __restrict__ v, float& dot, float& nrm) {
-  u64 a0 = 0, a1 = 0, a2 = 0, a3 = 0, n0 = 0, n1 = 0, n2 = 0, n3 = 0;   // all-zero bits = (0.f, 0.f)
-#pragma unroll
-  for (int c4 = 0; c4 < 16; c4 += 2) {
-    const ulonglong2 x = *reinterpret_cast<const ulonglong2*>(v + 4 * c4);
-    const ulonglong2 y = *reinterpret_cast<const ulonglong2*>(v + 4 * c4 + 4);
-    a0 = ffma2(as_u64(R[2 * c4 + 0]), x.x, a0);
-    a1 = ffma2(as_u64(R[2 * c4 + 1]), x.y, a1);
-    a2 = ffma2(as_u64(R[2 * c4 + 2]), y.x, a2);
-    a3 = ffma2(as_u64(R[2 * c4 + 3]), y.y, a3);
-    n0 = ffma2(x.x, x.x, n0);
-    n1 = ffma2(x.y, x.y, n1);
-    n2 = ffma2(y.x, y.x, n2);
-    n3 = ffma2(y.y, y.y, n3);
-  }
-  dot = hsum4(a0, a1, a2, a3);
-  nrm = hsum4(n0, n1, n2, n3);
-}
-
-// Thread <-> row mapping of a unit.  lt = thread index inside the unit (0 .. 64G-1).
+// Thread <-> tile mapping of a unit.  lt = thread index inside the unit (0 .. 64G-1).
+// Rows of the tile: row(j) = G (ib + j) + rp, j = 0..3; columns 16 cb .. 16 cb + 15.
+// After a reduce-scatter, lane cb of the group owns row(cb).
 template <int G>
-struct RowMap {
-  int lane, lw, rp, i, row;
-  __device__ __forceinline__ explicit RowMap(int lt) {
+struct TileMap {
+  int lane, lw, cb, rp, ib, row_own;
+  __device__ __forceinline__ explicit TileMap(int lt) {
     lane = lt & 31;
     lw = lt >> 5;
+    cb = lane & 3;
     rp = lw % G;
-    i = (lw / G) * 32 + lane;
-    row = G * i + rp;
+    ib = (lw / G) * 32 + 4 * (lane >> 2);
+    row_own = G * (ib + cb) + rp;
   }
+  __device__ __forceinline__ int row(int j) const { return G * (ib + j) + rp; }
 };
 
+// Sum v[j] over the 4 lanes of a lane group; lane cb receives the total of v[cb] (3 shuffles).
+template <typename T>
+__device__ __forceinline__ T reduce_scatter4(T v0, T v1, T v2, T v3, int cb) {
+  const bool hi = cb & 2, odd = cb & 1;
+  const T s0 = hi ? v0 : v2, s1 = hi ? v1 : v3;
+  const T k0 = hi ? v2 : v0, k1 = hi ? v3 : v1;
+  const T r0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 2);
+  const T r1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 2);
+  const T snd = odd ? r0 : r1, kp = odd ? r1 : r0;
+  return kp + __shfl_xor_sync(0xffffffffu, snd, 1);
+}
+template <typename T>
+__device__ __forceinline__ T group_sum4(T v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  return v;
+}
+
+// Partial GEMV of the tile with the lane's 16-float operand slice `op` (4 LDS.128) and the
+// squared norm of the slice: own = full dot of the row this lane owns, nrm = |whole operand|^2.
+__device__ __forceinline__ void tile_dot(const float2 (&R)[4][8], const float* __restrict__ op, int cb, float& own, float& nrm) {
+  ulonglong2 x[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) x[k] = *reinterpret_cast<const ulonglong2*>(op + 4 * k);
+  u64 a[4][2];
+  u64 n0 = 0, n1 = 0;   // all-zero bits = (0.f, 0.f)
+#pragma unroll
+  for (int j = 0; j < 4; ++j) a[j][0] = a[j][1] = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      a[j][0] = ffma2(as_u64(R[j][2 * k]), x[k].x, a[j][0]);
+      a[j][1] = ffma2(as_u64(R[j][2 * k + 1]), x[k].y, a[j][1]);
+    }
+    n0 = ffma2(x[k].x, x[k].x, n0);
+    n1 = ffma2(x[k].y, x[k].y, n1);
+  }
+  own = reduce_scatter4(hsum2(a[0][0], a[0][1]), hsum2(a[1][0], a[1][1]), hsum2(a[2][0], a[2][1]), hsum2(a[3][0], a[3][1]), cb);
+  nrm = group_sum4(hsum2(n0, n1));
+}
+
+// Direct residual of the tile rows: sum_c (p_j q_c - R[j][c])^2 in f32 (what CP:172-173
+// evaluates); lane cb receives the row it owns.
+__device__ __forceinline__ float tile_sse(const float2 (&R)[4][8], const float* __restrict__ qop, const float (&pj)[4], int cb) {
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float4 x = *reinterpret_cast<const float4*>(qop + 4 * k);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      // fl(fl(p q_c) - R): the outer product is rounded before the subtraction in the reference
+      // (matmul, then sub); a fused multiply-subtract would differ when the fit is nearly exact
+      const float t0 = __fsub_rn(__fmul_rn(pj[j], x.x), R[j][2 * k].x), t1 = __fsub_rn(__fmul_rn(pj[j], x.y), R[j][2 * k].y);
+      const float t2 = __fsub_rn(__fmul_rn(pj[j], x.z), R[j][2 * k + 1].x), t3 = __fsub_rn(__fmul_rn(pj[j], x.w), R[j][2 * k + 1].y);
+      acc[j] = fmaf(t3, t3, fmaf(t2, t2, fmaf(t1, t1, fmaf(t0, t0, acc[j]))));
+    }
+  }
+  return reduce_scatter4(acc[0], acc[1], acc[2], acc[3], cb);
+}
+
 // ---------------------------------------------------------------------------------------------
-// Load (and, for RAW_* / MAP kinds, build + quantise) the unit's matrix row into registers.
-template <int G>
-__device__ __forceinline__ void load_unit(float2 (&R)[32], const AlsScaleDev& sc, AlsSmem& sm, float* tile,
-                                          int64_t unit_idx, int unit, int lt, bool emit) {
+// Load (and, for RAW_* / MAP kinds, build + quantise) the unit's matrix into register tiles.
+template <int G, bool USE_LUT>
+__device__ __forceinline__ void load_unit_impl(float2 (&R)[4][8], const AlsScaleDev& sc, AlsSmem& sm, float* tile,
+                                               int64_t unit_idx, int unit, int lt, bool emit) {
   constexpr int NT = 64 * G;
   constexpr int ROWS = 64 * G;
-  const RowMap<G> m(lt);
+  const TileMap<G> m(lt);
   const int bar_id = (G == 4) ? 0 : 1 + unit;
-  const int sorted = sm.sorted;
+  const BinCtx<double, USE_LUT> bin_d(sm, sm.thr_d);
+  const BinCtx<float, USE_LUT> bin_f(sm, sm.thr_f);
   uint8_t* bins = emit ? sc.bins : nullptr;
   float* values = emit ? sc.values : nullptr;
   const int64_t mat_off = unit_idx * (int64_t)(ROWS * kCols);
 
   if (sc.kind == RDM_SRC_MAP_F32) {
     // ---- pair build fused: nothing but the decoder map is read from HBM
+    const float* map;
+    int pi = 0, pj = 0, side = 8;
     if constexpr (G == 4) {
-      const int side = sc.side, ratio = side >> 4;
+      side = sc.side;
+      const int ratio = side >> 4;
       const int64_t img = unit_idx / sc.pages;
       const int pg = (int)(unit_idx - img * sc.pages);
-      const int pi = pg / ratio, pj = pg - pi * ratio;
-      const float* map = reinterpret_cast<const float*>(sc.src) + img * (int64_t)side * side;
+      pi = pg / ratio;
+      pj = pg - pi * ratio;
+      map = reinterpret_cast<const float*>(sc.src) + img * (int64_t)side * side;
       if (lt < 64) {
         int y = 8 * pi + (lt >> 3), x = 8 * pj + (lt & 7);
         double v = bicubic_half_at([&](int r, int c) { return (double)map[r * side + c]; }, y, x, side);
         sm.inv_d[lt] = 1.0 / v;   // torch.pow(area,-1): IEEE reciprocal
       }
-      const double d = (double)map[(16 * pi + (m.row >> 4)) * side + 16 * pj + (m.row & 15)];
-      unit_barrier(bar_id, NT);
-      const int r0 = min((m.row >> 4) >> 1, 5), c0 = min((m.row & 15) >> 1, 5);
-      const int bd = lloyd_bin<double>(d, sm.thr_d, sorted);   // the 55 columns outside the window
-      uint32_t pk = 0;
-#pragma unroll
-      for (int c = 0; c < 64; ++c) {
-        const bool win = (unsigned)((c >> 3) - r0) < 3u && (unsigned)((c & 7) - c0) < 3u;
-        int b = bd;
-        if (win) b = lloyd_bin<double>(__dmul_rn(d, sm.inv_d[c]), sm.thr_d, sorted);
-        if (c & 1) R[c >> 1].y = sm.lvl_f[b]; else R[c >> 1].x = sm.lvl_f[b];
-        pk |= (uint32_t)b << (8 * (c & 3));
-        if ((c & 3) == 3) {
-          if (bins) *reinterpret_cast<uint32_t*>(bins + mat_off + m.row * 64 + (c - 3)) = pk;
-          pk = 0;
-        }
-      }
     } else {
-      const float* map = reinterpret_cast<const float*>(sc.src) + unit_idx * 64;
-      const float dv = map[lt];
-      sm.inv_f[unit][lt] = __frcp_rn(dv);   // RN:248
-      unit_barrier(bar_id, NT);
-      uint32_t pk = 0;
+      map = reinterpret_cast<const float*>(sc.src) + unit_idx * 64;
+      sm.inv_f[unit][lt] = __frcp_rn(map[lt]);   // RN:248
+    }
+    unit_barrier(bar_id, NT);
 #pragma unroll
-      for (int c = 0; c < 64; ++c) {
-        int b = lloyd_bin<float>(__fmul_rn(dv, sm.inv_f[unit][c]), sm.thr_f, sorted);   // RN:252
-        if (c & 1) R[c >> 1].y = sm.lvl_f[b]; else R[c >> 1].x = sm.lvl_f[b];
-        pk |= (uint32_t)b << (8 * (c & 3));
-        if ((c & 3) == 3) {
-          if (bins) *reinterpret_cast<uint32_t*>(bins + mat_off + m.row * 64 + (c - 3)) = pk;
-          pk = 0;
+    for (int j = 0; j < 4; ++j) {
+      const int row = m.row(j);
+      uint32_t pk[4] = {0u, 0u, 0u, 0u};
+      if constexpr (G == 4) {
+        const double d = (double)map[(16 * pi + (row >> 4)) * side + 16 * pj + (row & 15)];
+        const int r0 = min((row >> 4) >> 1, 5), c0 = min((row & 15) >> 1, 5);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const int c = 16 * m.cb + e;
+          const bool win = (unsigned)((c >> 3) - r0) < 3u && (unsigned)((c & 7) - c0) < 3u;
+          const int b = bin_d(win ? __dmul_rn(d, sm.inv_d[c]) : d);   // 55 of 64 columns hold d itself
+          const float v = sm.lvl_f[b];
+          if (e & 1) R[j][e >> 1].y = v; else R[j][e >> 1].x = v;
+          pk[e >> 2] |= (uint32_t)b << (8 * (e & 3));
+        }
+      } else {
+        const float dv = map[row];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const int c = 16 * m.cb + e;
+          const int b = bin_f(__fmul_rn(dv, sm.inv_f[unit][c]));   // RN:252
+          const float v = sm.lvl_f[b];
+          if (e & 1) R[j][e >> 1].y = v; else R[j][e >> 1].x = v;
+          pk[e >> 2] |= (uint32_t)b << (8 * (e & 3));
         }
       }
-    }
-    if (values) {
+      if (bins) *reinterpret_cast<uint4*>(bins + mat_off + row * 64 + 16 * m.cb) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      if (values) {
 #pragma unroll
-      for (int c4 = 0; c4 < 16; ++c4)
-        *reinterpret_cast<float4*>(values + mat_off + m.row * 64 + 4 * c4) =
-            make_float4(R[2 * c4].x, R[2 * c4].y, R[2 * c4 + 1].x, R[2 * c4 + 1].y);
+        for (int k = 0; k < 4; ++k)
+          *reinterpret_cast<float4*>(values + mat_off + row * 64 + 16 * m.cb + 4 * k) =
+              make_float4(R[j][2 * k].x, R[j][2 * k].y, R[j][2 * k + 1].x, R[j][2 * k + 1].y);
+      }
     }
     return;
   }
 
   // ---- matrix given in HBM: coalesced 128-bit loads, quantise on the fly, transpose through an
-  // XOR-swizzled shared tile into row-per-thread registers.
+  // XOR-swizzled shared tile into the register tiles.
+#ifdef RDM_TIMING
+  const long long tq0 = clock64();
+#endif
   if (sc.kind == RDM_SRC_RAW_F64 || sc.kind == RDM_SRC_VAL_F64) {
     const double* src = reinterpret_cast<const double*>(sc.src) + mat_off;
     const bool quant = sc.kind == RDM_SRC_RAW_F64;
     constexpr int ITERS = ROWS * 32 / NT;   // element pairs per thread
-#pragma unroll 8
-    for (int k = 0; k < ITERS; ++k) {
+    // 16 independent 128-bit loads in flight per thread (the matrix tile is not live yet, so the
+    // registers are free): two round trips to HBM per page instead of four
+#pragma unroll 1
+    for (int k0 = 0; k0 < ITERS; k0 += 16) {
+     double2 xs[16];
+#pragma unroll
+     for (int kk = 0; kk < 16; ++kk) xs[kk] = ldg_stream_f64x2(src + 2 * (lt + NT * (k0 + kk)));
+#pragma unroll
+     for (int kk = 0; kk < 16; ++kk) {
+      const int k = k0 + kk;
       const int e2 = lt + NT * k;
       const int r = e2 >> 5, cp = e2 & 31;
-      double2 x = ldg_stream_f64x2(src + 2 * e2);
+      double2 x = xs[kk];
       float v0, v1;
       if (quant) {
-        int b0 = lloyd_bin<double>(x.x, sm.thr_d, sorted), b1 = lloyd_bin<double>(x.y, sm.thr_d, sorted);
+        int b0 = bin_d(x.x), b1 = bin_d(x.y);
         v0 = sm.lvl_f[b0];
         v1 = sm.lvl_f[b1];
         if (bins) *reinterpret_cast<uint16_t*>(bins + mat_off + 2 * e2) = (uint16_t)(b0 | (b1 << 8));
@@ -218,6 +299,7 @@ __device__ __forceinline__ void load_unit(float2 (&R)[32], const AlsScaleDev& sc
       if (values) *reinterpret_cast<float2*>(values + mat_off + 2 * e2) = make_float2(v0, v1);
       const int swz = (r / G) & 7;
       *reinterpret_cast<float2*>(tile + r * 64 + (((cp >> 1) ^ swz) << 2) + 2 * (cp & 1)) = make_float2(v0, v1);
+     }
     }
   } else {
     const float* src = reinterpret_cast<const float*>(sc.src) + mat_off;
@@ -229,8 +311,7 @@ __device__ __forceinline__ void load_unit(float2 (&R)[32], const AlsScaleDev& sc
       const int r = e4 >> 4, c4 = e4 & 15;
       float4 x = ldg_stream_f32x4(src + 4 * e4);
       if (quant) {
-        int b0 = lloyd_bin<float>(x.x, sm.thr_f, sorted), b1 = lloyd_bin<float>(x.y, sm.thr_f, sorted);
-        int b2 = lloyd_bin<float>(x.z, sm.thr_f, sorted), b3 = lloyd_bin<float>(x.w, sm.thr_f, sorted);
+        int b0 = bin_f(x.x), b1 = bin_f(x.y), b2 = bin_f(x.z), b3 = bin_f(x.w);
         x = make_float4(sm.lvl_f[b0], sm.lvl_f[b1], sm.lvl_f[b2], sm.lvl_f[b3]);
         if (bins)
           *reinterpret_cast<uint32_t*>(bins + mat_off + 4 * e4) = (uint32_t)(b0 | (b1 << 8) | (b2 << 16) | (b3 << 24));
@@ -240,36 +321,35 @@ __device__ __forceinline__ void load_unit(float2 (&R)[32], const AlsScaleDev& sc
       *reinterpret_cast<float4*>(tile + r * 64 + ((c4 ^ swz) << 2)) = x;
     }
   }
+#ifdef RDM_TIMING
+  const long long tq1 = clock64();
+#endif
   unit_barrier(bar_id, NT);
-  {
-    const int swz = m.i & 7;
-    const float4* t4 = reinterpret_cast<const float4*>(tile) + m.row * 16;
+#ifdef RDM_TIMING
+  if (lt == 0 && unit == 0 && blockIdx.x % 37 == 0) printf("  block %d kind %d: global load+quantise %lld cycles, barrier wait %lld\n", blockIdx.x, sc.kind, tq1 - tq0, clock64() - tq1);
+  if (lt == 255 && blockIdx.x % 37 == 0) printf("  block %d (thread 255): global load+quantise %lld cycles\n", blockIdx.x, tq1 - tq0);
+#endif
 #pragma unroll
-    for (int c4 = 0; c4 < 16; ++c4) {
-      float4 x = t4[c4 ^ swz];
-      R[2 * c4] = make_float2(x.x, x.y);
-      R[2 * c4 + 1] = make_float2(x.z, x.w);
+  for (int j = 0; j < 4; ++j) {
+    const int row = m.row(j);
+    const int swz = (row / G) & 7;
+    const float4* t4 = reinterpret_cast<const float4*>(tile) + row * 16;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float4 x = t4[(4 * m.cb + k) ^ swz];
+      R[j][2 * k] = make_float2(x.x, x.y);
+      R[j][2 * k + 1] = make_float2(x.z, x.w);
     }
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Direct residual of one row: sum_j (p q_j - R_ij)^2 in f32 (what CP:172-173 evaluates).
-__device__ __forceinline__ float sse_row(const float2 (&R)[32], const float* __restrict__ q, float p) {
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-  for (int c4 = 0; c4 < 16; ++c4) {
-    float4 x = *reinterpret_cast<const float4*>(q + 4 * c4);
-    // fl(fl(p q_j) - R_ij): the outer product is rounded before the subtraction in the reference
-    // (matmul, then sub); a fused multiply-subtract would differ when the fit is nearly exact
-    float t0 = __fsub_rn(__fmul_rn(p, x.x), R[2 * c4].x), t1 = __fsub_rn(__fmul_rn(p, x.y), R[2 * c4].y);
-    float t2 = __fsub_rn(__fmul_rn(p, x.z), R[2 * c4 + 1].x), t3 = __fsub_rn(__fmul_rn(p, x.w), R[2 * c4 + 1].y);
-    a0 = fmaf(t0, t0, a0);
-    a1 = fmaf(t1, t1, a1);
-    a2 = fmaf(t2, t2, a2);
-    a3 = fmaf(t3, t3, a3);
-  }
-  return (a0 + a1) + (a2 + a3);
+template <int G>
+__device__ __forceinline__ void load_unit(float2 (&R)[4][8], const AlsScaleDev& sc, AlsSmem& sm, float* tile,
+                                          int64_t unit_idx, int unit, int lt, bool emit) {
+  if (sm.lut.ncell)   // CTA-uniform
+    load_unit_impl<G, true>(R, sc, sm, tile, unit_idx, unit, lt, emit);
+  else
+    load_unit_impl<G, false>(R, sc, sm, tile, unit_idx, unit, lt, emit);
 }
 
 // Record (CP:53-61, CP:121-130).  Row i's residual sum_j (p_i q_j - R_ij)^2 equals
@@ -277,91 +357,116 @@ __device__ __forceinline__ float sse_row(const float2 (&R)[32], const float* __r
 // in f64 its absolute error is ~1e-7 |R_i|^2 (s_i and |q|^2 are f32).  That is used when the
 // row's residual is a sizeable part of its energy; rows fitted almost exactly (below kDirectFrac
 // of |R_i|^2 - near-constant or nearly rank-1 rows, where arg-min ties could flip k*) are
-// evaluated directly with sse_row(), the third pass the reference always makes.  The decision is
-// per row, so no cross-thread dependency exists: each thread parks its row's value for iteration
-// k in shared memory E[k][thread] and the unit reduces all iterations once, after the loop.
+// evaluated directly with tile_sse(), the third pass the reference always makes (a warp takes
+// that path when any of its rows asks for it).  Each thread parks the value of the row it owns
+// for iteration k in shared memory E[k][thread]; the unit reduces all iterations once, after
+// the loop (two rows per slot, so the scratch fits in the dead staging tile).
 constexpr double kDirectFrac = 0.005;
 
-// n_iter alternating iterations; returns this thread's p_{n_iter}[row].  RECORD: write the SSE of
-// iterations 0..n_iter to rec[] and p_1 to p1_out[].  E: shared scratch, (n_iter+1) x (NT+1) floats.
+// n_iter alternating iterations; returns p_{n_iter} of the row this thread owns.  RECORD: write
+// the SSE of iterations 0..n_iter to rec[] and p_1 to p1_out[].  E: (n_iter+1) x (NT/2+1) floats.
 template <int G, bool RECORD>
-__device__ __forceinline__ float als_iterate(const float2 (&R)[32], AlsSmem& sm, float* __restrict__ E, int unit, int lt, int n_iter,
+__device__ __forceinline__ float als_iterate(const float2 (&R)[4][8], AlsSmem& sm, float* __restrict__ E, int unit, int lt, int n_iter,
                                              float* __restrict__ rec, float* __restrict__ p1_out) {
   constexpr int NW = 2 * G;
   constexpr int NT = 64 * G;
-  constexpr int ES = NT + 1;                     // odd stride: the final column sums are conflict-free
-  const RowMap<G> m(lt);
+  constexpr int EH = NT / 2;                     // two rows (lanes l, l^4) share one slot
+  constexpr int ES = EH + 1;                     // odd stride: the final column sums are conflict-free
+  const TileMap<G> m(lt);
   const int gw = unit * NW + m.lw;
   const int bar_id = (G == 4) ? 0 : 1 + unit;
-  const int qp_base = (G == 4) ? 0 : unit;
+  const int qp_row = (G == 4) ? m.rp : unit;
   float* qw = sm.q_w[gw];
   float* ps = sm.p_s + unit * 64;
+  const float* qop = qw + 16 * m.cb;
+  const float* pop = ps + 64 * m.rp + 16 * m.cb;
+  const int eslot = ((lt >> 3) << 2) | (lt & 3);
 
-  // q_0 = 1: s = row sum, |q|^2 = 64.
+  // q_0 = 1
   qw[m.lane] = 1.0f;
   qw[m.lane + 32] = 1.0f;
   __syncwarp();
   float s, Q;
-  dot_norm(R, qw, s, Q);
+  tile_dot(R, qop, m.cb, s, Q);                  // s = row sum, Q = 64
   float invA = 1.0f / (Q + kLambda);             // torch.inverse of the 1x1 matrix |q|^2 + lambda
   double r2 = 0.0, direct_below = 0.0;
   if (RECORD) {
+    double t[4];
 #pragma unroll
-    for (int c = 0; c < 32; ++c) r2 = fma((double)R[c].y, (double)R[c].y, fma((double)R[c].x, (double)R[c].x, r2));
+    for (int j = 0; j < 4; ++j) {
+      t[j] = 0.0;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) t[j] = fma((double)R[j][e].y, (double)R[j][e].y, fma((double)R[j][e].x, (double)R[j][e].x, t[j]));
+    }
+    r2 = reduce_scatter4(t[0], t[1], t[2], t[3], m.cb);
     direct_below = kDirectFrac * r2;
+    const float ones[4] = {1.f, 1.f, 1.f, 1.f};
+    const float e0 = tile_sse(R, qop, ones, m.cb);   // k = 0: p = q = 1 (CP:55, CP:123)
     unit_barrier(bar_id, NT);                    // the staging tile (aliased by E) is dead from here on
-    E[lt] = sse_row(R, qw, 1.0f);                // k = 0: p = q = 1 (CP:55, CP:123)
+    const float e0p = e0 + __shfl_xor_sync(0xffffffffu, e0, 4);
+    if (!(m.lane & 4)) E[eslot] = e0p;
   }
   float p = 1.0f;
+#ifdef RDM_TIMING
+  const long long tl0 = clock64();
+#endif
   for (int k = 1; k <= n_iter; ++k) {
     p = s * invA;                                // (R q) @ inverse(A)
     if (!RECORD && k == n_iter) break;
-    ps[m.row] = p;
-    if (RECORD && k == 1) p1_out[m.row] = p;
+    ps[m.row_own] = p;
+    if (RECORD && k == 1) p1_out[m.row_own] = p;
     unit_barrier(bar_id, NT);                    // A: p visible
     float u, pseg;
-    dot_norm(R, ps + 64 * m.rp, u, pseg);        // q partial and |p segment|^2 from the same loads
+    tile_dot(R, pop, m.cb, u, pseg);             // this row's share of q_{ib+cb}; |p segment r'|^2
     if (RECORD) {
       const double e = r2 + (double)p * ((double)p * (double)Q - 2.0 * (double)s);
       float ef = fmaxf((float)e, 0.f);
-      if (e < direct_below) ef = sse_row(R, qw, p);   // qw still holds q_{k-1}
-      E[k * ES + lt] = ef;
+      const bool want = e < direct_below;
+      if (__any_sync(0xffffffffu, want)) {       // qw still holds q_{k-1}
+        float pj[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pj[j] = ps[m.row(j)];
+        const float ed = tile_sse(R, qop, pj, m.cb);
+        if (want) ef = ed;
+      }
+      ef += __shfl_xor_sync(0xffffffffu, ef, 4);
+      if (!(m.lane & 4)) E[k * ES + eslot] = ef;
     }
-    float npp = pseg;
+    sm.qpart[qp_row][m.ib + m.cb] = u;
     if constexpr (G == 4) {
-      sm.qpart[m.rp][m.i] = u;
       if (m.lw < 4 && m.lane == 0) sm.part_pp[m.rp] = pseg;
-    } else {
-      sm.qpart[qp_base][m.i] = u;
     }
     unit_barrier(bar_id, NT);                    // B: q partials (and |p|^2 segments) visible
     if (k == n_iter) break;
     // every warp finalises q for itself (no further barrier)
-    float u0, u1;
+    float npp = pseg, u0, u1;
     if constexpr (G == 4) {
       const float4 a = *reinterpret_cast<const float4*>(sm.part_pp);
       npp = (a.x + a.y) + (a.z + a.w);
       u0 = (sm.qpart[0][m.lane] + sm.qpart[1][m.lane]) + (sm.qpart[2][m.lane] + sm.qpart[3][m.lane]);
       u1 = (sm.qpart[0][m.lane + 32] + sm.qpart[1][m.lane + 32]) + (sm.qpart[2][m.lane + 32] + sm.qpart[3][m.lane + 32]);
     } else {
-      u0 = sm.qpart[qp_base][m.lane];
-      u1 = sm.qpart[qp_base][m.lane + 32];
+      u0 = sm.qpart[unit][m.lane];
+      u1 = sm.qpart[unit][m.lane + 32];
     }
     const float invB = 1.0f / (npp + kLambda);
     __syncwarp();
     qw[m.lane] = u0 * invB;
     qw[m.lane + 32] = u1 * invB;
     __syncwarp();
-    dot_norm(R, qw, s, Q);
+    tile_dot(R, qop, m.cb, s, Q);
     invA = 1.0f / (Q + kLambda);
   }
+#ifdef RDM_TIMING
+  if (RECORD && lt == 0 && unit == 0 && blockIdx.x % 37 == 0) printf("  block %d loop %lld cycles for %d iterations\n", blockIdx.x, clock64() - tl0, n_iter);
+#endif
   if (RECORD) {
     unit_barrier(bar_id, NT);
     for (int k = lt; k <= n_iter; k += NT) {
       const float* col = E + k * ES;
       double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
 #pragma unroll 4
-      for (int j = 0; j < NT; j += 4) {
+      for (int j = 0; j < EH; j += 4) {
         t0 += (double)col[j];
         t1 += (double)col[j + 1];
         t2 += (double)col[j + 2];
@@ -379,15 +484,27 @@ __device__ __forceinline__ void als_unit(const AlsParams& P, const AlsScaleDev& 
                                          int64_t unit_idx, int unit, int lt) {
   constexpr int NT = 64 * G;
   constexpr int ROWS = 64 * G;
-  const RowMap<G> m(lt);
+  const TileMap<G> m(lt);
+  const int row = m.row_own;
   const int bar_id = (G == 4) ? 0 : 1 + unit;
   const int ws_stride = sc.limit + 1 + ROWS;
   float* ws = sc.ws + unit_idx * ws_stride;
-  float2 R[32];
+  float2 R[4][8];
 
   if constexpr (PHASE == 0) {
+#ifdef RDM_TIMING
+    const long long t0 = clock64();
+#endif
     load_unit<G>(R, sc, sm, tile, unit_idx, unit, lt, true);
+#ifdef RDM_TIMING
+    const long long t1 = clock64();
+#endif
     als_iterate<G, true>(R, sm, E, unit, lt, sc.limit, ws, ws + sc.limit + 1);
+#ifdef RDM_TIMING
+    const long long t2 = clock64();
+    if (lt == 0 && (unit_idx % 37) == 0)
+      printf("unit %lld rows %d: load %lld cycles, iterate(+record) %lld cycles\n", (long long)unit_idx, ROWS, t1 - t0, t2 - t1);
+#endif
     return;
   } else {
     // ---- batch-wide rmse record and first arg-min (CP:172-173, CP:74, CP:143)
@@ -421,7 +538,7 @@ __device__ __forceinline__ void als_unit(const AlsParams& P, const AlsScaleDev& 
     if (kstar == 0) {
       p = 1.0f;
     } else if (kstar == 1) {
-      p = ws[sc.limit + 1 + m.row];
+      p = ws[sc.limit + 1 + row];
     } else {   // rare: replay k* iterations from the source
       load_unit<G>(R, sc, sm, tile, unit_idx, unit, lt, false);
       p = als_iterate<G, false>(R, sm, nullptr, unit, lt, kstar, nullptr, nullptr);
@@ -437,16 +554,16 @@ __device__ __forceinline__ void als_unit(const AlsParams& P, const AlsScaleDev& 
 #pragma unroll
     for (int w = 1; w < 2 * G; ++w) gm *= scratch[w];
     const float out = p / gm;
-    if (sc.pages_out) sc.pages_out[unit_idx * ROWS + m.row] = out;
+    if (sc.pages_out) sc.pages_out[unit_idx * ROWS + row] = out;
     if (sc.map_out) {
       if constexpr (G == 1) {
-        sc.map_out[img * 64 + m.row] = out;
+        sc.map_out[img * 64 + row] = out;
       } else {
         const int side = sc.side, ratio = side >> 4;
         float* mp = sc.map_out + img * (int64_t)side * side;
         // CP:218-238 as written: block-row j of every block-column holds page j (< ratio)
         if (pg < ratio)
-          for (int bc = 0; bc < ratio; ++bc) mp[(16 * pg + (m.row >> 4)) * side + 16 * bc + (m.row & 15)] = out;
+          for (int bc = 0; bc < ratio; ++bc) mp[(16 * pg + (row >> 4)) * side + 16 * bc + (row & 15)] = out;
       }
     }
   }
@@ -474,6 +591,15 @@ __global__ void __launch_bounds__(kAlsThreads, 2) als_kernel(const __grid_consta
     __syncthreads();
     // the branch-free search needs non-decreasing thresholds in BOTH dtypes
     if (tid < kThr - 1 && (!(sm.thr_d[tid] <= sm.thr_d[tid + 1]) || !(sm.thr_f[tid] <= sm.thr_f[tid + 1]))) sm.sorted = 0;
+    __syncthreads();
+    // f32 compares for the 8x8 path (RAW_F32, or MAP with 64 rows), f64 compares for pages
+    const bool f32cmp = sc.kind == RDM_SRC_RAW_F32 || (sc.kind == RDM_SRC_MAP_F32 && sc.rows == 64);
+    if (f32cmp)
+      build_lloyd_lut<float>(sm.lut, sm.thr_f, sm.sorted, sm.cell_s, tid, kAlsThreads);
+    else
+      build_lloyd_lut<double>(sm.lut, sm.thr_d, sm.sorted, sm.cell_s, tid, kAlsThreads);
+  } else if (tid == 0) {
+    sm.lut.ncell = 0;
   }
   __syncthreads();
   const int64_t n_units = P.n_images * sc.pages;
@@ -487,7 +613,7 @@ __global__ void __launch_bounds__(kAlsThreads, 2) als_kernel(const __grid_consta
     const int64_t unit_idx = (int64_t)local_cta * 4 + unit;
     // 64-row units: four independent units per CTA, so E lives behind the four staging tiles
     if (unit_idx < n_units)
-      als_unit<1, PHASE>(P, sc, sm, tile + unit * (64 * 64), tile + kTileFloats + unit * ((sc.limit + 1) * 65), unit_idx, unit, tid & 63);
+      als_unit<1, PHASE>(P, sc, sm, tile + unit * (64 * 64), tile + kTileFloats + unit * ((sc.limit + 1) * 33), unit_idx, unit, tid & 63);
   }
 }
 
@@ -589,8 +715,8 @@ extern "C" int rdm_als_fused_phases(const rdm_als_scale_t* scales, int32_t n_sca
   // dynamic shared memory: staging tile, plus the record scratch E of phase 0
   size_t dyn1 = kTileFloats * sizeof(float), dyn = dyn1;
   for (int k = 0; k < n_scales; ++k) {
-    const size_t need = (scales[k].rows == 256) ? (size_t)(scales[k].limit + 1) * 257 * sizeof(float)
-                                                : dyn1 + (size_t)4 * (scales[k].limit + 1) * 65 * sizeof(float);
+    const size_t need = (scales[k].rows == 256) ? (size_t)(scales[k].limit + 1) * 129 * sizeof(float)
+                                                : dyn1 + (size_t)4 * (scales[k].limit + 1) * 33 * sizeof(float);
     if (need > dyn) dyn = need;
   }
   cudaError_t e = cudaFuncSetAttribute(als_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);

@@ -118,6 +118,68 @@ __device__ __forceinline__ void load_codebook(const double* __restrict__ thr, co
   __syncthreads();
 }
 
+// ---- Lloyd bin by table lookup ------------------------------------------------------------
+// The 6-step search above is a chain of 6 dependent shared-memory loads per element, which made
+// quantisation latency-bound (measured: ~35k cycles to quantise one 256x64 page).  The upper bits
+// of a positive IEEE number are monotonic in its value, so cell(x) = (top bits of x) >> shift
+// orders values; a byte table over the cells between the first and last threshold stores how many
+// thresholds lie in LOWER cells.  With at most one threshold per cell (checked when the table is
+// built; 2^-10 relative cell width against a minimum threshold ratio of 1.0027 in the shipped
+// codebooks) the bin is lut[cell] + (x >= thr[lut[cell]]): two dependent loads, still exactly the
+// reference's count of thresholds <= x, in x's dtype.
+constexpr int kLutMax = 8192;
+
+template <typename T>
+__device__ __forceinline__ int lloyd_cell(T x);
+template <>
+__device__ __forceinline__ int lloyd_cell<double>(double x) { return __double2hiint(x) >> 10; }
+template <>
+__device__ __forceinline__ int lloyd_cell<float>(float x) { return __float_as_int(x) >> 13; }
+
+struct LloydLut {
+  int base;       // cell of the first threshold
+  int ncell;      // cells in the table (<= kLutMax); 0 = table unusable, use lloyd_bin()
+  uint8_t lut[kLutMax];
+};
+
+// Build the table for thresholds `tab` (kThrPad entries of T, NaN padded, see load_codebook).
+// All threads of the CTA call this; `sorted` as returned by load_codebook.
+template <typename T>
+__device__ __forceinline__ void build_lloyd_lut(LloydLut& L, const T* __restrict__ tab, int sorted, int* cell_s /* >= 40 ints, shared */,
+                                                int tid, int nthreads) {
+  if (tid < kThr) cell_s[tid] = lloyd_cell<T>(tab[tid]);
+  if (tid == 0) L.ncell = 0;
+  __syncthreads();
+  const int base = cell_s[0];
+  const int span = cell_s[kThr - 1] - base + 2;
+  bool ok = sorted && tab[0] > (T)0 && span <= kLutMax;
+  for (int i = 0; i < kThr - 1; ++i) ok = ok && (cell_s[i] < cell_s[i + 1]);   // one threshold per cell
+  if (!ok) return;      // uniform: every thread sees the same table
+  for (int c = tid; c < span; c += nthreads) {
+    int pos = 0;        // number of thresholds whose cell is < base + c
+#pragma unroll
+    for (int step = 32; step >= 1; step >>= 1) {
+      const int j = pos + step - 1;
+      pos += (j < kThr && cell_s[j] < base + c) ? step : 0;
+    }
+    L.lut[c] = (uint8_t)pos;
+  }
+  if (tid == 0) {
+    L.base = base;
+    L.ncell = span;
+  }
+  __syncthreads();
+}
+
+// Branch-free (so that independent look-ups interleave): base/ncell are passed in registers.
+template <typename T>
+__device__ __forceinline__ int lloyd_bin_lut(T x, const T* __restrict__ tab, const uint8_t* __restrict__ lut, int base, int ncell, T thr0) {
+  const int c = max(min(lloyd_cell<T>(x) - base, ncell - 1), 0);
+  const int b = lut[c];
+  const int r = b + ((x >= tab[b]) ? 1 : 0);   // tab[40..] is NaN: never true
+  return (x >= thr0) ? r : 0;   // below the first threshold, zero, negative or NaN: all 40 compares false
+}
+
 // Bicubic (A = -0.75) weights at t = 0.5: the only ones an exact halving needs (CP:308-311).
 #define RDM_W0 (-0.09375)
 #define RDM_W1 (0.59375)
