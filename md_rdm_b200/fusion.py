@@ -52,10 +52,28 @@ class FusionPlan:
         K, w_off, kmax, n_w = tail_layout(self.scales)
         self.K, self.w_off, self.kmax, self.n_weights = K, w_off, kmax, n_w
 
-        # ---- inputs (static buffers: copy into them, then run())
-        self.x_d1 = torch.ones((N, 1, 8, 8), dtype=torch.int64, device=dev)
+        # ---- inputs (static buffers: copy into them, then run()).  x_d1 and the per-scale sources are
+        # views of ONE device byte buffer so that a host call needs a single H2D copy.
+        shapes = [("x_d1", (N, 1, 8, 8), torch.int64)]
+        for s in self.scales:
+            if source == "map":
+                shapes.append((s, (N, 1, s, s), f32))
+            elif s == 8:
+                shapes.append((s, (N, 64, 64), f32))
+            else:
+                shapes.append((s, (N, (s // 16) ** 2, 256, 64), f64))
+        self._layout, off = [], 0
+        for key, shape, dt in shapes:
+            nbytes = int(torch.empty((), dtype=dt).element_size()) * int(torch.Size(shape).numel())
+            self._layout.append((key, shape, dt, off, nbytes))
+            off += (nbytes + 255) // 256 * 256
+        self._in_bytes = off
+        self._in_dev = torch.zeros((off,), dtype=torch.uint8, device=dev)
+        views = self._views(self._in_dev)
+        self.x_d1 = views["x_d1"]
+        self.x_d1.fill_(1)
         self.weights = torch.ones((n_w,), dtype=f32, device=dev)
-        self.src: Dict[int, torch.Tensor] = {}
+        self.src: Dict[int, torch.Tensor] = {s: views[s].fill_(1) for s in self.scales}
         # ---- outputs
         self.rel: Dict[int, torch.Tensor] = {}
         self.pages: Dict[int, torch.Tensor] = {}
@@ -72,13 +90,10 @@ class FusionPlan:
             P = 1 if s == 8 else (s // 16) ** 2
             limit = limit_8 if s == 8 else limit_page
             if source == "map":
-                self.src[s] = torch.ones((N, 1, s, s), dtype=f32, device=dev)
                 kind = _cabi.SRC_MAP_F32
             elif s == 8:
-                self.src[s] = torch.ones((N, 64, 64), dtype=f32, device=dev)
                 kind = _cabi.SRC_RAW_F32
             else:
-                self.src[s] = torch.ones((N, P, 256, 64), dtype=f64, device=dev)
                 kind = _cabi.SRC_RAW_F64
             thr, lvl = self.quant.device_tables(s, dev)
             self._tables[s] = (thr, lvl)
@@ -106,8 +121,13 @@ class FusionPlan:
         self._sides = i32_array(list(self.scales))
         self._a_ptrs = ptr_array([self.A[k].data_ptr() if (want_A and k <= kmax) else None for k in range(8)])
         self._graph: Optional[torch.cuda.CUDAGraph] = None
+        self._graph_e2e: Optional[torch.cuda.CUDAGraph] = None
         self._pinned = None
         self.launches_per_run = 3   # als_kernel<0>, als_kernel<1>, fuse_tail_kernel
+
+    def _views(self, buf: torch.Tensor):
+        """Typed views (x_d1 and one source per scale) of a packed input byte buffer."""
+        return {key: buf[off:off + nbytes].view(dt).view(shape) for key, shape, dt, off, nbytes in self._layout}
 
     # ------------------------------------------------------------------ device path
     def run(self) -> torch.Tensor:
@@ -167,9 +187,12 @@ class FusionPlan:
 
     # ------------------------------------------------------------------ host end-to-end
     def _host_buffers(self):
+        """Pinned host staging: one packed input buffer (typed views `x_d1`, `src[s]`) and the output."""
         if self._pinned is None:
-            pin = lambda t: torch.empty(t.shape, dtype=t.dtype).pin_memory()
-            self._pinned = dict(x_d1=pin(self.x_d1), src={s: pin(self.src[s]) for s in self.scales}, depth=pin(self.depth))
+            h_in = torch.zeros((self._in_bytes,), dtype=torch.uint8).pin_memory()
+            v = self._views(h_in)
+            self._pinned = dict(packed=h_in, x_d1=v["x_d1"], src={s: v[s] for s in self.scales},
+                                depth=torch.empty(self.depth.shape, dtype=self.depth.dtype).pin_memory())
         return self._pinned
 
     def h2d_bytes(self) -> int:
@@ -178,28 +201,74 @@ class FusionPlan:
     def d2h_bytes(self) -> int:
         return self.depth.numel() * 8
 
+    def _enqueue_e2e(self) -> None:
+        hb = self._host_buffers()
+        self._in_dev.copy_(hb["packed"], non_blocking=True)      # one H2D copy for all inputs
+        self.run()
+        hb["depth"].copy_(self.depth, non_blocking=True)          # D2H of the fused log-depth maps
+
+    def capture_e2e(self) -> None:
+        """CUDA graph of the whole host call: H2D copy node, the three kernels, D2H copy node."""
+        self._host_buffers()
+        with torch.cuda.device(self.device):
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                self._enqueue_e2e()
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._enqueue_e2e()
+            self._graph_e2e = g
+
+    def submit_pinned(self, use_graph: bool = True) -> None:
+        """Asynchronous host call on the current stream: inputs are taken from this plan's pinned
+        staging buffers (`_host_buffers()`), the result lands in its pinned `depth` buffer."""
+        if use_graph:
+            if self._graph_e2e is None:
+                self.capture_e2e()
+            self._graph_e2e.replay()
+        else:
+            self._enqueue_e2e()
+
+    def run_pinned(self, use_graph: bool = True) -> torch.Tensor:
+        """Synchronous host call with the inputs already staged in the pinned buffers."""
+        self.submit_pinned(use_graph)
+        torch.cuda.current_stream(self.device).synchronize()
+        return self._pinned["depth"]
+
     def run_host(self, x_d1: torch.Tensor, srcs: Sequence[torch.Tensor], use_graph: bool = True) -> torch.Tensor:
-        """Host tensors in -> host (pinned) log-depth out, synchronous: H2D copies, the three
-        launches (graph replay), D2H copy, stream sync."""
+        """Host tensors in -> host (pinned) log-depth out, synchronous: stage, H2D copy, the three
+        launches, D2H copy, stream sync."""
         hb = self._host_buffers()
         hb["x_d1"].copy_(x_d1.reshape(hb["x_d1"].shape))
         for s, t in zip(self.scales, srcs):
             hb["src"][s].copy_(t.reshape(hb["src"][s].shape))
         return self.run_pinned(use_graph)
 
-    def run_pinned(self, use_graph: bool = True) -> torch.Tensor:
-        """Same, with the inputs already staged in this plan's pinned host buffers."""
-        hb = self._host_buffers()
-        self.x_d1.copy_(hb["x_d1"], non_blocking=True)
-        for s in self.scales:
-            self.src[s].copy_(hb["src"][s], non_blocking=True)
-        if use_graph:
-            self.replay()
-        else:
-            self.run()
-        hb["depth"].copy_(self.depth, non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
-        return hb["depth"]
+
+def capture_ring(plans: Sequence[FusionPlan], n_streams: int, e2e: bool = False) -> torch.cuda.CUDAGraph:
+    """ONE CUDA graph that runs every plan of `plans` once, plan i on branch i % n_streams (fork/join
+    inside the capture): a whole ring of batches per host launch, so the host launch rate
+    (~25-50 us per Python graph replay) does not bound a multi-batch pipeline."""
+    dev = plans[0].device
+    with torch.cuda.device(dev):
+        side = [torch.cuda.Stream() for _ in range(n_streams)]
+        for p in plans:                 # warm-up outside capture
+            p._enqueue_e2e() if e2e else p.run()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            cur = torch.cuda.current_stream()
+            for s in side:
+                s.wait_stream(cur)
+            for i, p in enumerate(plans):
+                with torch.cuda.stream(side[i % n_streams]):
+                    p._enqueue_e2e() if e2e else p.run()
+            for s in side:
+                cur.wait_stream(s)
+    return g
 
 
 _plans: Dict[tuple, FusionPlan] = {}

@@ -34,7 +34,10 @@ def _rel_err(a, b):
 
 
 def _depth_ok(ours, ref):
-    return bool(((ours - ref).abs() <= DEPTH_TOL * ref.abs().clamp_min(1.0)).all())
+    # NaN-aware: a DORN map with violent 1 <-> 89 jumps can make the (-3,19,19,-3)/32 bicubic go
+    # negative, and log() of that is NaN in the reference too
+    both_nan = torch.isnan(ours) & torch.isnan(ref)
+    return bool((both_nan | ((ours - ref).abs() <= DEPTH_TOL * ref.abs().clamp_min(1.0))).all())
 
 
 R = None
@@ -490,7 +493,7 @@ def test_edge_batches(dev, books):
     assert _depth_ok(plan.depth.cpu(), ref["depth"])
     # no relative decoders at all: decoder 1 only (the reference's HEAD configuration, RN:63)
     plan = FusionPlan(2, (), "map", device=dev)
-    x = torch.randint(1, 90, (2, 1, 8, 8), dtype=torch.int64)
+    x = torch.randint(1, 90, (2, 1, 8, 8), dtype=torch.int64, generator=torch.Generator().manual_seed(17))
     w = torch.tensor([0.7, 1.1, 0.4, 0.9])
     plan.load_inputs(x.to(dev), [], w.to(dev))
     plan.run()
