@@ -92,7 +92,9 @@ def reconstruct(splits):
 
 
 def quick_gm(t, rc):
-    """CP:244-255."""
+    """CP:244-255 (int32 SID labels, MOD:126, are widened to int64: same values, same f32 result)."""
+    if t.dtype in (torch.int32, torch.int16, torch.uint8):
+        t = t.long()
     return R.quick_gm(t, int(rc))
 
 

@@ -97,6 +97,27 @@ __device__ __forceinline__ void unit_barrier(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// ---- shared-memory accesses of the iteration loop by 32-bit shared address.  With generic
+// pointers nvcc 12.9 re-derived the shared window base (S2UR SR_CgaCtaId + ULEA, ~75 cycles of
+// scoreboard wait) inside every iteration (profiles/r1_als_kernel_stalls.txt).
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 lds_v4f32(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ ulonglong2 lds_v2u64(uint32_t a) {
+  ulonglong2 v;
+  asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "r"(a) : "memory");
+  return v;
+}
+
 // ---- packed f32x2 arithmetic (sm_100a FFMA2)
 using u64 = unsigned long long;
 __device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) {
@@ -148,10 +169,10 @@ __device__ __forceinline__ T group_sum4(T v) {
 
 // Partial GEMV of the tile with the lane's 16-float operand slice `op` (4 LDS.128) and the
 // squared norm of the slice: own = full dot of the row this lane owns, nrm = |whole operand|^2.
-__device__ __forceinline__ void tile_dot(const float2 (&R)[4][8], const float* __restrict__ op, int cb, float& own, float& nrm) {
+__device__ __forceinline__ void tile_dot(const float2 (&R)[4][8], uint32_t op, int cb, float& own, float& nrm) {
   ulonglong2 x[4];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) x[k] = *reinterpret_cast<const ulonglong2*>(op + 4 * k);
+  for (int k = 0; k < 4; ++k) x[k] = lds_v2u64(op + 16 * k);
   u64 a[4][2];
   u64 n0 = 0, n1 = 0;   // all-zero bits = (0.f, 0.f)
 #pragma unroll
@@ -172,11 +193,11 @@ __device__ __forceinline__ void tile_dot(const float2 (&R)[4][8], const float* _
 
 // Direct residual of the tile rows: sum_c (p_j q_c - R[j][c])^2 in f32 (what CP:172-173
 // evaluates); lane cb receives the row it owns.
-__device__ __forceinline__ float tile_sse(const float2 (&R)[4][8], const float* __restrict__ qop, const float (&pj)[4], int cb) {
+__device__ __forceinline__ float tile_sse(const float2 (&R)[4][8], uint32_t qop, const float (&pj)[4], int cb) {
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const float4 x = *reinterpret_cast<const float4*>(qop + 4 * k);
+    const float4 x = lds_v4f32(qop + 16 * k);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       // fl(fl(p q_c) - R): the outer product is rounded before the subtraction in the reference
@@ -376,15 +397,18 @@ __device__ __forceinline__ float als_iterate(const float2 (&R)[4][8], AlsSmem& s
   const int gw = unit * NW + m.lw;
   const int bar_id = (G == 4) ? 0 : 1 + unit;
   const int qp_row = (G == 4) ? m.rp : unit;
-  float* qw = sm.q_w[gw];
-  float* ps = sm.p_s + unit * 64;
-  const float* qop = qw + 16 * m.cb;
-  const float* pop = ps + 64 * m.rp + 16 * m.cb;
+  const uint32_t qw = smem_u32(sm.q_w[gw]);                    // this warp's copy of q
+  const uint32_t ps = smem_u32(sm.p_s + unit * 64);            // p of this unit
+  const uint32_t qop = qw + 64 * m.cb;                         // operand slices (16 floats)
+  const uint32_t pop = ps + 256 * m.rp + 64 * m.cb;
+  const uint32_t qpart = smem_u32(sm.qpart);
+  const uint32_t ppart = smem_u32(sm.part_pp);
   const int eslot = ((lt >> 3) << 2) | (lt & 3);
+  const uint32_t Es = RECORD ? smem_u32(E) + 4 * eslot : 0;
 
   // q_0 = 1
-  qw[m.lane] = 1.0f;
-  qw[m.lane + 32] = 1.0f;
+  sts_f32(qw + 4 * m.lane, 1.0f);
+  sts_f32(qw + 4 * m.lane + 128, 1.0f);
   __syncwarp();
   float s, Q;
   tile_dot(R, qop, m.cb, s, Q);                  // s = row sum, Q = 64
@@ -404,7 +428,7 @@ __device__ __forceinline__ float als_iterate(const float2 (&R)[4][8], AlsSmem& s
     const float e0 = tile_sse(R, qop, ones, m.cb);   // k = 0: p = q = 1 (CP:55, CP:123)
     unit_barrier(bar_id, NT);                    // the staging tile (aliased by E) is dead from here on
     const float e0p = e0 + __shfl_xor_sync(0xffffffffu, e0, 4);
-    if (!(m.lane & 4)) E[eslot] = e0p;
+    if (!(m.lane & 4)) sts_f32(Es, e0p);
   }
   float p = 1.0f;
 #ifdef RDM_TIMING
@@ -413,7 +437,7 @@ __device__ __forceinline__ float als_iterate(const float2 (&R)[4][8], AlsSmem& s
   for (int k = 1; k <= n_iter; ++k) {
     p = s * invA;                                // (R q) @ inverse(A)
     if (!RECORD && k == n_iter) break;
-    ps[m.row_own] = p;
+    sts_f32(ps + 4 * m.row_own, p);
     if (RECORD && k == 1) p1_out[m.row_own] = p;
     unit_barrier(bar_id, NT);                    // A: p visible
     float u, pseg;
@@ -425,34 +449,37 @@ __device__ __forceinline__ float als_iterate(const float2 (&R)[4][8], AlsSmem& s
       if (__any_sync(0xffffffffu, want)) {       // qw still holds q_{k-1}
         float pj[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) pj[j] = ps[m.row(j)];
+        for (int j = 0; j < 4; ++j) pj[j] = lds_f32(ps + 4 * m.row(j));
         const float ed = tile_sse(R, qop, pj, m.cb);
         if (want) ef = ed;
       }
       ef += __shfl_xor_sync(0xffffffffu, ef, 4);
-      if (!(m.lane & 4)) E[k * ES + eslot] = ef;
+      if (!(m.lane & 4)) sts_f32(Es + 4 * k * ES, ef);
     }
-    sm.qpart[qp_row][m.ib + m.cb] = u;
+    sts_f32(qpart + 4 * (64 * qp_row + m.ib + m.cb), u);
     if constexpr (G == 4) {
-      if (m.lw < 4 && m.lane == 0) sm.part_pp[m.rp] = pseg;
+      if (m.lw < 4 && m.lane == 0) sts_f32(ppart + 4 * m.rp, pseg);
     }
     unit_barrier(bar_id, NT);                    // B: q partials (and |p|^2 segments) visible
     if (k == n_iter) break;
     // every warp finalises q for itself (no further barrier)
     float npp = pseg, u0, u1;
     if constexpr (G == 4) {
-      const float4 a = *reinterpret_cast<const float4*>(sm.part_pp);
+      const float4 a = lds_v4f32(ppart);
+      const uint32_t q0a = qpart + 4 * m.lane;
+      const float a0 = lds_f32(q0a), a1 = lds_f32(q0a + 256), a2 = lds_f32(q0a + 512), a3 = lds_f32(q0a + 768);
+      const float b0 = lds_f32(q0a + 128), b1 = lds_f32(q0a + 384), b2 = lds_f32(q0a + 640), b3 = lds_f32(q0a + 896);
       npp = (a.x + a.y) + (a.z + a.w);
-      u0 = (sm.qpart[0][m.lane] + sm.qpart[1][m.lane]) + (sm.qpart[2][m.lane] + sm.qpart[3][m.lane]);
-      u1 = (sm.qpart[0][m.lane + 32] + sm.qpart[1][m.lane + 32]) + (sm.qpart[2][m.lane + 32] + sm.qpart[3][m.lane + 32]);
+      u0 = (a0 + a1) + (a2 + a3);
+      u1 = (b0 + b1) + (b2 + b3);
     } else {
-      u0 = sm.qpart[unit][m.lane];
-      u1 = sm.qpart[unit][m.lane + 32];
+      u0 = lds_f32(qpart + 4 * (64 * unit + m.lane));
+      u1 = lds_f32(qpart + 4 * (64 * unit + m.lane + 32));
     }
     const float invB = 1.0f / (npp + kLambda);
     __syncwarp();
-    qw[m.lane] = u0 * invB;
-    qw[m.lane + 32] = u1 * invB;
+    sts_f32(qw + 4 * m.lane, u0 * invB);
+    sts_f32(qw + 4 * m.lane + 128, u1 * invB);
     __syncwarp();
     tile_dot(R, qop, m.cb, s, Q);
     invA = 1.0f / (Q + kLambda);
@@ -513,9 +540,19 @@ __device__ __forceinline__ void als_unit(const AlsParams& P, const AlsScaleDev& 
     const int64_t g0 = (img / P.group) * P.group;   // first image of the reference batch
     float* rm = sm.rm + unit * 64;
     const double inv_cnt = 1.0 / ((double)P.group * (double)(ROWS * kCols));
+    const int64_t gstride = (int64_t)sc.pages * ws_stride;
     for (int k = lt; k <= sc.limit; k += NT) {
+      const float* col = sc.ws + (g0 * sc.pages + pg) * (int64_t)ws_stride + k;
       double t = 0.0;
-      for (int b = 0; b < P.group; ++b) t += (double)sc.ws[((g0 + b) * sc.pages + pg) * (int64_t)ws_stride + k];
+      int b = 0;
+      for (; b + 8 <= P.group; b += 8) {   // 8 independent loads in flight, summed in image order
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = col[(b + j) * gstride];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t += (double)v[j];
+      }
+      for (; b < P.group; ++b) t += (double)col[b * gstride];
       rm[k] = (float)sqrt(t * inv_cnt);
     }
     unit_barrier(bar_id, NT);
@@ -719,8 +756,9 @@ extern "C" int rdm_als_fused_phases(const rdm_als_scale_t* scales, int32_t n_sca
                                                 : dyn1 + (size_t)4 * (scales[k].limit + 1) * 33 * sizeof(float);
     if (need > dyn) dyn = need;
   }
-  cudaError_t e = cudaFuncSetAttribute(als_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(als_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn1);
+  static size_t smem_set0[64], smem_set1[64];
+  cudaError_t e = ensure_dyn_smem(als_kernel<0>, dyn, smem_set0);
+  if (e == cudaSuccess) e = ensure_dyn_smem(als_kernel<1>, dyn1, smem_set1);
   if (e != cudaSuccess) {
     set_error("rdm_als_fused: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     return (int)e;

@@ -26,6 +26,20 @@ int launch_status(const char* what);   // cudaGetLastError -> return code + mess
     }                                     \
   } while (0)
 
+// Opt-in dynamic shared memory, set once per (kernel, device) and raised only when a larger
+// size is needed: cudaFuncSetAttribute costs a few microseconds of host time per call.
+// `cache` is a per-kernel array of 64 entries (benign race: at worst the attribute is set twice).
+template <typename Kernel>
+inline cudaError_t ensure_dyn_smem(Kernel kernel, size_t bytes, size_t* cache) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev >= 0 && dev < 64 && cache[dev] >= bytes) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess && dev >= 0 && dev < 64) cache[dev] = bytes;
+  return e;
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 inline bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 inline int ilog2(int v) { int n = 0; while ((1 << n) < v) ++n; return n; }

@@ -413,7 +413,12 @@ __global__ void __launch_bounds__(256) recombination_bwd_kernel(const double* __
 // Fused tail.  Grid = n_images * bands; every CTA rebuilds the (tiny) pyramids of its image in
 // shared memory and writes one horizontal band of the 128x128 f64 log-depth map, so the 128 KB
 // per image output - the only significant HBM traffic of stages 4+5 - is spread over the chip.
+// All decoders descend their pyramids TOGETHER, one level per stage (5-6 stages of two barriers
+// instead of one barrier-separated stage per decoder and level), and the expensive f64 log() calls
+// of a level are spread over all threads before the per-slot weighted sum is formed in candidate
+// order (CP:521 sums decoder 1 first).
 constexpr int kMaxRel = 6;
+constexpr int kMaxDec = kMaxRel + 1;
 struct TailParams {
   const int64_t* x_d1;
   const float* rel[kMaxRel];
@@ -425,34 +430,29 @@ struct TailParams {
   int32_t n_rel;
   int32_t w_off[8];         // first weight of slot k
   int32_t K[8];             // candidates in slot k
-  int32_t cand[kMaxRel + 1][8];   // candidate index of decoder d in slot k
+  int32_t cand[kMaxDec][8]; // candidate index of decoder d in slot k
+  int32_t doff[kMaxDec];    // start (doubles) of decoder d's pyramid in shared memory
+  int32_t nlev[kMaxDec];    // levels n_d (side 2^n_d)
+  int32_t act[8][kMaxDec];  // decoders that have level k, in candidate order
+  int32_t nact[8];
+  int32_t dtotal;           // doubles of pyramid storage
+  int32_t lmax;             // floats of per-stage log scratch
   int32_t kmax;
   int32_t bands;
 };
 
 __global__ void __launch_bounds__(256) fuse_tail_kernel(const __grid_constant__ TailParams P) {
-  extern __shared__ __align__(16) double D[];               // kPyrDoubles
-  float* yh = reinterpret_cast<float*>(D + kPyrDoubles);     // kPyrDoubles floats, slot k at off_level(k)
+  extern __shared__ __align__(16) double D[];                // P.dtotal doubles
+  float* yh = reinterpret_cast<float*>(D + P.dtotal);         // slot k at off_level(k)
+  const int ylen = off_level(P.kmax + 1);
+  float* L = yh + ylen;                                       // P.lmax floats: f32(log F) of the current level
   __shared__ float scratch[32];
   const int64_t img = blockIdx.x / P.bands;
   const int band = blockIdx.x - (int)(img * P.bands);
   const bool lead = band == 0;
   const int tid = threadIdx.x;
-  const int ylen = off_level(P.kmax + 1);
-  for (int i = tid; i < ylen; i += blockDim.x) yh[i] = 0.f;
 
-  auto level_emit = [&](int dec) {
-    return [&, dec](int k, int idx, double f) {
-      const int cand = P.cand[dec][k];
-      const int64_t M = 1 << (2 * k);
-      const double lg = log(f);                                      // CP:478-480
-      if (lead && P.A_out[k]) P.A_out[k][(img * P.K[k] + cand) * M + idx] = lg;
-      float* y = yh + off_level(k) + idx;
-      *y = fmaf((float)lg, P.w[P.w_off[k] + cand], *y);               // CP:521 / CP:526
-    };
-  };
-
-  // ---- decoder 1 (ordinary map): x / gm(x) in f32 (RN:117), then 3 levels + D_0
+  // ---- top levels: decoder 1 = x / gm(x) in f32 (RN:117); relative decoders as they come
   {
     float v = 1.f, pw = 1.f;
     if (tid < 64) {
@@ -460,26 +460,47 @@ __global__ void __launch_bounds__(256) fuse_tail_kernel(const __grid_constant__ 
       pw = (float)pow((double)v, 1.0 / 64.0);
     }
     const float gm = block_prod<float>(pw, scratch);
-    if (tid < 64) D[off_level(3) + tid] = (double)(v / gm);
-    __syncthreads();
-    pyramid_down(D, 3, level_emit(0));
-    __syncthreads();
-    if (tid == 0) {
-      const double d0 = D[0];
-      const double lg = log(d0);
-      if (lead && P.A_out[0]) P.A_out[0][img] = lg;
-      yh[0] = fmaf((float)lg, P.w[P.w_off[0]], yh[0]);
+    if (tid < 64) D[P.doff[0] + off_level(3) + tid] = (double)(v / gm);
+    for (int r = 0; r < P.n_rel; ++r) {
+      const int side = P.side[r];
+      const float* src = P.rel[r] + img * (int64_t)side * side;
+      double* dn = D + P.doff[r + 1] + off_level(P.nlev[r + 1]);
+      for (int idx = tid; idx < side * side; idx += blockDim.x) dn[idx] = (double)src[idx];
     }
   }
-  // ---- relative decoders
-  for (int r = 0; r < P.n_rel; ++r) {
-    const int side = P.side[r], n = 31 - __clz(side);
-    const float* src = P.rel[r] + img * (int64_t)side * side;
+  __syncthreads();
+  for (int k = P.kmax; k >= 1; --k) {
+    const int side = 1 << k, half = side >> 1, na = P.nact[k];
+    // (a) level k-1 of every decoder that has level k
+    for (int item = tid; item < na * half * half; item += blockDim.x) {
+      const int a = item >> (2 * (k - 1)), idx = item & (half * half - 1);
+      const double* cur = D + P.doff[P.act[k][a]] + off_level(k);
+      const int y = idx >> (k - 1), x = idx & (half - 1);
+      D[P.doff[P.act[k][a]] + off_level(k - 1) + idx] = bicubic_half_at([&](int r, int c) { return cur[r * side + c]; }, y, x, side);
+    }
     __syncthreads();
-    double* dn = D + off_level(n);
-    for (int idx = tid; idx < side * side; idx += blockDim.x) dn[idx] = (double)src[idx];
+    // (b1) F_k = D_k / up2(D_{k-1}) (CP:389) and its log (CP:478-480), all decoders, all threads
+    for (int item = tid; item < na * side * side; item += blockDim.x) {
+      const int a = item >> (2 * k), idx = item & (side * side - 1);
+      const int d = P.act[k][a];
+      const double* base = D + P.doff[d];
+      const int y = idx >> k, x = idx & (side - 1);
+      const double lg = log(base[off_level(k) + idx] / base[off_level(k - 1) + (y >> 1) * half + (x >> 1)]);
+      if (lead && P.A_out[k]) P.A_out[k][(img * P.K[k] + P.cand[d][k]) * (int64_t)(side * side) + idx] = lg;
+      L[item] = (float)lg;
+    }
     __syncthreads();
-    pyramid_down(D, n, level_emit(r + 1));
+    // (b2) slot k of y_hat: sum over candidates in decoder order (CP:521 / CP:526)
+    for (int idx = tid; idx < side * side; idx += blockDim.x) {
+      float y = 0.f;
+      for (int a = 0; a < na; ++a) y = fmaf(L[a * side * side + idx], P.w[P.w_off[k] + P.cand[P.act[k][a]][k]], y);
+      yh[off_level(k) + idx] = y;
+    }
+  }
+  if (tid == 0) {   // slot 0: D_0 of decoder 1
+    const double lg = log(D[P.doff[0]]);
+    if (lead && P.A_out[0]) P.A_out[0][img] = lg;
+    yh[0] = fmaf((float)lg, P.w[P.w_off[0]], 0.f);
   }
   __syncthreads();
   if (lead && P.yhat_out)
@@ -516,6 +537,14 @@ static int grid_cap(int64_t items, int per_block) {
 }  // namespace rdm
 
 using namespace rdm;
+
+static size_t smem_set_decompose_bwd_kernel_double_[64];
+static size_t smem_set_decompose_bwd_kernel_float_[64];
+static size_t smem_set_decompose_kernel_double_[64];
+static size_t smem_set_decompose_kernel_float_[64];
+static size_t smem_set_fuse_tail_kernel[64];
+static size_t smem_set_recombination_bwd_kernel_double_[64];
+static size_t smem_set_recombination_bwd_kernel_float_[64];
 
 extern "C" int64_t rdm_pyramid_len(int32_t side, int32_t relative_map) {
   if (!is_pow2(side)) return -1;
@@ -563,11 +592,11 @@ extern "C" int rdm_decompose(const void* in, int32_t in_is_f64, int64_t n_images
   const size_t smem = kPyrDoubles * sizeof(double);
   cudaError_t e;
   if (in_is_f64) {
-    e = cudaFuncSetAttribute(decompose_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = ensure_dyn_smem(decompose_kernel<double>, smem, smem_set_decompose_kernel_double_);
     if (e == cudaSuccess)
       decompose_kernel<double><<<(unsigned)n_images, 256, smem, (cudaStream_t)stream>>>((const double*)in, side, n, relative_map, pyramid_out, n_images);
   } else {
-    e = cudaFuncSetAttribute(decompose_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = ensure_dyn_smem(decompose_kernel<float>, smem, smem_set_decompose_kernel_float_);
     if (e == cudaSuccess)
       decompose_kernel<float><<<(unsigned)n_images, 256, smem, (cudaStream_t)stream>>>((const float*)in, side, n, relative_map, pyramid_out, n_images);
   }
@@ -588,11 +617,11 @@ extern "C" int rdm_decompose_bwd(const void* in, int32_t in_is_f64, int64_t n_im
   const size_t smem = 2 * kPyrDoubles * sizeof(double);
   cudaError_t e;
   if (in_is_f64) {
-    e = cudaFuncSetAttribute(decompose_bwd_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = ensure_dyn_smem(decompose_bwd_kernel<double>, smem, smem_set_decompose_bwd_kernel_double_);
     if (e == cudaSuccess)
       decompose_bwd_kernel<double><<<(unsigned)n_images, 256, smem, (cudaStream_t)stream>>>((const double*)in, side, n, relative_map, grad_pyramid, n_images, (double*)grad_in);
   } else {
-    e = cudaFuncSetAttribute(decompose_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = ensure_dyn_smem(decompose_bwd_kernel<float>, smem, smem_set_decompose_bwd_kernel_float_);
     if (e == cudaSuccess)
       decompose_bwd_kernel<float><<<(unsigned)n_images, 256, smem, (cudaStream_t)stream>>>((const float*)in, side, n, relative_map, grad_pyramid, n_images, (float*)grad_in);
   }
@@ -727,11 +756,11 @@ extern "C" int rdm_recombination_bwd(const double* grad_out, void* const* grad_c
   const size_t smem = kPyrDoubles * sizeof(double);
   cudaError_t e;
   if (comps_are_f64) {
-    e = cudaFuncSetAttribute(recombination_bwd_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = ensure_dyn_smem(recombination_bwd_kernel<double>, smem, smem_set_recombination_bwd_kernel_double_);
     if (e == cudaSuccess)
       recombination_bwd_kernel<double><<<(unsigned)batch, 256, smem, (cudaStream_t)stream>>>(grad_out, pl, n_comps, n, batch);
   } else {
-    e = cudaFuncSetAttribute(recombination_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = ensure_dyn_smem(recombination_bwd_kernel<float>, smem, smem_set_recombination_bwd_kernel_float_);
     if (e == cudaSuccess)
       recombination_bwd_kernel<float><<<(unsigned)batch, 256, smem, (cudaStream_t)stream>>>(grad_out, pl, n_comps, n, batch);
   }
@@ -771,7 +800,11 @@ extern "C" int rdm_fuse_tail(const int64_t* x_d1, const float* const* rel, const
   for (int k = 0; k < 8; ++k) {
     P.K[k] = (k <= 3) ? 1 : 0;
     P.cand[0][k] = 0;
+    P.nact[k] = 0;
   }
+  P.nlev[0] = 3;
+  P.doff[0] = 0;
+  int dtotal = off_level(4);
   for (int r = 0; r < n_rel; ++r) {
     RDM_REQUIRE(rel[r], "rdm_fuse_tail: rel[%d] is null", r);
     RDM_REQUIRE(is_pow2(sides[r]) && sides[r] >= 2 && sides[r] <= 64, "rdm_fuse_tail: rel side must be a power of two in 2..64 (got %d)", sides[r]);
@@ -780,19 +813,33 @@ extern "C" int rdm_fuse_tail(const int64_t* x_d1, const float* const* rel, const
     const int n = ilog2(sides[r]);
     if (n > P.kmax) P.kmax = n;
     for (int k = 1; k <= n; ++k) P.cand[r + 1][k] = P.K[k]++;
+    P.nlev[r + 1] = n;
+    P.doff[r + 1] = dtotal;
+    dtotal += off_level(n + 1);
   }
+  P.dtotal = (dtotal + 1) & ~1;
+  int lmax = 0;
+  for (int k = 1; k <= P.kmax; ++k) {
+    for (int d = 0; d <= n_rel; ++d)
+      if (P.nlev[d] >= k) P.act[k][P.nact[k]++] = d;
+    lmax = P.nact[k] * (1 << (2 * k)) > lmax ? P.nact[k] * (1 << (2 * k)) : lmax;
+  }
+  P.lmax = lmax;
   int woff = 0;
   for (int k = 0; k < 8; ++k) {
     P.w_off[k] = woff;
     woff += P.K[k];
     P.A_out[k] = (A_out && k <= P.kmax) ? A_out[k] : nullptr;
   }
+  // bands: enough CTAs to spread the 128 KB/image output, few enough that the pyramid work (redone
+  // by every band) stays small: >= 64 CTAs in total
   int bands = 1;
-  while (bands < 16 && n_images * bands < kNumSMs) bands <<= 1;
+  while (bands < 16 && n_images * bands < 64) bands <<= 1;
   P.bands = bands;
   RDM_REQUIRE(n_images * bands < (1ll << 31), "rdm_fuse_tail: too many images");
-  const size_t smem = kPyrDoubles * (sizeof(double) + sizeof(float));
-  cudaError_t e = cudaFuncSetAttribute(fuse_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const size_t smem = (size_t)P.dtotal * sizeof(double) + ((size_t)off_level(P.kmax + 1) + lmax) * sizeof(float);
+  RDM_REQUIRE(smem <= 220 * 1024, "rdm_fuse_tail: decoder pyramids need %zu bytes of shared memory (max 220 KB)", smem);
+  cudaError_t e = ensure_dyn_smem(fuse_tail_kernel, smem, smem_set_fuse_tail_kernel);
   if (e != cudaSuccess) {
     set_error("rdm_fuse_tail: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     return (int)e;

@@ -377,3 +377,25 @@ def synthetic_batch(B: int, scales: Sequence[int], seed: int):
     Ks = [k for k in slot_sizes(scales) if k > 0]
     weights = [torch.abs(torch.randn(k, 1, generator=g)) for k in Ks]
     return x_d1, rel, weights
+
+
+# --------------------------------------------------------------------------- training step (BASELINE config 3)
+def training_targets(y128: torch.Tensor) -> List[torch.Tensor]:
+    """MOD:119-127 `compute_final_depth` targets for the masked 128x128 f64 ground truth: components of
+    the normalised target (n=7) with slot 0 replaced by D_0 of the SID-labelled 8x8 target."""
+    comps = decompose(gm_normalize(y128), 7)
+    ord8 = depth2label_sid(resize(y128, 8))                         # int32 labels, utils.py:195-211
+    ord_comps = decompose(gm_normalize(ord8), 3)
+    comps[0] = ord_comps[0]
+    return comps
+
+
+def training_loss(y_raw: torch.Tensor, y_hat: Sequence[torch.Tensor]):
+    """MOD:64-92 without the ordinal loss: resize to 128, mask, per-scale MSE (detached sum, CP:499-510),
+    recombination, MSE against the masked target.  Returns (loss_all, mse, fine_detail_loss, final_depth)."""
+    y = mask_target(resize(y_raw, 128))                              # MOD:68, MOD:74-78
+    targets = training_targets(y)
+    fine = torch.sum(torch.as_tensor([torch.nn.MSELoss()(a, b) for a, b in zip(y_hat, targets)]))   # CP:499-510
+    final = recombination(list(y_hat))                               # MOD:132
+    mse = torch.nn.MSELoss()(final, y)                               # MOD:89
+    return mse + fine, mse, fine, final

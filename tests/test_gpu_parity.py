@@ -521,3 +521,76 @@ def test_backward_decompose_chain(dev, side, dtype):
     assert abs(loss.item() - loss_ref.item()) <= 1e-6 * max(1.0, abs(loss_ref.item()))
     tol = 1e-9 if dtype == torch.float64 else 2e-4
     assert torch.allclose(xg.grad.cpu().double(), xr.grad.double(), rtol=tol, atol=tol * xr.grad.abs().max().item())
+
+
+def test_training_step_config3(dev, books):
+    """BASELINE config 3: ground-truth preparation + decomposition (MOD:68-78, 119-133, 145-149), fusion
+    forward, the module's loss, backward to the Weights parameters - written against the drop-in names."""
+    import md_rdm_b200.computations as cp
+    from md_rdm_b200.rdm_net import Ordinal_Layer, Quantization, Weights
+    scales, B = (8, 16, 32), 4
+    x_d1, rel, weights = fr.synthetic_batch(B, scales, seed=303)
+    g = torch.Generator().manual_seed(304)
+    y_raw = 0.5 + 9.5 * torch.rand(B, 1, 226, 226, generator=g, dtype=torch.float64)
+    y_raw = y_raw * (torch.rand(B, 1, 226, 226, generator=g) > 0.05)         # 5 % invalid pixels
+    # ---- oracle (CPU, torch autograd)
+    w_ref = [w.clone().requires_grad_(True) for w in weights]
+    fwd = fr.fusion_forward(x_d1, rel, w_ref, books)
+    loss_ref, mse_ref, fine_ref, final_ref = fr.training_loss(y_raw, fwd["y_hat"])
+    loss_ref.backward()
+    # ---- product (GPU), the reference's own call sequence
+    quant = Quantization()
+    xd = x_d1.to(dev)
+    x_rel = [Ordinal_Layer(int(math.log2(s)) + 3, False, quant)(r.to(dev)) for s, r in zip(scales, rel)]
+    Bn, C, H, W = xd.size()
+    f_d1 = cp.decompose_depth_map([], torch.div(xd, cp.quick_gm(xd.view(Bn, H * W, 1), H).expand(Bn, H * W).view(Bn, 1, H, W)), 3)[::-1]
+    rows = [f_d1] + [cp.decompose_depth_map([], r, int(math.log2(r.shape[2])), relative_map=True)[::-1] for r in x_rel]
+    wl = Weights(vector_sizes=fr.slot_sizes(scales), use_cuda=True, relative_only=False)
+    with torch.no_grad():
+        for p_, w_ in zip(wl.weight_list, weights):
+            p_.copy_(w_)
+    y_hat = wl(cp.relative_fine_detail_matrix(rows, True))
+
+    def normalize(batch):                                            # MOD:145-149
+        b, c, h, w = batch.size()
+        return torch.div(batch, cp.quick_gm(batch.view(b, h * w, 1), h).expand(b, h * w).view(b, 1, h, w))
+
+    def depth2label_sid(depth, K=90.0, alpha=0.02, beta=10.0):       # utils.py:195-211 (caller glue, out of the path)
+        a, b_, k = torch.tensor(alpha, device=dev), torch.tensor(beta, device=dev), torch.tensor(K, device=dev)
+        label = k * torch.log(depth / a) / torch.log(b_ / a)
+        return torch.max(label, torch.zeros(label.shape, device=dev)).int()
+
+    y = cp.resize(y_raw.to(dev), 128)                                # MOD:68
+    y = (y * (y > 0)) + ((y <= 0) + 1e-4)                            # MOD:74-78
+    component_target = cp.decompose_depth_map([], normalize(y), 7)[::-1]                                  # MOD:123
+    ord_components = cp.decompose_depth_map([], normalize(depth2label_sid(cp.resize(y, 8))), 3)[::-1]    # MOD:126
+    component_target[0] = ord_components[0]
+    components, fine = cp.optimize_components(y_hat, component_target, True)                               # MOD:130
+    final = cp.recombination(components)                                                                   # MOD:132
+    mse = torch.nn.MSELoss()(final, y)                                                                     # MOD:89
+    loss = mse + fine
+    loss.backward()
+    assert _depth_ok(final.detach().cpu(), final_ref.detach())
+    assert abs(fine.item() - fine_ref.item()) <= 1e-5 * abs(fine_ref.item())
+    assert abs(loss.item() - loss_ref.item()) <= 1e-5 * abs(loss_ref.item())
+    for p_, r_ in zip(wl.weight_list, w_ref):
+        if p_.numel():
+            assert _rel_err(p_.grad.cpu(), r_.grad) < 1e-4
+
+
+def test_kitti_shaped_tiles_config5(dev, books):
+    """BASELINE config 5: a 228x912 KITTI input gives 8x29 coarse maps; the reference path is
+    square / power-of-two only, so the stress is defined as 4 square tiles per image, tile-major, ONE
+    arg-min group per call (B*4 images).  Batch 16 -> 64 tiles, scales 8/16/32."""
+    scales, B, T = (8, 16, 32), 16, 4
+    x_d1, rel, weights = fr.synthetic_batch(B * T, scales, seed=555)
+    ref = fr.fusion_forward(x_d1, rel, weights, books, want_intermediates=True)
+    plan = _run_plan(dev, x_d1, rel, weights, "map")
+    for si, s in enumerate(scales):
+        for pi, it in enumerate(ref["inter"][si]):
+            assert torch.equal(plan.bins[s][:, pi].cpu(), it["bins"])
+            assert int(plan.kstar[s].view(-1)[pi]) == it["kstar"]
+    assert _depth_ok(plan.depth.cpu(), ref["depth"])
+    # tiles of one image side by side: the 128x512 log-depth panorama of the stress definition
+    pano = plan.depth.view(B, T, 128, 128).permute(0, 2, 1, 3).reshape(B, 128, T * 128)
+    assert pano.shape == (16, 128, 512) and torch.equal(pano[:, :, 128:256], plan.depth.view(B, T, 128, 128)[:, 1])
