@@ -13,6 +13,9 @@
 //   fuse_tail               : RN:117-133 + network/module.py:132
 #include "rdm_common.cuh"
 
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+
 namespace rdm {
 
 constexpr int kMaxPtrs = 16;
@@ -64,6 +67,36 @@ __global__ void __launch_bounds__(256) gm_kernel(const TIn* __restrict__ t, int6
     for (int64_t i = threadIdx.x; i < n; i += blockDim.x) norm_out[b * n + i] = (TAcc)row[i] / gm;
 }
 
+// Large rows (the 128x128 ground truth, MOD:145-149: 16 384 f64 pow() per image) are split over a
+// thread-block CLUSTER of 8 CTAs: each CTA multiplies its eighth, the partial products are
+// exchanged through distributed shared memory (no workspace, no second launch), then every CTA
+// normalises its own eighth with 128-bit accesses.
+constexpr int kGmCluster = 8;
+template <typename TIn, typename TAcc>
+__global__ void __launch_bounds__(256) gm_cluster_kernel(const TIn* __restrict__ t, int64_t n, double e, TAcc* __restrict__ gm_out,
+                                                         TAcc* __restrict__ norm_out) {
+  __shared__ TAcc scratch[32];
+  __shared__ TAcc part;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int64_t b = blockIdx.x / kGmCluster;
+  const int64_t chunk = n / kGmCluster;
+  const TIn* row = t + b * n + rank * chunk;
+  TAcc prod = (TAcc)1;
+  for (int64_t i = threadIdx.x; i < chunk; i += blockDim.x) prod *= pow_as<TAcc>((TAcc)row[i], e);
+  const TAcc mine = block_prod<TAcc>(prod, scratch);
+  if (threadIdx.x == 0) part = mine;
+  cluster.sync();
+  TAcc gm = (TAcc)1;
+  for (int r = 0; r < kGmCluster; ++r) gm *= *cluster.map_shared_rank(&part, r);   // rank order: deterministic
+  cluster.sync();   // nobody leaves while its `part` may still be read
+  if (gm_out && rank == 0 && threadIdx.x == 0) gm_out[b] = gm;
+  if (norm_out) {
+    TAcc* dst = norm_out + b * n + rank * chunk;
+    for (int64_t i = threadIdx.x; i < chunk; i += blockDim.x) dst[i] = (TAcc)row[i] / gm;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Pyramid of one map held in shared memory D[] (level k at off_level(k)), level `top` filled by
 // the caller.  emit(k, idx, F) is called for every fine-detail value F_k[idx], k = top..1.
@@ -81,6 +114,64 @@ __device__ __forceinline__ void pyramid_down(double* D, int top, Emit emit) {
     for (int idx = threadIdx.x; idx < side * side; idx += blockDim.x) {
       int y = idx >> k, x = idx & (side - 1);
       emit(k, idx, cur[idx] / nxt[(y >> 1) * half + (x >> 1)]);   // CP:389 torch.div(dn, upsample(dn_1))
+    }
+  }
+}
+
+// Top level of a large map, banded over the chip: CTA (image, band) stages 10 source rows (8 own
+// + 1 halo on either side) with coalesced 128-bit loads, forms 4 rows of D_{n-1} and writes 8 rows
+// of F_n with 128-bit stores.  D_{n-1} is parked in the F_{n-1} slot of the output (same size);
+// the per-image kernel below then decomposes it in place.
+template <typename TIn>
+__global__ void __launch_bounds__(256) decompose_top_kernel(const TIn* __restrict__ in, int side, int n, int relative,
+                                                            double* __restrict__ out, int64_t n_images) {
+  extern __shared__ __align__(16) double S[];   // 10 rows x side
+  const int bands = side >> 3, half = side >> 1;
+  const int64_t img = blockIdx.x / bands;
+  const int band = blockIdx.x - (int)(img * bands);
+  const TIn* src = in + img * (int64_t)side * side;
+  const int base = relative ? 0 : 1;
+  double* fn = out + n_images * (base + off_fine(n)) + img * (int64_t)side * side;
+  double* dnext = out + n_images * (base + off_fine(n - 1)) + img * (int64_t)half * half;
+  const int r_lo = 8 * band - 1;
+  for (int i = threadIdx.x; i < 10 * side; i += blockDim.x) {
+    const int rr = i / side, c = i - rr * side;
+    const int r = min(max(r_lo + rr, 0), side - 1);
+    S[i] = (double)src[r * side + c];
+  }
+  __syncthreads();
+  double* dsm = S + 10 * side;                   // 4 rows x half of D_{n-1}
+  for (int i = threadIdx.x; i < 4 * half; i += blockDim.x) {
+    const int yy = i / half, x = i - yy * half;
+    // source rows 2y-1 .. 2y+2 with y = 4 band + yy are staged rows 2 yy .. 2 yy + 3 (clamped on load)
+    const double w[4] = {RDM_W0, RDM_W1, RDM_W1, RDM_W0};
+    double acc = 0.0;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const double* rowp = S + (2 * yy + a) * side;
+      double inner = 0.0;
+#pragma unroll
+      for (int bb = 0; bb < 4; ++bb) {
+        const int c = min(max(2 * x - 1 + bb, 0), side - 1);
+        inner = (bb == 0) ? __dmul_rn(rowp[c], w[0]) : fma(rowp[c], w[bb], inner);
+      }
+      acc = (a == 0) ? __dmul_rn(inner, w[0]) : fma(inner, w[a], acc);
+    }
+    dsm[i] = acc;
+    dnext[(4 * band + yy) * half + x] = acc;
+  }
+  __syncthreads();
+  const bool vec_ok = (reinterpret_cast<uintptr_t>(fn) & 15u) == 0;
+  for (int i = threadIdx.x; i < 8 * half; i += blockDim.x) {   // two output pixels per thread
+    const int rr = i / half, x2 = i - rr * half;
+    const double d = dsm[(rr >> 1) * half + x2];
+    const double* sp = S + (rr + 1) * side + 2 * x2;
+    double* dst = fn + (8 * band + rr) * side + 2 * x2;
+    if (vec_ok) {
+      stg_stream_f64x2(dst, sp[0] / d, sp[1] / d);
+    } else {   // level-major offsets are N * odd doubles when D_0 is present: only 8-byte aligned for odd N
+      dst[0] = sp[0] / d;
+      dst[1] = sp[1] / d;
     }
   }
 }
@@ -554,6 +645,25 @@ extern "C" int64_t rdm_pyramid_len(int32_t side, int32_t relative_map) {
 
 template <typename TIn, typename TAcc>
 static int gm_launch(const void* t, int64_t batch, int64_t n, double e, void* gm_out, void* norm_out, rdm_stream_t stream) {
+  if (n >= 4096 && n % kGmCluster == 0 && batch * kGmCluster < (1ll << 31)) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(batch * kGmCluster));
+    cfg.blockDim = dim3(256);
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kGmCluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t err = cudaLaunchKernelEx(&cfg, gm_cluster_kernel<TIn, TAcc>, (const TIn*)t, n, e, (TAcc*)gm_out, (TAcc*)norm_out);
+    if (err != cudaSuccess) {
+      set_error("gm_cluster_kernel: %s", cudaGetErrorString(err));
+      return (int)err;
+    }
+    return launch_status("gm_cluster_kernel");
+  }
   gm_kernel<TIn, TAcc><<<(unsigned)batch, 256, 0, (cudaStream_t)stream>>>((const TIn*)t, n, e, (TAcc*)gm_out, (TAcc*)norm_out);
   return launch_status("gm_kernel");
 }
@@ -591,7 +701,23 @@ extern "C" int rdm_decompose(const void* in, int32_t in_is_f64, int64_t n_images
   if (len == 0) return 0;
   const size_t smem = kPyrDoubles * sizeof(double);
   cudaError_t e;
-  if (in_is_f64) {
+  if (side == 128) {
+    // banded top level over the whole chip, then the per-image kernel on D_6 (parked in the F_6 slot)
+    const size_t tsm = (10 * 128 + 4 * 64) * sizeof(double);
+    const unsigned ctas = (unsigned)(n_images * 16);
+    RDM_REQUIRE(n_images * 16 < (1ll << 31), "rdm_decompose: too many images");
+    if (in_is_f64)
+      decompose_top_kernel<double><<<ctas, 256, tsm, (cudaStream_t)stream>>>((const double*)in, 128, 7, relative_map, pyramid_out, n_images);
+    else
+      decompose_top_kernel<float><<<ctas, 256, tsm, (cudaStream_t)stream>>>((const float*)in, 128, 7, relative_map, pyramid_out, n_images);
+    int rc = launch_status("decompose_top_kernel");
+    if (rc) return rc;
+    e = ensure_dyn_smem(decompose_kernel<double>, smem, smem_set_decompose_kernel_double_);
+    if (e == cudaSuccess) {
+      const double* d6 = pyramid_out + n_images * ((relative_map ? 0 : 1) + off_fine(6));
+      decompose_kernel<double><<<(unsigned)n_images, 256, smem, (cudaStream_t)stream>>>(d6, 64, 6, relative_map, pyramid_out, n_images);
+    }
+  } else if (in_is_f64) {
     e = ensure_dyn_smem(decompose_kernel<double>, smem, smem_set_decompose_kernel_double_);
     if (e == cudaSuccess)
       decompose_kernel<double><<<(unsigned)n_images, 256, smem, (cudaStream_t)stream>>>((const double*)in, side, n, relative_map, pyramid_out, n_images);
