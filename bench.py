@@ -253,24 +253,41 @@ def run_ours(args):
     from md_rdm_b200 import _cabi
     _cabi.load()   # fail loudly before anything is timed
 
-    from md_rdm_b200.fusion import capture_ring
+    from md_rdm_b200.fusion import capture_lane, capture_ring
     ab = algorithmic_bytes()
-    n_plans = args.ring
+    n_plans = max(args.ring // args.streams, 1) * args.streams   # whole plans per lane
     ring = build_ring(dev, rank, n_plans, "raw")
     ring_in_bytes = sum(p.h2d_bytes() for p in ring)
     streams = [torch.cuda.Stream() for _ in range(args.streams)]
     K, W = args.steps, args.warmup
     replay = lambda p: p.replay()   # noqa: E731
-    # one graph = one pass over the ring (n_plans steps on `streams` branches): the host launches
-    # K / n_plans graphs instead of K, so the timed region is GPU-bound, not Python-bound
-    ring_graph = capture_ring(ring, args.streams)
+    # `streams` independent lanes: lane j owns plans j, j+S, ... of the ring, one stream and one CUDA graph
+    # that runs its plans back to back (3 kernels each).  Lanes are replayed round-robin and never join, so
+    # several batches stay in flight and the host launches K / (ring/S) graphs instead of K.
+    S = args.streams
+    lanes = [capture_lane(ring[j::S]) for j in range(S)]
+    per_lane = n_plans // S
 
     def run_steps(k):
-        """Exactly k steps: whole-ring graphs, then single-plan graphs for the remainder."""
-        for _ in range(k // n_plans):
-            ring_graph.replay()
-        for i in range(k % n_plans):
-            ring[i].replay()
+        """Exactly k steps: lane graphs round-robin, then single-plan graphs for the remainder."""
+        cur = torch.cuda.current_stream()
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        for _, st in lanes:
+            st.wait_event(fork)
+        n_graphs = k // per_lane
+        for i in range(n_graphs):
+            g, st = lanes[i % S]
+            with torch.cuda.stream(st):
+                g.replay()
+        rem = k - n_graphs * per_lane
+        for i in range(rem):
+            with torch.cuda.stream(lanes[(n_graphs + i) % S][1]):
+                ring[((n_graphs + i) % S)].replay()
+        for _, st in lanes:
+            ev = torch.cuda.Event()
+            ev.record(st)
+            cur.wait_event(ev)
 
     def timed(k, fn):
         cur = torch.cuda.current_stream()
@@ -350,7 +367,8 @@ def run_ours(args):
                         "reconstruction -> bins, relative maps, y_hat, 128x128 f64 log-depth",
             "batch": BATCH, "scales": list(SCALES), "images_per_step_per_gpu": BATCH,
             "l2_policy": f"inputs larger than L2: ring of {n_plans} resident batches = {ring_in_bytes / 1e6:.0f} MB of inputs (L2 126 MB)",
-            "batches_in_flight": args.streams, "cuda_graph": f"one graph launch per {n_plans} steps (ring), 3 kernels per step",
+            "batches_in_flight": args.streams,
+            "cuda_graph": f"{args.streams} lanes (streams), one graph launch per {n_plans // args.streams} steps of a lane, 3 kernels per step",
             "launches_per_step": 3,
             "single_stream_ms_per_step": lat_ms,
             "algorithmic_bytes_per_image": ab,
@@ -424,9 +442,9 @@ def main():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--streams", type=int, default=4, help="batches in flight (CUDA streams)")
-    ap.add_argument("--ring", type=int, default=16, help="resident input batches (ring > L2)")
-    ap.add_argument("--cpu-images", type=int, default=8)
+    ap.add_argument("--streams", type=int, default=8, help="batches in flight (CUDA stream branches)")
+    ap.add_argument("--ring", type=int, default=32, help="resident input batches (ring > L2)")
+    ap.add_argument("--cpu-images", type=int, default=48)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -248,6 +248,24 @@ class FusionPlan:
         return self.run_pinned(use_graph)
 
 
+def capture_lane(plans: Sequence[FusionPlan], e2e: bool = False):
+    """A CUDA graph that runs `plans` one after the other on ONE stream, plus that stream.  Several lanes
+    replayed round-robin keep several batches in flight without any join between them (a fork/join graph
+    over the whole ring drains the GPU at every replay)."""
+    dev = plans[0].device
+    with torch.cuda.device(dev):
+        stream = torch.cuda.Stream()
+        with torch.cuda.stream(stream):
+            for p in plans:                 # warm-up outside capture
+                p._enqueue_e2e() if e2e else p.run()
+        stream.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=stream):
+            for p in plans:
+                p._enqueue_e2e() if e2e else p.run()
+    return g, stream
+
+
 def capture_ring(plans: Sequence[FusionPlan], n_streams: int, e2e: bool = False) -> torch.cuda.CUDAGraph:
     """ONE CUDA graph that runs every plan of `plans` once, plan i on branch i % n_streams (fork/join
     inside the capture): a whole ring of batches per host launch, so the host launch rate
