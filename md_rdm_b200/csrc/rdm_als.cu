@@ -118,6 +118,11 @@ __device__ __forceinline__ ulonglong2 lds_v2u64(uint32_t a) {
   return v;
 }
 
+#ifndef RDM_EXP
+#define RDM_EXP 0   // timing experiments only (wrong results): 1 no SSE, 2 no divisions, 4 no barriers, 16 no reduce-scatter
+#endif
+constexpr int kExp = RDM_EXP;
+
 // ---- packed f32x2 arithmetic (sm_100a FFMA2)
 using u64 = unsigned long long;
 __device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) {
@@ -130,6 +135,14 @@ __device__ __forceinline__ float2 as_f2(u64 v) { return *reinterpret_cast<float2
 __device__ __forceinline__ float hsum2(u64 a, u64 b) {
   const float2 fa = as_f2(a), fb = as_f2(b);
   return (fa.x + fa.y) + (fb.x + fb.y);
+}
+
+// 1/x for x in the normal range (|q|^2 + lambda, |p|^2 + lambda): MUFU.RCP plus one Newton step, the
+// same sequence the compiler emits for 1.0f / x minus its range-check branch and slow path.
+__device__ __forceinline__ float rcp_newton(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return fmaf(fmaf(-x, r, 1.0f), r, r);
 }
 
 // Thread <-> tile mapping of a unit.  lt = thread index inside the unit (0 .. 64G-1).
@@ -186,6 +199,11 @@ __device__ __forceinline__ void tile_dot(const float2 (&R)[4][8], uint32_t op, i
     }
     n0 = ffma2(x[k].x, x[k].x, n0);
     n1 = ffma2(x[k].y, x[k].y, n1);
+  }
+  if (kExp & 16) {
+    own = (hsum2(a[0][0], a[0][1]) + hsum2(a[1][0], a[1][1])) + (hsum2(a[2][0], a[2][1]) + hsum2(a[3][0], a[3][1]));
+    nrm = hsum2(n0, n1);
+    return;
   }
   own = reduce_scatter4(hsum2(a[0][0], a[0][1]), hsum2(a[1][0], a[1][1]), hsum2(a[2][0], a[2][1]), hsum2(a[3][0], a[3][1]), cb);
   nrm = group_sum4(hsum2(n0, n1));
@@ -384,6 +402,7 @@ __device__ __forceinline__ void load_unit(float2 (&R)[4][8], const AlsScaleDev& 
 // the loop (two rows per slot, so the scratch fits in the dead staging tile).
 constexpr double kDirectFrac = 0.005;
 
+
 // n_iter alternating iterations; returns p_{n_iter} of the row this thread owns.  RECORD: write
 // the SSE of iterations 0..n_iter to rec[] and p_1 to p1_out[].  E: (n_iter+1) x (NT/2+1) floats.
 template <int G, bool RECORD>
@@ -412,8 +431,9 @@ __device__ __forceinline__ float als_iterate(const float2 (&R)[4][8], AlsSmem& s
   __syncwarp();
   float s, Q;
   tile_dot(R, qop, m.cb, s, Q);                  // s = row sum, Q = 64
-  float invA = 1.0f / (Q + kLambda);             // torch.inverse of the 1x1 matrix |q|^2 + lambda
-  double r2 = 0.0, direct_below = 0.0;
+  float invA = rcp_newton(Q + kLambda);          // torch.inverse of the 1x1 matrix |q|^2 + lambda
+  double r2 = 0.0;
+  float r2h = 0.f, r2l = 0.f, direct_below = 0.f;
   if (RECORD) {
     double t[4];
 #pragma unroll
@@ -423,7 +443,9 @@ __device__ __forceinline__ float als_iterate(const float2 (&R)[4][8], AlsSmem& s
       for (int e = 0; e < 8; ++e) t[j] = fma((double)R[j][e].y, (double)R[j][e].y, fma((double)R[j][e].x, (double)R[j][e].x, t[j]));
     }
     r2 = reduce_scatter4(t[0], t[1], t[2], t[3], m.cb);
-    direct_below = kDirectFrac * r2;
+    r2h = (float)r2;                             // |R_i|^2 as an unevaluated f32 pair (exact to ~2^-48)
+    r2l = (float)(r2 - (double)r2h);
+    direct_below = (float)(kDirectFrac * r2);
     const float ones[4] = {1.f, 1.f, 1.f, 1.f};
     const float e0 = tile_sse(R, qop, ones, m.cb);   // k = 0: p = q = 1 (CP:55, CP:123)
     unit_barrier(bar_id, NT);                    // the staging tile (aliased by E) is dead from here on
@@ -439,12 +461,18 @@ __device__ __forceinline__ float als_iterate(const float2 (&R)[4][8], AlsSmem& s
     if (!RECORD && k == n_iter) break;
     sts_f32(ps + 4 * m.row_own, p);
     if (RECORD && k == 1) p1_out[m.row_own] = p;
-    unit_barrier(bar_id, NT);                    // A: p visible
+    if (!(kExp & 4)) unit_barrier(bar_id, NT);   // A: p visible
     float u, pseg;
     tile_dot(R, pop, m.cb, u, pseg);             // this row's share of q_{ib+cb}; |p segment r'|^2
-    if (RECORD) {
-      const double e = r2 + (double)p * ((double)p * (double)Q - 2.0 * (double)s);
-      float ef = fmaxf((float)e, 0.f);
+    if (RECORD && !(kExp & 1)) {
+      // e = |R_i|^2 + p (p |q|^2 - 2 s) in f32 pair arithmetic (error-free product and sum): same
+      // ~1e-7 |R_i|^2 absolute accuracy as an f64 evaluation - s and |q|^2 are f32 anyway - on the FP32 pipe
+      const float t = fmaf(p, Q, -2.0f * s);
+      const float ph = p * t, pl = fmaf(p, t, -ph);
+      const float sm1 = r2h + ph, bb = sm1 - r2h;
+      const float er = (r2h - (sm1 - bb)) + (ph - bb);
+      const float e = sm1 + (er + (r2l + pl));
+      float ef = fmaxf(e, 0.f);
       const bool want = e < direct_below;
       if (__any_sync(0xffffffffu, want)) {       // qw still holds q_{k-1}
         float pj[4];
@@ -460,7 +488,7 @@ __device__ __forceinline__ float als_iterate(const float2 (&R)[4][8], AlsSmem& s
     if constexpr (G == 4) {
       if (m.lw < 4 && m.lane == 0) sts_f32(ppart + 4 * m.rp, pseg);
     }
-    unit_barrier(bar_id, NT);                    // B: q partials (and |p|^2 segments) visible
+    if (!(kExp & 4)) unit_barrier(bar_id, NT);   // B: q partials (and |p|^2 segments) visible
     if (k == n_iter) break;
     // every warp finalises q for itself (no further barrier)
     float npp = pseg, u0, u1;
@@ -476,13 +504,13 @@ __device__ __forceinline__ float als_iterate(const float2 (&R)[4][8], AlsSmem& s
       u0 = lds_f32(qpart + 4 * (64 * unit + m.lane));
       u1 = lds_f32(qpart + 4 * (64 * unit + m.lane + 32));
     }
-    const float invB = 1.0f / (npp + kLambda);
+    const float invB = (kExp & 2) ? (npp + kLambda) * 1e-4f : rcp_newton(npp + kLambda);
     __syncwarp();
     sts_f32(qw + 4 * m.lane, u0 * invB);
     sts_f32(qw + 4 * m.lane + 128, u1 * invB);
     __syncwarp();
     tile_dot(R, qop, m.cb, s, Q);
-    invA = 1.0f / (Q + kLambda);
+    invA = (kExp & 2) ? (Q + kLambda) * 1e-2f : rcp_newton(Q + kLambda);
   }
 #ifdef RDM_TIMING
   if (RECORD && lt == 0 && unit == 0 && blockIdx.x % 37 == 0) printf("  block %d loop %lld cycles for %d iterations\n", blockIdx.x, clock64() - tl0, n_iter);
