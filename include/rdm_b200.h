@@ -218,6 +218,29 @@ int rdm_fuse_tail(const int64_t* x_d1, const float* const* rel, const int32_t* s
 /* number of f32 weights rdm_fuse_tail expects for these relative decoder sides (-1 = bad sides) */
 int64_t rdm_fuse_tail_weight_count(const int32_t* sides, int32_t n_rel);
 
+/* ------------------------------------------------------------------ SURVEY 8f "next": DORN head + ordinal loss */
+
+/* RN:313-345 Ordinal_Layer.DornOrdinalRegression: x (N,2K,H,W) f32 ->
+ * ord_out (N,K,H,W) f64 = softmax over each (even, odd) channel pair of clamp(x, 1e-8, 1e4), odd member;
+ * decode_out (N,H*W) i64 = #{k : ord > 0.5}.  HW = H*W <= 8192. */
+int rdm_dorn_regression_f32(const float* x, int64_t n_images, int32_t K, int32_t HW,
+                            int64_t* decode_out, double* ord_out, rdm_stream_t stream);
+/* backward of the above w.r.t. x (grad_x (N,2K,H,W) f32, fully overwritten). */
+int rdm_dorn_regression_bwd(const float* x, const double* ord, const double* grad_ord,
+                            int64_t n_images, int32_t K, int32_t HW, float* grad_x,
+                            rdm_stream_t stream);
+
+/* loss.py:17-59 Ordinal_Loss.calc: ord (N,K,H,W) f64, target (N,H*W) i32 SID labels ->
+ * loss_out[0] = -(sum_{k<=t} log(f32(clamp(ord))) + sum_{k>t} log(f32(clamp(1-ord)))) / (N H W), f32.
+ * ws: caller workspace of rdm_ordinal_loss_ws_doubles() f64 values. */
+int rdm_ordinal_loss_f64(const double* ord, const int32_t* target, int64_t n_images, int32_t K,
+                         int32_t HW, double* ws, float* loss_out, rdm_stream_t stream);
+int64_t rdm_ordinal_loss_ws_doubles(void);
+/* backward: grad_ord (N,K,H,W) f64 from grad_loss (device f32 scalar). */
+int rdm_ordinal_loss_bwd(const double* ord, const int32_t* target, const float* grad_loss,
+                         int64_t n_images, int32_t K, int32_t HW, double* grad_ord,
+                         rdm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,166 @@
+// SURVEY 8f "next", rank 1: the step immediately before the fusion path (it produces x_d1) and the
+// other loss of the training step.
+//   dorn_regression (+bwd) : RN:313-345 Ordinal_Layer.DornOrdinalRegression
+//   ordinal_loss (+bwd)    : loss.py:17-59 Ordinal_Loss.calc
+// Both are streaming kernels bounded by HBM bandwidth: x (N,2K,H,W) f32 is read once, the ordinal
+// probabilities (N,K,H,W) f64 written once; the reference materialises six (N,K,H,W)-sized
+// temporaries (clones, cat, clamp, double, softmax, clone) and, in the loss, an (N,K,H,W) index
+// tensor filled by a Python loop over K plus two boolean masks.
+#include "rdm_common.cuh"
+
+namespace rdm {
+
+constexpr double kClampLo = 1e-8, kClampHi = 1e4;   // RN:334 torch.clamp(C, min=1e-8, max=1e4)
+
+// softmax over the pair (A, B) as ATen computes it: exp(x - max) / sum, in f64; returns P(B).
+__device__ __forceinline__ double pair_softmax_b(double a, double b) {
+  const double m = fmax(a, b);
+  const double ea = exp(a - m), eb = exp(b - m);
+  return eb / (ea + eb);
+}
+
+// One CTA per image: ord[n,k,hw] = softmax(clamp(x[n,2k,hw]), clamp(x[n,2k+1,hw]))[1] (f64),
+// decode[n,hw] = #{k : ord > 0.5}.  hw is the fastest index of both tensors: coalesced.
+__global__ void __launch_bounds__(256) dorn_regression_kernel(const float* __restrict__ x, int K, int HW, int64_t* __restrict__ decode,
+                                                              double* __restrict__ ord) {
+  extern __shared__ int cnt[];   // HW counters
+  const int64_t n = blockIdx.x;
+  for (int i = threadIdx.x; i < HW; i += blockDim.x) cnt[i] = 0;
+  __syncthreads();
+  const float* xn = x + n * 2 * (int64_t)K * HW;
+  double* on = ord + n * (int64_t)K * HW;
+  for (int idx = threadIdx.x; idx < K * HW; idx += blockDim.x) {
+    const int k = idx / HW, hw = idx - k * HW;
+    const double a = fmin(fmax((double)xn[(2 * k) * (int64_t)HW + hw], kClampLo), kClampHi);
+    const double b = fmin(fmax((double)xn[(2 * k + 1) * (int64_t)HW + hw], kClampLo), kClampHi);
+    const double p = pair_softmax_b(a, b);
+    on[idx] = p;
+    if (p > 0.5) atomicAdd(&cnt[hw], 1);   // RN:342 sum(ord_c1 > 0.5)
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < HW; i += blockDim.x) decode[n * HW + i] = cnt[i];
+}
+
+// backward: d ord / dB = ord (1 - ord), d ord / dA = -ord (1 - ord), gated by the clamp (RN:334).
+__global__ void __launch_bounds__(256) dorn_regression_bwd_kernel(const float* __restrict__ x, const double* __restrict__ ord,
+                                                                  const double* __restrict__ g_ord, int64_t total, int K, int HW,
+                                                                  float* __restrict__ gx) {
+  for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
+    const int hw = (int)(o % HW);
+    const int64_t nk = o / HW;
+    const int k = (int)(nk % K);
+    const int64_t n = nk / K;
+    const int64_t ia = (n * 2 * K + 2 * k) * HW + hw, ib = ia + HW;
+    const double p = ord[o];
+    const double g = g_ord[o] * p * (1.0 - p);
+    const double a = (double)x[ia], b = (double)x[ib];
+    gx[ia] = (a >= kClampLo && a <= kClampHi) ? (float)(-g) : 0.f;
+    gx[ib] = (b >= kClampLo && b <= kClampHi) ? (float)g : 0.f;
+  }
+}
+
+// loss.py:41-57: -( sum_{k<=t} log(clamp(ord).float()) + sum_{k>t} log(clamp(1-ord).float()) ) / (N H W)
+__global__ void __launch_bounds__(256) ordinal_loss_kernel(const double* __restrict__ ord, const int32_t* __restrict__ target, int64_t total,
+                                                           int K, int HW, double* __restrict__ partial) {
+  __shared__ double part[8];
+  double acc = 0.0;
+  for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
+    const int hw = (int)(o % HW);
+    const int64_t nk = o / HW;
+    const int k = (int)(nk % K);
+    const int64_t n = nk / K;
+    const int t = target[n * HW + hw];
+    const double p = ord[o];
+    const double v = (k <= t) ? p : 1.0 - p;
+    acc += (double)logf((float)fmin(fmax(v, 1e-8), 1e8));
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += part[i];
+    partial[blockIdx.x] = t;
+  }
+}
+
+__global__ void ordinal_loss_finish_kernel(const double* __restrict__ partial, int n_partial, double scale, float* __restrict__ loss) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < n_partial; ++i) t += partial[i];   // fixed order: deterministic
+    *loss = (float)(t * scale);
+  }
+}
+
+__global__ void __launch_bounds__(256) ordinal_loss_bwd_kernel(const double* __restrict__ ord, const int32_t* __restrict__ target,
+                                                               const float* __restrict__ g_loss, int64_t total, int K, int HW, double scale,
+                                                               double* __restrict__ g_ord) {
+  const double g = (double)g_loss[0] * scale;
+  for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
+    const int hw = (int)(o % HW);
+    const int64_t nk = o / HW;
+    const int k = (int)(nk % K);
+    const int64_t n = nk / K;
+    const int t = target[n * HW + hw];
+    const double p = ord[o];
+    const double v = (k <= t) ? p : 1.0 - p;
+    // d/dv log(float(clamp(v))) = 1/v inside the clamp range, 0 outside; dv/dp = +1 (k<=t) or -1
+    double d = (v >= 1e-8 && v <= 1e8) ? 1.0 / (double)(float)v : 0.0;
+    g_ord[o] = g * ((k <= t) ? d : -d);
+  }
+}
+
+static int grid_cap2(int64_t items) {
+  int64_t blocks = (items + 255) / 256;
+  if (blocks > (int64_t)kNumSMs * 8) blocks = (int64_t)kNumSMs * 8;
+  return blocks < 1 ? 1 : (int)blocks;
+}
+
+}  // namespace rdm
+
+using namespace rdm;
+
+extern "C" int rdm_dorn_regression_f32(const float* x, int64_t n_images, int32_t K, int32_t HW, int64_t* decode_out, double* ord_out,
+                                       rdm_stream_t stream) {
+  RDM_REQUIRE(x && decode_out && ord_out, "rdm_dorn_regression_f32: null pointer");
+  RDM_REQUIRE(K >= 1 && HW >= 1 && HW <= 8192, "rdm_dorn_regression_f32: bad K / HW");
+  RDM_REQUIRE(n_images >= 0 && n_images < (1ll << 31), "rdm_dorn_regression_f32: bad n_images");
+  if (n_images == 0) return 0;
+  dorn_regression_kernel<<<(unsigned)n_images, 256, HW * sizeof(int), (cudaStream_t)stream>>>(x, K, HW, decode_out, ord_out);
+  return launch_status("dorn_regression_kernel");
+}
+
+extern "C" int rdm_dorn_regression_bwd(const float* x, const double* ord, const double* grad_ord, int64_t n_images, int32_t K, int32_t HW,
+                                       float* grad_x, rdm_stream_t stream) {
+  RDM_REQUIRE(x && ord && grad_ord && grad_x, "rdm_dorn_regression_bwd: null pointer");
+  RDM_REQUIRE(K >= 1 && HW >= 1 && n_images >= 0, "rdm_dorn_regression_bwd: bad shape");
+  if (n_images == 0) return 0;
+  const int64_t total = n_images * K * HW;
+  dorn_regression_bwd_kernel<<<grid_cap2(total), 256, 0, (cudaStream_t)stream>>>(x, ord, grad_ord, total, K, HW, grad_x);
+  return launch_status("dorn_regression_bwd_kernel");
+}
+
+extern "C" int64_t rdm_ordinal_loss_ws_doubles(void) { return (int64_t)kNumSMs * 8; }
+
+extern "C" int rdm_ordinal_loss_f64(const double* ord, const int32_t* target, int64_t n_images, int32_t K, int32_t HW, double* ws,
+                                    float* loss_out, rdm_stream_t stream) {
+  RDM_REQUIRE(ord && target && ws && loss_out, "rdm_ordinal_loss_f64: null pointer");
+  RDM_REQUIRE(K >= 1 && HW >= 1 && n_images >= 1, "rdm_ordinal_loss_f64: bad shape");
+  const int64_t total = n_images * K * HW;
+  const int grid = grid_cap2(total);
+  ordinal_loss_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(ord, target, total, K, HW, ws);
+  int rc = launch_status("ordinal_loss_kernel");
+  if (rc) return rc;
+  ordinal_loss_finish_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(ws, grid, -1.0 / ((double)n_images * HW), loss_out);
+  return launch_status("ordinal_loss_finish_kernel");
+}
+
+extern "C" int rdm_ordinal_loss_bwd(const double* ord, const int32_t* target, const float* grad_loss, int64_t n_images, int32_t K,
+                                    int32_t HW, double* grad_ord, rdm_stream_t stream) {
+  RDM_REQUIRE(ord && target && grad_loss && grad_ord, "rdm_ordinal_loss_bwd: null pointer");
+  RDM_REQUIRE(K >= 1 && HW >= 1 && n_images >= 1, "rdm_ordinal_loss_bwd: bad shape");
+  const int64_t total = n_images * K * HW;
+  ordinal_loss_bwd_kernel<<<grid_cap2(total), 256, 0, (cudaStream_t)stream>>>(ord, target, grad_loss, total, K, HW,
+                                                                              -1.0 / ((double)n_images * HW), grad_ord);
+  return launch_status("ordinal_loss_bwd_kernel");
+}

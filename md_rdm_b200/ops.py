@@ -705,3 +705,101 @@ def _zero_setup_2(ctx, inputs, output):
 pair_pages.register_autograd(_zero_grad_backward(2, 2), setup_context=_zero_setup_2)
 lloyd_quantize.register_autograd(_zero_grad_backward(1, 3), setup_context=_zero_setup_1)
 als_rank1.register_autograd(_zero_grad_backward(1, 10), setup_context=_zero_setup_1)
+
+
+# ============================================================================ SURVEY 8f "next": DORN head + ordinal loss
+@torch.library.custom_op("rdm::dorn_regression", mutates_args=())
+def dorn_regression(x: Tensor) -> Tuple[Tensor, Tensor]:
+    """RN:313-345: x (N,2K,H,W) f32 -> (decode (N,1,H,W) int64, ord (N,K,H,W) f64)."""
+    _need_cuda("dorn_regression", x)
+    if x.dim() != 4 or x.shape[1] % 2 or x.dtype != torch.float32:
+        raise RuntimeError("rdm::dorn_regression: expected (N,2K,H,W) f32")
+    N, C, H, W = x.shape
+    decode = torch.empty((N, 1, H, W), dtype=torch.int64, device=x.device)
+    ord_ = torch.empty((N, C // 2, H, W), dtype=torch.float64, device=x.device)
+    with torch.cuda.device(x.device):
+        check(load().rdm_dorn_regression_f32(_p(x.contiguous()), N, C // 2, H * W, _p(decode), _p(ord_), _stream()), "rdm_dorn_regression_f32")
+    return decode, ord_
+
+
+@dorn_regression.register_fake
+def _(x):
+    N, C, H, W = x.shape
+    return x.new_empty((N, 1, H, W), dtype=torch.int64), x.new_empty((N, C // 2, H, W), dtype=torch.float64)
+
+
+@torch.library.custom_op("rdm::dorn_regression_bwd", mutates_args=())
+def dorn_regression_bwd(x: Tensor, ord_: Tensor, grad_ord: Tensor) -> Tensor:
+    N, C, H, W = x.shape
+    gx = torch.empty_like(x, memory_format=torch.contiguous_format)
+    with torch.cuda.device(x.device):
+        check(load().rdm_dorn_regression_bwd(_p(x.contiguous()), _p(ord_.contiguous()), _p(grad_ord.double().contiguous()), N, C // 2, H * W,
+                                             _p(gx), _stream()), "rdm_dorn_regression_bwd")
+    return gx
+
+
+@dorn_regression_bwd.register_fake
+def _(x, ord_, grad_ord):
+    return torch.empty_like(x)
+
+
+def _dorn_setup(ctx, inputs, output):
+    ctx.save_for_backward(inputs[0], output[1])
+
+
+def _dorn_backward(ctx, g_decode, g_ord):
+    x, ord_ = ctx.saved_tensors
+    if g_ord is None:
+        return torch.zeros_like(x)
+    return torch.ops.rdm.dorn_regression_bwd(x, ord_, g_ord)
+
+
+dorn_regression.register_autograd(_dorn_backward, setup_context=_dorn_setup)
+
+
+@torch.library.custom_op("rdm::ordinal_loss", mutates_args=())
+def ordinal_loss(ord_: Tensor, target: Tensor) -> Tensor:
+    """loss.py:17-59: ord (N,K,H,W) f64, target (N,1,H,W) integer SID labels -> 0-d f32 loss."""
+    _need_cuda("ordinal_loss", ord_, target)
+    if ord_.dim() != 4 or ord_.dtype != torch.float64 or target.numel() != ord_.shape[0] * ord_.shape[2] * ord_.shape[3]:
+        raise RuntimeError("rdm::ordinal_loss: expected ord (N,K,H,W) f64 and target (N,1,H,W)")
+    N, K, H, W = ord_.shape
+    lib = load()
+    ws = torch.empty((lib.rdm_ordinal_loss_ws_doubles(),), dtype=torch.float64, device=ord_.device)
+    loss = torch.empty((), dtype=torch.float32, device=ord_.device)
+    with torch.cuda.device(ord_.device):
+        check(lib.rdm_ordinal_loss_f64(_p(ord_.contiguous()), _p(target.to(torch.int32).contiguous()), N, K, H * W, _p(ws), _p(loss), _stream()),
+              "rdm_ordinal_loss_f64")
+    return loss
+
+
+@ordinal_loss.register_fake
+def _(ord_, target):
+    return ord_.new_empty((), dtype=torch.float32)
+
+
+@torch.library.custom_op("rdm::ordinal_loss_bwd", mutates_args=())
+def ordinal_loss_bwd(ord_: Tensor, target: Tensor, grad_loss: Tensor) -> Tensor:
+    N, K, H, W = ord_.shape
+    g = torch.empty_like(ord_, memory_format=torch.contiguous_format)
+    with torch.cuda.device(ord_.device):
+        check(load().rdm_ordinal_loss_bwd(_p(ord_.contiguous()), _p(target.to(torch.int32).contiguous()), _p(grad_loss.float().contiguous()),
+                                          N, K, H * W, _p(g), _stream()), "rdm_ordinal_loss_bwd")
+    return g
+
+
+@ordinal_loss_bwd.register_fake
+def _(ord_, target, grad_loss):
+    return torch.empty_like(ord_)
+
+
+def _oloss_setup(ctx, inputs, output):
+    ctx.save_for_backward(inputs[0], inputs[1])
+
+
+def _oloss_backward(ctx, g):
+    ord_, target = ctx.saved_tensors
+    return torch.ops.rdm.ordinal_loss_bwd(ord_, target, g), None
+
+
+ordinal_loss.register_autograd(_oloss_backward, setup_context=_oloss_setup)

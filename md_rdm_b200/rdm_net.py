@@ -2,9 +2,8 @@
 `Ordinal_Layer` (RN:237-396), `Quantization` (RN:397-442), `Weights` (RN:443-491).
 
 Same constructors, method names and return conventions; the arithmetic runs in the sm_100a
-kernels behind `torch.ops.rdm.*`.  The DORN branch of `Ordinal_Layer` (RN:313-345) is the
-producer of the ordinary map and is outside the fusion path: it stays in PyTorch, verbatim
-semantics.
+kernels behind `torch.ops.rdm.*`, including the DORN branch of `Ordinal_Layer` (RN:313-345), the
+producer of the ordinary map (SURVEY 8f "next" row; `md_rdm_b200/loss.py` has the matching loss).
 """
 from __future__ import annotations
 
@@ -72,17 +71,11 @@ class Ordinal_Layer(nn.Module):
             return relative_depths.view(N, C, W)
         return values.view(N, C, W)
 
-    # ------------------------------------------------------------------ RN:313-345 (PyTorch, out of the fusion path)
+    # ------------------------------------------------------------------ RN:313-345 (SURVEY 8f "next" row)
     def DornOrdinalRegression(self, x):
-        N, C, H, W = x.size()
-        ord_num = C // 2
-        A = x[:, ::2, :, :].clone().view(N, 1, ord_num * H * W)
-        B = x[:, 1::2, :, :].clone().view(N, 1, ord_num * H * W)
-        Cc = torch.clamp(torch.cat((A, B), dim=1), min=1e-8, max=1e4).double()
-        ord_c = nn.functional.softmax(Cc, dim=1)
-        ord_c1 = ord_c[:, 1, :].clone().view(-1, ord_num, H, W)
-        decode_c = torch.sum((ord_c1 > 0.5), dim=1).view(-1, 1, H, W)
-        return decode_c, ord_c1
+        """(decode_c (N,1,H,W) int64, ord_c1 (N,K,H,W) f64): one kernel instead of two clones, cat,
+        clamp, double, softmax, clone, compare, sum."""
+        return R.dorn_regression(x.float())
 
     # ------------------------------------------------------------------ RN:347-396
     def forward(self, x):

@@ -399,3 +399,27 @@ def training_loss(y_raw: torch.Tensor, y_hat: Sequence[torch.Tensor]):
     final = recombination(list(y_hat))                               # MOD:132
     mse = torch.nn.MSELoss()(final, y)                               # MOD:89
     return mse + fine, mse, fine, final
+
+
+# --------------------------------------------------------------------------- SURVEY 8f "next": DORN head + ordinal loss
+def dorn_regression(x: torch.Tensor):
+    """RN:313-345.  x (N,2K,H,W) -> (decode (N,1,H,W) int64, ord (N,K,H,W) f64)."""
+    N, C, H, W = x.size()
+    K = C // 2
+    A = x[:, ::2, :, :].clone().view(N, 1, K * H * W)
+    B = x[:, 1::2, :, :].clone().view(N, 1, K * H * W)
+    Cc = torch.clamp(torch.cat((A, B), dim=1), min=1e-8, max=1e4).double()
+    ord_c1 = torch.nn.functional.softmax(Cc, dim=1)[:, 1, :].clone().view(-1, K, H, W)
+    return torch.sum((ord_c1 > 0.5), dim=1).view(-1, 1, H, W), ord_c1
+
+
+def ordinal_loss(ord_labels: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    """loss.py:17-59 with the K-loop written as an arange (same index tensor)."""
+    N, C, H, W = ord_labels.size()
+    Kidx = torch.arange(C, dtype=torch.int).view(1, C, 1, 1).expand(N, C, H, W)
+    mask_0 = (Kidx <= target).detach()
+    mask_1 = (Kidx > target).detach()
+    one = torch.ones(ord_labels[mask_1].size())
+    loss = torch.sum(torch.log(torch.clamp(ord_labels[mask_0], min=1e-8, max=1e8).float())) \
+        + torch.sum(torch.log(torch.clamp(one - ord_labels[mask_1], min=1e-8, max=1e8).float()))
+    return loss / (-(N * H * W))

@@ -595,3 +595,47 @@ def test_kitti_shaped_tiles_config5(dev, books):
     pano = plan.depth.view(B, T, 128, 128).permute(0, 2, 1, 3).reshape(B, 128, T * 128)
     assert pano.shape == (16, 128, 512)
     assert _eq_nan(pano[:, :, 128:256], plan.depth.view(B, T, 128, 128)[:, 1])
+
+
+def test_full_model_config1_golden(dev, books):
+    """BASELINE config 1: what the reference's full model (CNN included, decoders 1,6,7,8,9, batch 1) feeds
+    into and gets out of the fusion path, against the CUDA path (fused plan and drop-in names)."""
+    import md_rdm_b200.computations as cp
+    from md_rdm_b200.rdm_net import Ordinal_Layer, Quantization
+    g = load_golden("full_model_b1.npz")
+    scales = (8, 16, 32, 64)
+    x_d1 = torch.from_numpy(g["x_d1"])
+    rel = [torch.from_numpy(g[f"rel_in_{s}"]) for s in scales]          # real decoder outputs: partly negative
+    weights = [torch.from_numpy(g[f"w_{i}"]) for i in range(7)]
+    plan = _run_plan(dev, x_d1, rel, weights, "map")
+    for s in scales:
+        assert _rel_err(plan.rel[s].cpu(), torch.from_numpy(g[f"rel_out_{s}"])) < REL_MAP, s
+    for i, y in enumerate(plan.yhat_list()):
+        assert torch.allclose(y.cpu(), torch.from_numpy(g[f"yhat_{i}"]), rtol=0, atol=5e-5), i
+    assert _depth_ok(plan.depth.cpu(), torch.from_numpy(g["depth"]))
+    quant = Quantization()
+    for s, r in zip(scales, rel):
+        out = Ordinal_Layer(int(math.log2(s)) + 3, False, quant)(r.to(dev))
+        assert _rel_err(out.cpu(), torch.from_numpy(g[f"rel_out_{s}"])) < REL_MAP, s
+
+
+def test_dorn_regression_and_ordinal_loss_golden(dev):
+    """SURVEY 8f "next" row: DORN head (RN:313-345) + Ordinal_Loss (loss.py:17-59), forward and backward,
+    against the reference's own outputs and autograd gradient."""
+    from md_rdm_b200.loss import Ordinal_Loss, depth2label_sid
+    from md_rdm_b200.rdm_net import Ordinal_Layer
+    g = load_golden("dorn_loss.npz")
+    x = torch.from_numpy(g["x"]).to(dev).requires_grad_(True)
+    decode, ord_ = Ordinal_Layer(1, True, None)(x)
+    assert decode.dtype == torch.int64 and torch.equal(decode.cpu(), torch.from_numpy(g["decode"]))   # integer output: exact
+    assert ord_.dtype == torch.float64 and torch.allclose(ord_.detach().cpu(), torch.from_numpy(g["ord"]), rtol=1e-14, atol=1e-300)
+    target = torch.from_numpy(g["target"]).to(dev)
+    loss = Ordinal_Loss().calc(ord_, target, cuda=True)
+    assert loss.dtype == torch.float32 and abs(loss.item() - float(g["loss"])) <= 2e-6 * abs(float(g["loss"]))
+    loss.backward()
+    assert torch.allclose(x.grad.cpu(), torch.from_numpy(g["grad_x"]), rtol=1e-4, atol=1e-9)
+    # SID labels of a depth map (utils.py:195-211) on the device
+    gen = torch.Generator().manual_seed(808)
+    torch.randn(3, 180, 8, 8, generator=gen)
+    depth = 0.5 + 9.5 * torch.rand(3, 1, 8, 8, generator=gen, dtype=torch.float64)
+    assert torch.equal(depth2label_sid(depth.to(dev)).cpu(), torch.from_numpy(g["target"]))

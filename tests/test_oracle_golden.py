@@ -100,3 +100,30 @@ def test_properties():
     m = fr.retile_pages(pages)
     assert m.shape == (1, 1, 32, 32) and set(m.unique().tolist()) == {0.0, 1.0}
     assert torch.equal(m[0, 0, :16, :16], pages[0][0, 0]) and torch.equal(m[0, 0, 16:, 16:], pages[1][0, 0])
+
+
+def test_full_model_config1(books):
+    """BASELINE config 1: decoder outputs of the reference's full model (random init, batch 1, synthetic RGB,
+    relative decoders 6-9 re-enabled; tools/make_golden_full_model.py) -> y_hat and log-depth."""
+    g = load_golden("full_model_b1.npz")
+    scales = (8, 16, 32, 64)
+    x_d1 = torch.from_numpy(g["x_d1"])
+    rel = [torch.from_numpy(g[f"rel_in_{s}"]) for s in scales]
+    weights = [torch.from_numpy(g[f"w_{i}"]) for i in range(7)]
+    o = fr.fusion_forward(x_d1, rel, weights, books)
+    for s, r in zip(scales, o["rel"]):
+        assert (r - torch.from_numpy(g[f"rel_out_{s}"])).abs().max().item() <= 1e-6
+    for i, y in enumerate(o["y_hat"]):
+        assert torch.allclose(y, torch.from_numpy(g[f"yhat_{i}"]), rtol=0, atol=1e-6)
+    assert (o["depth"] - torch.from_numpy(g["depth"])).abs().max().item() <= 1e-6
+
+
+def test_dorn_and_ordinal_loss_golden():
+    g = load_golden("dorn_loss.npz")
+    x = torch.from_numpy(g["x"]).requires_grad_(True)
+    decode, ord_ = fr.dorn_regression(x)
+    assert torch.equal(decode, torch.from_numpy(g["decode"])) and torch.equal(ord_.detach(), torch.from_numpy(g["ord"]))
+    loss = fr.ordinal_loss(ord_, torch.from_numpy(g["target"]))
+    assert abs(loss.item() - float(g["loss"])) <= 1e-6 * abs(float(g["loss"]))
+    loss.backward()
+    assert torch.allclose(x.grad, torch.from_numpy(g["grad_x"]), rtol=1e-5, atol=1e-9)
