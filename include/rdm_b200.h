@@ -113,7 +113,9 @@ typedef struct rdm_als_scale {
   float* map_out;           /* optional (N,side,side) f32: CP:218-238 `reconstruct` re-tiling
                                (bug-compatible: only pages 0..side/16-1 reach the map) */
   float* ws;                /* REQUIRED workspace, N * rdm_als_ws_floats(rows, pages, limit) f32:
-                               per (image, page) the SSE record [limit+1] then p_1 [rows] */
+                               per (image, page) the SSE record [limit+1], then every iterate
+                               p_1..p_limit [limit][rows] (the arg-min is batch-wide, so the
+                               iterate to emit is only known after all images have finished) */
   float* record_out;        /* optional (N/group,P,limit+1) f32 rmse record (CP:53-61) */
   int32_t* kstar_out;       /* optional (N/group,P) i32 selected iteration (CP:74, CP:143) */
 } rdm_als_scale_t;

@@ -24,9 +24,11 @@
 // rmse record (CP:53-61, CP:121-130): see the comment above kDirectFrac.  Per-unit SSE goes to
 // the workspace; the arg-min is over the mean of the whole reference batch ("group",
 // CP:172-173), so phase 1 (second launch) sums the group's records, picks the first minimum
-// (CP:74, CP:143) and emits p_k*.  p_1 is checkpointed by phase 0 (k* is 0 or 1 on every
-// realistic input); for k* >= 2 phase 1 replays k* iterations from the source.
-// No kernel waits on another: two plain launches.
+// (CP:74, CP:143) and emits p_k*.  Phase 0 streams every iterate p_1..p_limit to the workspace (one
+// 4-byte store per thread per iteration, ~100 KB per unit that mostly lives in L2): on noise-like
+// inputs k* is 0 or 1, but on the smooth maps a real decoder produces the record
+// plateaus and k* lands anywhere up to `limit` (tests/golden/README.md), so no iterate can be
+// dropped.  No kernel waits on another: two plain launches.
 //
 // Bound: per unit 2*limit*rows*64 FMA against rows*64*(4..8) input bytes = 25..100 FMA/byte:
 // FP32-issue / dependency-latency bound, not HBM bound (DESIGN.md "K3").
@@ -46,7 +48,7 @@ struct AlsScaleDev {
   const double* lvl;
   uint8_t* bins;
   float* values;
-  float* ws;          // per unit: [limit+1] SSE record, then [rows] p_1
+  float* ws;          // per unit: [limit+1] SSE record, then [limit][rows] iterates p_1..p_limit
   float* pages_out;
   float* map_out;
   float* record_out;
@@ -403,11 +405,12 @@ __device__ __forceinline__ void load_unit(float2 (&R)[4][8], const AlsScaleDev& 
 constexpr double kDirectFrac = 0.005;
 
 
-// n_iter alternating iterations; returns p_{n_iter} of the row this thread owns.  RECORD: write
-// the SSE of iterations 0..n_iter to rec[] and p_1 to p1_out[].  E: (n_iter+1) x (NT/2+1) floats.
-template <int G, bool RECORD>
-__device__ __forceinline__ float als_iterate(const float2 (&R)[4][8], AlsSmem& sm, float* __restrict__ E, int unit, int lt, int n_iter,
-                                             float* __restrict__ rec, float* __restrict__ p1_out) {
+// n_iter alternating iterations.  Writes the SSE of iterations 0..n_iter to rec[] and the iterates
+// p_1..p_n_iter to hist[(k-1) * rows + row].  E: (n_iter+1) x (NT/2+1) floats of shared scratch.
+template <int G>
+__device__ __forceinline__ void als_iterate(const float2 (&R)[4][8], AlsSmem& sm, float* __restrict__ E, int unit, int lt, int n_iter,
+                                            float* __restrict__ rec, float* __restrict__ hist) {
+  constexpr bool RECORD = true;
   constexpr int NW = 2 * G;
   constexpr int NT = 64 * G;
   constexpr int EH = NT / 2;                     // two rows (lanes l, l^4) share one slot
@@ -458,9 +461,8 @@ __device__ __forceinline__ float als_iterate(const float2 (&R)[4][8], AlsSmem& s
 #endif
   for (int k = 1; k <= n_iter; ++k) {
     p = s * invA;                                // (R q) @ inverse(A)
-    if (!RECORD && k == n_iter) break;
     sts_f32(ps + 4 * m.row_own, p);
-    if (RECORD && k == 1) p1_out[m.row_own] = p;
+    hist[(k - 1) * NT + m.row_own] = p;          // fire-and-forget: phase 1 picks p_k*
     if (!(kExp & 4)) unit_barrier(bar_id, NT);   // A: p visible
     float u, pseg;
     tile_dot(R, pop, m.cb, u, pseg);             // this row's share of q_{ib+cb}; |p segment r'|^2
@@ -530,7 +532,6 @@ __device__ __forceinline__ float als_iterate(const float2 (&R)[4][8], AlsSmem& s
       rec[k] = (float)((t0 + t1) + (t2 + t3));
     }
   }
-  return p;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -542,11 +543,11 @@ __device__ __forceinline__ void als_unit(const AlsParams& P, const AlsScaleDev& 
   const TileMap<G> m(lt);
   const int row = m.row_own;
   const int bar_id = (G == 4) ? 0 : 1 + unit;
-  const int ws_stride = sc.limit + 1 + ROWS;
+  const int64_t ws_stride = (int64_t)sc.limit + 1 + (int64_t)sc.limit * ROWS;
   float* ws = sc.ws + unit_idx * ws_stride;
-  float2 R[4][8];
 
   if constexpr (PHASE == 0) {
+    float2 R[4][8];
 #ifdef RDM_TIMING
     const long long t0 = clock64();
 #endif
@@ -554,7 +555,7 @@ __device__ __forceinline__ void als_unit(const AlsParams& P, const AlsScaleDev& 
 #ifdef RDM_TIMING
     const long long t1 = clock64();
 #endif
-    als_iterate<G, true>(R, sm, E, unit, lt, sc.limit, ws, ws + sc.limit + 1);
+    als_iterate<G>(R, sm, E, unit, lt, sc.limit, ws, ws + sc.limit + 1);
 #ifdef RDM_TIMING
     const long long t2 = clock64();
     if (lt == 0 && (unit_idx % 37) == 0)
@@ -570,7 +571,7 @@ __device__ __forceinline__ void als_unit(const AlsParams& P, const AlsScaleDev& 
     const double inv_cnt = 1.0 / ((double)P.group * (double)(ROWS * kCols));
     const int64_t gstride = (int64_t)sc.pages * ws_stride;
     for (int k = lt; k <= sc.limit; k += NT) {
-      const float* col = sc.ws + (g0 * sc.pages + pg) * (int64_t)ws_stride + k;
+      const float* col = sc.ws + (g0 * sc.pages + pg) * ws_stride + k;
       double t = 0.0;
       int b = 0;
       for (; b + 8 <= P.group; b += 8) {   // 8 independent loads in flight, summed in image order
@@ -599,15 +600,7 @@ __device__ __forceinline__ void als_unit(const AlsParams& P, const AlsScaleDev& 
         for (int k = lt; k <= sc.limit; k += NT) sc.record_out[gp * (sc.limit + 1) + k] = rm[k];
       if (sc.kstar_out && lt == 0) sc.kstar_out[gp] = kstar;
     }
-    float p;
-    if (kstar == 0) {
-      p = 1.0f;
-    } else if (kstar == 1) {
-      p = ws[sc.limit + 1 + row];
-    } else {   // rare: replay k* iterations from the source
-      load_unit<G>(R, sc, sm, tile, unit_idx, unit, lt, false);
-      p = als_iterate<G, false>(R, sm, nullptr, unit, lt, kstar, nullptr, nullptr);
-    }
+    const float p = (kstar == 0) ? 1.0f : ws[sc.limit + 1 + (int64_t)(kstar - 1) * ROWS + row];
     // ---- quick_gm(p, H) with H = rows: prod_i p_i^(1/H^2)  (CP:76, CP:146, CP:244-255)
     const float pw = (float)pow((double)p, 1.0 / ((double)ROWS * (double)ROWS));
     float prod = warp_prod(pw);
@@ -644,7 +637,7 @@ __global__ void __launch_bounds__(kAlsThreads, 2) als_kernel(const __grid_consta
     if ((int)blockIdx.x >= P.s[k].cta_begin) si = k;
   const AlsScaleDev& sc = P.s[si];
   const int tid = threadIdx.x;
-  if (sc.thr) {
+  if (PHASE == 0 && sc.thr) {   // phase 1 never quantises
     if (tid == 0) sm.sorted = 1;
     __syncthreads();
     if (tid < kThrPad) {
@@ -713,7 +706,7 @@ using namespace rdm;
 extern "C" int rdm_als_fused_phases(const rdm_als_scale_t*, int32_t, int64_t, int32_t, int32_t, rdm_stream_t);
 
 extern "C" int64_t rdm_als_ws_floats(int32_t rows, int32_t pages, int32_t limit) {
-  return (int64_t)pages * ((int64_t)limit + 1 + rows);
+  return (int64_t)pages * ((int64_t)limit + 1 + (int64_t)limit * rows);
 }
 
 extern "C" int rdm_als_fused(const rdm_als_scale_t* scales, int32_t n_scales, int64_t n_images, int32_t group,
@@ -784,9 +777,8 @@ extern "C" int rdm_als_fused_phases(const rdm_als_scale_t* scales, int32_t n_sca
                                                 : dyn1 + (size_t)4 * (scales[k].limit + 1) * 33 * sizeof(float);
     if (need > dyn) dyn = need;
   }
-  static size_t smem_set0[64], smem_set1[64];
+  static size_t smem_set0[64];
   cudaError_t e = ensure_dyn_smem(als_kernel<0>, dyn, smem_set0);
-  if (e == cudaSuccess) e = ensure_dyn_smem(als_kernel<1>, dyn1, smem_set1);
   if (e != cudaSuccess) {
     set_error("rdm_als_fused: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     return (int)e;
@@ -797,7 +789,7 @@ extern "C" int rdm_als_fused_phases(const rdm_als_scale_t* scales, int32_t n_sca
     if (rc) return rc;
   }
   if (phase_mask & 2) {
-    als_kernel<1><<<(unsigned)ctas, kAlsThreads, dyn1, (cudaStream_t)stream>>>(P);
+    als_kernel<1><<<(unsigned)ctas, kAlsThreads, 0, (cudaStream_t)stream>>>(P);
     return launch_status("als_kernel<select>");
   }
   return 0;

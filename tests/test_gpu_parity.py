@@ -599,8 +599,13 @@ def test_kitti_shaped_tiles_config5(dev, books):
 
 def test_full_model_config1_golden(dev, books):
     """BASELINE config 1: what the reference's full model (CNN included, decoders 1,6,7,8,9, batch 1) feeds
-    into and gets out of the fusion path, against the CUDA path (fused plan and drop-in names)."""
-    import md_rdm_b200.computations as cp
+    into and gets out of the fusion path, against the CUDA path (fused plan and drop-in names).
+
+    Real decoder outputs are smooth, so the ALS record PLATEAUS: from iteration ~3 on its f32 values differ
+    by one ulp, and which of them is the first minimum is decided by summation-order noise (the reference
+    itself would pick another index with another BLAS).  Parity is therefore stated as: bins bit-exact;
+    record equal to 1e-6; our k* is a tie of the reference's own record (within 2e-7 relative of its
+    minimum); and maps, y_hat, log-depth match the reference algorithm evaluated at that k*."""
     from md_rdm_b200.rdm_net import Ordinal_Layer, Quantization
     g = load_golden("full_model_b1.npz")
     scales = (8, 16, 32, 64)
@@ -608,15 +613,27 @@ def test_full_model_config1_golden(dev, books):
     rel = [torch.from_numpy(g[f"rel_in_{s}"]) for s in scales]          # real decoder outputs: partly negative
     weights = [torch.from_numpy(g[f"w_{i}"]) for i in range(7)]
     plan = _run_plan(dev, x_d1, rel, weights, "map")
-    for s in scales:
-        assert _rel_err(plan.rel[s].cpu(), torch.from_numpy(g[f"rel_out_{s}"])) < REL_MAP, s
-    for i, y in enumerate(plan.yhat_list()):
-        assert torch.allclose(y.cpu(), torch.from_numpy(g[f"yhat_{i}"]), rtol=0, atol=5e-5), i
-    assert _depth_ok(plan.depth.cpu(), torch.from_numpy(g["depth"]))
-    quant = Quantization()
-    for s, r in zip(scales, rel):
-        out = Ordinal_Layer(int(math.log2(s)) + 3, False, quant)(r.to(dev))
-        assert _rel_err(out.cpu(), torch.from_numpy(g[f"rel_out_{s}"])) < REL_MAP, s
+    # the oracle at the reference's own k* (stored with the golden) reproduces the reference's outputs
+    ref = fr.fusion_forward(x_d1, rel, weights, books, want_intermediates=True, force_k=[g[f"kstar_{s}"].tolist() for s in scales])
+    assert (ref["depth"] - torch.from_numpy(g["depth"])).abs().max().item() <= 1e-5   # CPU-to-CPU f32 noise
+    ks = []
+    for si, s in enumerate(scales):
+        ours_k = plan.kstar[s].view(-1).tolist()
+        ks.append(ours_k)
+        for pi, it in enumerate(ref["inter"][si]):
+            assert torch.equal(plan.bins[s][:, pi].cpu(), it["bins"]), (s, pi)
+            rec_ref = g[f"record_{s}"][pi]                       # the reference's record
+            assert np.allclose(plan.record[s][0, pi].cpu().numpy(), rec_ref, rtol=2e-6, atol=1e-8), (s, pi)
+            assert rec_ref[ours_k[pi]] <= rec_ref.min() * (1 + 2e-7), (s, pi, ours_k[pi], int(g[f"kstar_{s}"][pi]))
+    forced = fr.fusion_forward(x_d1, rel, weights, books, force_k=ks)
+    for si, s in enumerate(scales):
+        assert _rel_err(plan.rel[s].cpu(), forced["rel"][si]) < REL_MAP, s
+    for y, yr in zip(plan.yhat_list(), forced["y_hat"]):
+        assert torch.allclose(y.cpu(), yr, rtol=0, atol=5e-5)
+    assert _depth_ok(plan.depth.cpu(), forced["depth"])
+    # scale 8 (k* = 1, no plateau) also matches the golden directly, through the drop-in class
+    out = Ordinal_Layer(6, False, Quantization())(rel[0].to(dev))
+    assert _rel_err(out.cpu(), torch.from_numpy(g["rel_out_8"])) < REL_MAP
 
 
 def test_dorn_regression_and_ordinal_loss_golden(dev):

@@ -94,12 +94,19 @@ def main():
             out[f"w_{i}"] = w.detach().numpy()
     for i, t in enumerate(y_keep):
         out[f"yhat_{i}"] = t.numpy()
-    np.savez_compressed(os.path.join(REPO, "tests", "golden", "full_model_b1.npz"), **out)
-    # the oracle on the same decoder outputs
+    # the oracle on the same decoder outputs; its per-page k* and rmse record (bit-equal to the reference's
+    # on this machine) are stored because the record PLATEAUS on smooth maps and the arg-min among one-ulp
+    # ties is machine dependent (tests compare at the stored k*)
     w = [torch.from_numpy(out[f"w_{i}"]) for i in range(7)]
-    o = fr.fusion_forward(captured["x_d1"], captured["rel_in"], w, books)
+    o = fr.fusion_forward(captured["x_d1"], captured["rel_in"], w, books, want_intermediates=True)
     print("oracle vs reference full model: max |depth diff| =", float((o["depth"] - depth).abs().max()),
           "nan:", bool(torch.isnan(depth).any()))
+    assert float((o["depth"] - depth).abs().max()) == 0.0
+    for s, inter in zip((8, 16, 32, 64), o["inter"]):
+        out[f"kstar_{s}"] = np.array([it["kstar"] for it in inter], dtype=np.int32)
+        out[f"record_{s}"] = np.array([it["record"] for it in inter], dtype=np.float32)
+        print(s, "k* per page:", out[f"kstar_{s}"].tolist())
+    np.savez_compressed(os.path.join(REPO, "tests", "golden", "full_model_b1.npz"), **out)
     shutil.rmtree(tmp, ignore_errors=True)
 
 
