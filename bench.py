@@ -207,18 +207,29 @@ def timed_steps(ring, streams, steps, fn):
 
 
 def time_serial(fns, reps):
-    """Average duration of the launches issued by `fns` (one per ring entry) back to back on ONE stream."""
-    cur = torch.cuda.current_stream()
+    """Average duration of the launches issued by `fns` (one per ring entry) back to back on ONE stream.
+    The launches are captured into a CUDA graph first, so the host launch rate (several microseconds per
+    Python + ctypes call) is not what gets measured for the short kernels."""
+    n = len(fns)
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        for f in fns[:4]:
+            f()
+    stream.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=stream):
+        for f in fns:
+            f()
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    for f in fns[:4]:
-        f()
-    torch.cuda.synchronize()
-    start.record(cur)
-    for i in range(reps):
-        fns[i % len(fns)]()
-    end.record(cur)
-    torch.cuda.synchronize()
-    return start.elapsed_time(end) / reps * 1e-3   # seconds per launch
+    rounds = max(reps // n, 1)
+    with torch.cuda.stream(stream):
+        g.replay()
+        start.record(stream)
+        for _ in range(rounds):
+            g.replay()
+        end.record(stream)
+    stream.synchronize()
+    return start.elapsed_time(end) / (rounds * n) * 1e-3   # seconds per launch
 
 
 def cpu_baseline_port(images: int):

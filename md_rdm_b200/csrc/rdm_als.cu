@@ -21,7 +21,7 @@
 // GEMV) was bound by shared-memory operand delivery, not by FMA issue (profiles/README.md).
 // Per iteration: 2 named barriers.
 //
-// rmse record (CP:53-61, CP:121-130): see the comment above kDirectFrac.  Per-unit SSE goes to
+// rmse record (CP:53-61, CP:121-130): see the comment above als_iterate.  Per-unit SSE goes to
 // the workspace; the arg-min is over the mean of the whole reference batch ("group",
 // CP:172-173), so phase 1 (second launch) sums the group's records, picks the first minimum
 // (CP:74, CP:143) and emits p_k*.  Phase 0 streams every iterate p_1..p_limit to the workspace (one
@@ -66,7 +66,7 @@ struct AlsParams {
 
 struct AlsSmem {
   __align__(16) float p_s[256];       // p by row index (64-row units: 4 x 64)
-  __align__(16) float q_w[8][64];     // per-warp copy of q
+  __align__(16) float q_w[2][8][64];  // per-warp copies of q, double buffered (q_{k-1} stays readable for the record)
   __align__(16) float qpart[4][64];   // q partial sums (256-row: by r'; 64-row: by unit)
   __align__(16) float part_pp[8];     // |p segment|^2 by r'
   double thr_d[kThrPad];
@@ -228,6 +228,34 @@ __device__ __forceinline__ float tile_sse(const float2 (&R)[4][8], uint32_t qop,
     }
   }
   return reduce_scatter4(acc[0], acc[1], acc[2], acc[3], cb);
+}
+
+// The same residual with fused arithmetic (FFMA2): t = R - p q (one rounding), acc += t^2.  Used for
+// the record of iterations k >= 1: as accurate as the reference's own f32 evaluation (~1e-7 after
+// averaging), which matters on smooth maps where the record declines by ~1 f32 ulp per iteration and
+// the arg-min follows that decline.
+__device__ __forceinline__ float tile_sse_fused(const float2 (&R)[4][8], uint32_t qop, const float (&pj)[4], int cb) {
+  ulonglong2 x[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) x[k] = lds_v2u64(qop + 16 * k);
+  u64 acc[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const u64 np2 = as_u64(make_float2(-pj[j], -pj[j]));
+    u64 a0 = 0, a1 = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const u64 t0 = ffma2(np2, x[k].x, as_u64(R[j][2 * k]));
+      const u64 t1 = ffma2(np2, x[k].y, as_u64(R[j][2 * k + 1]));
+      a0 = ffma2(t0, t0, a0);
+      a1 = ffma2(t1, t1, a1);
+    }
+    acc[j] = a0;
+    // fold the second chain in with a packed add
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(acc[j]) : "l"(a0), "l"(a1));
+  }
+  const float2 f0 = as_f2(acc[0]), f1 = as_f2(acc[1]), f2 = as_f2(acc[2]), f3 = as_f2(acc[3]);
+  return reduce_scatter4(f0.x + f0.y, f1.x + f1.y, f2.x + f2.y, f3.x + f3.y, cb);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -393,18 +421,21 @@ __device__ __forceinline__ void load_unit(float2 (&R)[4][8], const AlsScaleDev& 
     load_unit_impl<G, false>(R, sc, sm, tile, unit_idx, unit, lt, emit);
 }
 
-// Record (CP:53-61, CP:121-130).  Row i's residual sum_j (p_i q_j - R_ij)^2 equals
-// |R_i|^2 + p_i (p_i |q|^2 - 2 s_i) with s_i = R_i . q a by-product of the p-update; evaluated
-// in f64 its absolute error is ~1e-7 |R_i|^2 (s_i and |q|^2 are f32).  That is used when the
-// row's residual is a sizeable part of its energy; rows fitted almost exactly (below kDirectFrac
-// of |R_i|^2 - near-constant or nearly rank-1 rows, where arg-min ties could flip k*) are
-// evaluated directly with tile_sse(), the third pass the reference always makes (a warp takes
-// that path when any of its rows asks for it).  Each thread parks the value of the row it owns
-// for iteration k in shared memory E[k][thread]; the unit reduces all iterations once, after
-// the loop (two rows per slot, so the scratch fits in the dead staging tile).
-constexpr double kDirectFrac = 0.005;
-
-
+// Record (CP:53-61, CP:121-130).  Two evaluations of row i's residual sum_j (p_i q_j - R_ij)^2:
+//  * direct (tile_sse / tile_sse_fused): the third pass over the matrix the reference makes; as
+//    accurate as the reference's own f32 evaluation (~1e-7 after averaging);
+//  * algebraic: |R_i|^2 + p_i (p_i |q|^2 - 2 s_i), s_i = R_i . q being a by-product of the p-update;
+//    O(1) per row, absolute error ~1e-7 |R_i|^2 (s_i and |q|^2 are f32), i.e. ~1e-6 relative once the
+//    residual is a few per cent of the energy.
+// On smooth maps the record plateaus and declines by about one f32 ulp per iteration; the arg-min
+// follows that decline, so only the direct form is good enough there.  The choice is made per unit
+// and per iteration from the residual estimate |R|^2 - |p_k|^2 (|q_{k-1}|^2 + 2 lambda) (scalars every
+// thread holds after barrier B): below kDirectFrac of |R|^2 -> direct.  Iteration 0 is always direct,
+// with the reference's unfused rounding so that constant maps give exactly 0.
+// Each thread parks the value of the row it owns for iteration k in shared memory E[k][thread]; the
+// unit reduces all iterations once, after the loop (two rows per slot: the scratch fits in the dead
+// staging tile).
+constexpr float kDirectFrac = 0.015f;
 // n_iter alternating iterations.  Writes the SSE of iterations 0..n_iter to rec[] and the iterates
 // p_1..p_n_iter to hist[(k-1) * rows + row].  E: (n_iter+1) x (NT/2+1) floats of shared scratch.
 template <int G>
@@ -419,9 +450,10 @@ __device__ __forceinline__ void als_iterate(const float2 (&R)[4][8], AlsSmem& sm
   const int gw = unit * NW + m.lw;
   const int bar_id = (G == 4) ? 0 : 1 + unit;
   const int qp_row = (G == 4) ? m.rp : unit;
-  const uint32_t qw = smem_u32(sm.q_w[gw]);                    // this warp's copy of q
+  uint32_t qw = smem_u32(sm.q_w[0][gw]);                       // this warp's current copy of q
+  const uint32_t qw_flip = smem_u32(sm.q_w[0][gw]) ^ smem_u32(sm.q_w[1][gw]);
   const uint32_t ps = smem_u32(sm.p_s + unit * 64);            // p of this unit
-  const uint32_t qop = qw + 64 * m.cb;                         // operand slices (16 floats)
+  uint32_t qop = qw + 64 * m.cb;                               // operand slices (16 floats)
   const uint32_t pop = ps + 256 * m.rp + 64 * m.cb;
   const uint32_t qpart = smem_u32(sm.qpart);
   const uint32_t ppart = smem_u32(sm.part_pp);
@@ -436,7 +468,7 @@ __device__ __forceinline__ void als_iterate(const float2 (&R)[4][8], AlsSmem& sm
   tile_dot(R, qop, m.cb, s, Q);                  // s = row sum, Q = 64
   float invA = rcp_newton(Q + kLambda);          // torch.inverse of the 1x1 matrix |q|^2 + lambda
   double r2 = 0.0;
-  float r2h = 0.f, r2l = 0.f, direct_below = 0.f;
+  float r2h = 0.f, r2l = 0.f, r2tot = 0.f;
   if (RECORD) {
     double t[4];
 #pragma unroll
@@ -448,7 +480,13 @@ __device__ __forceinline__ void als_iterate(const float2 (&R)[4][8], AlsSmem& sm
     r2 = reduce_scatter4(t[0], t[1], t[2], t[3], m.cb);
     r2h = (float)r2;                             // |R_i|^2 as an unevaluated f32 pair (exact to ~2^-48)
     r2l = (float)(r2 - (double)r2h);
-    direct_below = (float)(kDirectFrac * r2);
+    {                                            // |R|^2 of the whole unit (decision threshold only)
+      const float w = warp_sum(r2h);
+      if (m.lane == 0) sts_f32(smem_u32(sm.rm) + 4 * gw, w);
+      unit_barrier(bar_id, NT);
+#pragma unroll
+      for (int w2 = 0; w2 < NW; ++w2) r2tot += lds_f32(smem_u32(sm.rm) + 4 * (unit * NW + w2));
+    }
     const float ones[4] = {1.f, 1.f, 1.f, 1.f};
     const float e0 = tile_sse(R, qop, ones, m.cb);   // k = 0: p = q = 1 (CP:55, CP:123)
     unit_barrier(bar_id, NT);                    // the staging tile (aliased by E) is dead from here on
@@ -464,55 +502,62 @@ __device__ __forceinline__ void als_iterate(const float2 (&R)[4][8], AlsSmem& sm
     sts_f32(ps + 4 * m.row_own, p);
     hist[(k - 1) * NT + m.row_own] = p;          // fire-and-forget: phase 1 picks p_k*
     if (!(kExp & 4)) unit_barrier(bar_id, NT);   // A: p visible
-    float u, pseg;
-    tile_dot(R, pop, m.cb, u, pseg);             // this row's share of q_{ib+cb}; |p segment r'|^2
-    if (RECORD && !(kExp & 1)) {
-      // e = |R_i|^2 + p (p |q|^2 - 2 s) in f32 pair arithmetic (error-free product and sum): same
-      // ~1e-7 |R_i|^2 absolute accuracy as an f64 evaluation - s and |q|^2 are f32 anyway - on the FP32 pipe
+    float ef = 0.f;
+    if (RECORD) {   // algebraic residual of this row (f32 pair arithmetic: error-free product and sum); straight-line
+                    // code next to the operand loads so that it fills their latency
       const float t = fmaf(p, Q, -2.0f * s);
       const float ph = p * t, pl = fmaf(p, t, -ph);
       const float sm1 = r2h + ph, bb = sm1 - r2h;
       const float er = (r2h - (sm1 - bb)) + (ph - bb);
-      const float e = sm1 + (er + (r2l + pl));
-      float ef = fmaxf(e, 0.f);
-      const bool want = e < direct_below;
-      if (__any_sync(0xffffffffu, want)) {       // qw still holds q_{k-1}
-        float pj[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) pj[j] = lds_f32(ps + 4 * m.row(j));
-        const float ed = tile_sse(R, qop, pj, m.cb);
-        if (want) ef = ed;
-      }
-      ef += __shfl_xor_sync(0xffffffffu, ef, 4);
-      if (!(m.lane & 4)) sts_f32(Es + 4 * k * ES, ef);
+      ef = fmaxf(sm1 + (er + (r2l + pl)), 0.f);
     }
+    float u, pseg;
+    tile_dot(R, pop, m.cb, u, pseg);             // this row's share of q_{ib+cb}; |p segment r'|^2
     sts_f32(qpart + 4 * (64 * qp_row + m.ib + m.cb), u);
     if constexpr (G == 4) {
       if (m.lw < 4 && m.lane == 0) sts_f32(ppart + 4 * m.rp, pseg);
     }
     if (!(kExp & 4)) unit_barrier(bar_id, NT);   // B: q partials (and |p|^2 segments) visible
-    if (k == n_iter) break;
-    // every warp finalises q for itself (no further barrier)
-    float npp = pseg, u0, u1;
+    float npp = pseg;
     if constexpr (G == 4) {
       const float4 a = lds_v4f32(ppart);
-      const uint32_t q0a = qpart + 4 * m.lane;
-      const float a0 = lds_f32(q0a), a1 = lds_f32(q0a + 256), a2 = lds_f32(q0a + 512), a3 = lds_f32(q0a + 768);
-      const float b0 = lds_f32(q0a + 128), b1 = lds_f32(q0a + 384), b2 = lds_f32(q0a + 640), b3 = lds_f32(q0a + 896);
       npp = (a.x + a.y) + (a.z + a.w);
-      u0 = (a0 + a1) + (a2 + a3);
-      u1 = (b0 + b1) + (b2 + b3);
-    } else {
-      u0 = lds_f32(qpart + 4 * (64 * unit + m.lane));
-      u1 = lds_f32(qpart + 4 * (64 * unit + m.lane + 32));
     }
-    const float invB = (kExp & 2) ? (npp + kLambda) * 1e-4f : rcp_newton(npp + kLambda);
-    __syncwarp();
-    sts_f32(qw + 4 * m.lane, u0 * invB);
-    sts_f32(qw + 4 * m.lane + 128, u1 * invB);
-    __syncwarp();
-    tile_dot(R, qop, m.cb, s, Q);
-    invA = (kExp & 2) ? (Q + kLambda) * 1e-2f : rcp_newton(Q + kLambda);
+    // the direct evaluation (rare on noise-like maps) needs p_k (ps) and q_{k-1} (this warp's old q copy)
+    const uint32_t qop_k = qop;
+    const bool direct = RECORD && (r2tot - npp * (Q + 2.0f * kLambda)) < kDirectFrac * r2tot;   // unit-uniform
+    if (k < n_iter) {
+      // every warp finalises q for itself (no further barrier), into its other q buffer
+      float u0, u1;
+      if constexpr (G == 4) {
+        const uint32_t q0a = qpart + 4 * m.lane;
+        const float a0 = lds_f32(q0a), a1 = lds_f32(q0a + 256), a2 = lds_f32(q0a + 512), a3 = lds_f32(q0a + 768);
+        const float b0 = lds_f32(q0a + 128), b1 = lds_f32(q0a + 384), b2 = lds_f32(q0a + 640), b3 = lds_f32(q0a + 896);
+        u0 = (a0 + a1) + (a2 + a3);
+        u1 = (b0 + b1) + (b2 + b3);
+      } else {
+        u0 = lds_f32(qpart + 4 * (64 * unit + m.lane));
+        u1 = lds_f32(qpart + 4 * (64 * unit + m.lane + 32));
+      }
+      const float invB = (kExp & 2) ? (npp + kLambda) * 1e-4f : rcp_newton(npp + kLambda);
+      qw ^= qw_flip;
+      qop = qw + 64 * m.cb;
+      sts_f32(qw + 4 * m.lane, u0 * invB);
+      sts_f32(qw + 4 * m.lane + 128, u1 * invB);
+      __syncwarp();
+      tile_dot(R, qop, m.cb, s, Q);
+      invA = (kExp & 2) ? (Q + kLambda) * 1e-2f : rcp_newton(Q + kLambda);
+    }
+    if (RECORD && !(kExp & 1)) {
+      if (direct) {   // reads only this warp's own data (its rows of p in ps, its old q copy): no barrier needed
+        float pj[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pj[j] = lds_f32(ps + 4 * m.row(j));
+        ef = tile_sse_fused(R, qop_k, pj, m.cb);
+      }
+      ef += __shfl_xor_sync(0xffffffffu, ef, 4);
+      if (!(m.lane & 4)) sts_f32(Es + 4 * k * ES, ef);
+    }
   }
 #ifdef RDM_TIMING
   if (RECORD && lt == 0 && unit == 0 && blockIdx.x % 37 == 0) printf("  block %d loop %lld cycles for %d iterations\n", blockIdx.x, clock64() - tl0, n_iter);

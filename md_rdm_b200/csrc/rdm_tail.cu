@@ -542,11 +542,16 @@ __global__ void __launch_bounds__(RDM_TAIL_THREADS) fuse_tail_kernel(const __gri
   float* L = yh + ylen;                                       // P.lmax floats: f32(log F) of the current level
   __shared__ float scratch[32];
   __shared__ float wsm[64];                                   // the (<= 4 + 6*6) weights, read from HBM once
+  __shared__ float wl[8][kMaxDec];                            // wl[k][a]: weight of the a-th active decoder of slot k
   const int64_t img = blockIdx.x / P.bands;
   const int band = blockIdx.x - (int)(img * P.bands);
   const bool lead = band == 0;
   const int tid = threadIdx.x;
   if (tid < P.w_off[7] + P.K[7]) wsm[tid] = P.w[tid];
+  if (tid < 8 * kMaxDec) {
+    const int k = tid / kMaxDec, a = tid - k * kMaxDec;
+    if (k >= 1 && k <= P.kmax && a < P.nact[k]) wl[k][a] = P.w[P.w_off[k] + P.cand[P.act[k][a]][k]];
+  }
 #ifdef RDM_TIMING
   long long tt[12];
   int ti = 0;
@@ -558,7 +563,7 @@ __global__ void __launch_bounds__(RDM_TAIL_THREADS) fuse_tail_kernel(const __gri
     float v = 1.f, pw = 1.f;
     if (tid < 64) {
       v = (float)P.x_d1[img * 64 + tid];
-      pw = (float)pow((double)v, 1.0 / 64.0);
+      pw = powf(v, 0.015625f);   // torch.pow(int64 -> f32, 1/64) is an f32 pow as well (CP:248-253)
     }
     const float gm = block_prod<float>(pw, scratch);
     if (tid < 64) D[P.doff[0] + off_level(3) + tid] = (double)(v / gm);
@@ -606,7 +611,7 @@ __global__ void __launch_bounds__(RDM_TAIL_THREADS) fuse_tail_kernel(const __gri
     const int n = 1 << (2 * k), na = P.nact[k];
     for (int idx = tid; idx < n; idx += blockDim.x) {
       float y = 0.f;
-      for (int a = 0; a < na; ++a) y = fmaf(L[lofs + a * n + idx], wsm[P.w_off[k] + P.cand[P.act[k][a]][k]], y);
+      for (int a = 0; a < na; ++a) y = fmaf(L[lofs + a * n + idx], wl[k][a], y);
       yh[off_level(k) + idx] = y;
     }
   };
@@ -688,32 +693,36 @@ __global__ void __launch_bounds__(RDM_TAIL_THREADS) fuse_tail_kernel(const __gri
   const int rows = 128 / P.bands;
   double* out = P.depth_out + img * 16384 + (int64_t)band * rows * 128;
   const double d0 = (double)yh[0];
-  for (int o0 = tid; o0 < rows * 64; o0 += 4 * blockDim.x) {
-    double a0[4], a1[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {   // four independent gather-sum chains
-      const int o = o0 + j * blockDim.x;
-      if (o < rows * 64) {
-        const int y = band * rows + (o >> 6), x = (o & 63) * 2;
-        a0[j] = a1[j] = 0.0;
-        for (int k = 1; k <= P.kmax; ++k) {
-          const int sh = 7 - k, cs = 1 << k;
-          const float* c = yh + off_level(k) + (y >> sh) * cs;
-          const double v0 = (double)c[x >> sh], v1 = (double)c[(x + 1) >> sh];
-          if (k == 1) {
-            a0[j] = v0;
-            a1[j] = v1;
-          } else {
-            a0[j] += v0;
-            a1[j] += v1;
-          }
-        }
+  // Levels above kmax do not exist, so the sum is constant on blocks of bs x bs pixels (bs = 2^(7-kmax)):
+  // one gather-sum per block, then bs rows of 128-bit stores.
+  const int bsh = 7 - P.kmax, bs = 1 << bsh;
+  if (bs >= 2) {
+    const int bpr = 128 >> bsh;                                  // blocks per row
+    for (int blk = tid; blk < (rows >> bsh) * bpr; blk += blockDim.x) {
+      const int by = blk / bpr, bx = blk - by * bpr;
+      const int y = band * rows + (by << bsh), x = bx << bsh;
+      double a = 0.0;
+      for (int k = 1; k <= P.kmax; ++k) {
+        const int sh = 7 - k;
+        const double v = (double)yh[off_level(k) + (y >> sh) * (1 << k) + (x >> sh)];
+        a = (k == 1) ? v : a + v;
       }
+      const double v = d0 + a;
+      for (int r = 0; r < bs; ++r)
+        for (int c = 0; c < bs; c += 2) stg_stream_f64x2(out + ((by << bsh) + r) * 128 + x + c, v, v);
     }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int o = o0 + j * blockDim.x;
-      if (o < rows * 64) stg_stream_f64x2(out + (o >> 6) * 128 + (o & 63) * 2, d0 + a0[j], d0 + a1[j]);
+  } else {
+    for (int o = tid; o < rows * 64; o += blockDim.x) {
+      const int y = band * rows + (o >> 6), x = (o & 63) * 2;
+      double a0 = 0.0, a1 = 0.0;
+      for (int k = 1; k <= P.kmax; ++k) {
+        const int sh = 7 - k, cs = 1 << k;
+        const float* c = yh + off_level(k) + (y >> sh) * cs;
+        const double v0 = (double)c[x >> sh], v1 = (double)c[(x + 1) >> sh];
+        a0 = (k == 1) ? v0 : a0 + v0;
+        a1 = (k == 1) ? v1 : a1 + v1;
+      }
+      stg_stream_f64x2(out + (o >> 6) * 128 + x, d0 + a0, d0 + a1);
     }
   }
 #ifdef RDM_TIMING
@@ -1071,8 +1080,8 @@ extern "C" int rdm_fuse_tail(const int64_t* x_d1, const float* const* rel, const
   }
   // bands: enough CTAs to spread the 128 KB/image output, few enough that the pyramid work (redone
   // by every band) stays small: >= 64 CTAs in total
-  int bands = 1;
-  while (bands < 16 && n_images * bands < 64) bands <<= 1;
+  int bands = 1;   // a band must hold whole constant blocks: rows per band >= 2^(7-kmax)
+  while (bands < 16 && bands < (1 << P.kmax) && n_images * bands < 64) bands <<= 1;
   P.bands = bands;
   RDM_REQUIRE(n_images * bands < (1ll << 31), "rdm_fuse_tail: too many images");
   const size_t smem = (size_t)P.dtotal * sizeof(double) + ((size_t)off_level(P.kmax + 1) + lmax) * sizeof(float);

@@ -604,8 +604,8 @@ def test_full_model_config1_golden(dev, books):
     Real decoder outputs are smooth, so the ALS record PLATEAUS: from iteration ~3 on its f32 values differ
     by one ulp, and which of them is the first minimum is decided by summation-order noise (the reference
     itself would pick another index with another BLAS).  Parity is therefore stated as: bins bit-exact;
-    record equal to 1e-5; our k* is a tie of the reference's own record (within 1e-6 relative of its
-    minimum); and maps, y_hat, log-depth match the reference algorithm evaluated at that k*."""
+    record equal to 1e-5; our k* is a tie of the reference's own record (within 3e-6 relative of its
+    minimum, the noise level of an f32 record); and maps, y_hat, log-depth match the reference algorithm evaluated at that k*."""
     from md_rdm_b200.rdm_net import Ordinal_Layer, Quantization
     g = load_golden("full_model_b1.npz")
     scales = (8, 16, 32, 64)
