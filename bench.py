@@ -265,7 +265,7 @@ def run_ours(args):
     _cabi.load()   # fail loudly before anything is timed
 
     from md_rdm_b200.fusion import capture_lane, capture_ring
-    ab = algorithmic_bytes()
+    ab = algorithmic_bytes(SCALES)
     n_plans = max(args.ring // args.streams, 1) * args.streams   # whole plans per lane
     ring = build_ring(dev, rank, n_plans, "raw")
     ring_in_bytes = sum(p.h2d_bytes() for p in ring)
@@ -373,9 +373,9 @@ def run_ours(args):
         "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 (ALS) + f64 (Lloyd compare, decomposition, recombination)", "data": "synthetic",
         "config": {
-            "workload": "BASELINE configs[1]: standalone fusion path, batch 16, scales 8/16/32; inputs = ordinary 8x8 map + raw pair "
-                        "matrices (1 f32 64x64 + 5 f64 256x64 per image) resident in HBM; quantize + ALS + decompose + weighted "
-                        "reconstruction -> bins, relative maps, y_hat, 128x128 f64 log-depth",
+            "workload": f"BASELINE configs[1]: standalone fusion path, batch 16, scales {'/'.join(map(str, SCALES))}; inputs = ordinary 8x8 "
+                        f"map + raw pair matrices (1 f32 64x64 + {sum((s // 16) ** 2 for s in SCALES if s > 8)} f64 256x64 per image) resident "
+                        "in HBM; quantize + ALS + decompose + weighted reconstruction -> bins, relative maps, y_hat, 128x128 f64 log-depth",
             "batch": BATCH, "scales": list(SCALES), "images_per_step_per_gpu": BATCH,
             "l2_policy": f"inputs larger than L2: ring of {n_plans} resident batches = {ring_in_bytes / 1e6:.0f} MB of inputs (L2 126 MB)",
             "batches_in_flight": args.streams,
@@ -472,8 +472,12 @@ def main():
     ap.add_argument("--ring", type=int, default=32, help="resident input batches (ring > L2)")
     ap.add_argument("--cpu-images", type=int, default=48)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scales", default="8,16,32", help="relative decoder scales (default: BASELINE configs[1]); "
+                    "8,16,32,64 is the configuration network/RDM_Net.py:96-97 names")
     ap.add_argument("--ref-budget-s", type=float, default=200.0, help="--impl reference: wall-clock budget for the literal port")
     args = ap.parse_args()
+    global SCALES
+    SCALES = tuple(int(v) for v in args.scales.split(","))
     if args.impl == "reference":
         args.steps = 20 if args.steps is None else args.steps
         args.warmup = 3 if args.warmup is None else max(args.warmup, 1)

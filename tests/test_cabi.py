@@ -78,3 +78,21 @@ def test_product_does_not_import_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(root, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
+
+
+def test_quantization_surface_and_mat_loader(tmp_path):
+    """Drop-in `Quantization` (RN:397-442): attribute names, get_with_id / get_size_id, and the .mat loader."""
+    import numpy as np
+    import scipy.io
+    from md_rdm_b200.codebooks import Quantization
+    q = Quantization()
+    assert q.depth_ratio_016_016_quant.shape == (40, 1) and q.depth_ratio_016_016_quant_inv.shape == (41, 1)
+    assert q.get_size_id(5) == 32 and q.get_with_id(5)[0] is q.depth_ratio_032_032_quant
+    assert q.derived[8] and not q.derived[16]
+    assert np.allclose(q.depth_ratio_008_008_quant, q.depth_ratio_016_016_quant ** 2, rtol=1e-15)
+    scipy.io.savemat(str(tmp_path / "depth_ratio_008_008_quant.mat"),
+                     {"depth_ratio_008_008_quant": np.linspace(0.5, 2.0, 40).reshape(40, 1),
+                      "depth_ratio_008_008_quant_inv": np.linspace(0.45, 2.1, 41).reshape(41, 1)})
+    q2 = Quantization.from_mat_dir(str(tmp_path))
+    assert not q2.derived[8] and q2.depth_ratio_008_008_quant[0, 0] == 0.5
+    assert np.array_equal(q2.depth_ratio_016_016_quant, q.depth_ratio_016_016_quant)

@@ -656,3 +656,20 @@ def test_dorn_regression_and_ordinal_loss_golden(dev):
     torch.randn(3, 180, 8, 8, generator=gen)
     depth = 0.5 + 9.5 * torch.rand(3, 1, 8, 8, generator=gen, dtype=torch.float64)
     assert torch.equal(depth2label_sid(depth.to(dev)).cpu(), torch.from_numpy(g["target"]))
+
+
+def test_relative_tail_128_and_fuse_maps(dev, books):
+    """Decoder 10 (128x128, 64 pages, RN:383-396) through the drop-in class, and the functional fast path."""
+    from md_rdm_b200.fusion import fuse_maps
+    from md_rdm_b200.rdm_net import Ordinal_Layer, Quantization
+    g = torch.Generator().manual_seed(128)
+    x = torch.exp(0.3 * torch.randn(1, 1, 128, 128, generator=g))
+    out = Ordinal_Layer(10, False, Quantization())(x.to(dev))
+    ref = fr.relative_decoder_tail(x, books)
+    assert out.shape == (1, 1, 128, 128) and _rel_err(out.cpu(), ref) < REL_MAP
+    x_d1, rel, weights = fr.synthetic_batch(3, (8, 16), seed=42)
+    depth, y_hat, filled = fuse_maps(x_d1.to(dev), [r.to(dev) for r in rel], [w.to(dev) for w in weights])
+    o = fr.fusion_forward(x_d1, rel, weights, books)
+    assert _depth_ok(depth.cpu(), o["depth"]) and len(y_hat) == 5
+    for a, b in zip(filled, o["rel"]):
+        assert _rel_err(a.cpu(), b) < REL_MAP
