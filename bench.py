@@ -371,12 +371,13 @@ def run_ours(args):
     out = {
         "metric": METRIC, "value": world * K * BATCH / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32 (ALS) + f64 (Lloyd compare, decomposition, recombination)", "data": "synthetic",
+        "dtype": "f32+f64", "data": "synthetic",
         "config": {
             "workload": f"BASELINE configs[1]: standalone fusion path, batch 16, scales {'/'.join(map(str, SCALES))}; inputs = ordinary 8x8 "
                         f"map + raw pair matrices (1 f32 64x64 + {sum((s // 16) ** 2 for s in SCALES if s > 8)} f64 256x64 per image) resident "
                         "in HBM; quantize + ALS + decompose + weighted reconstruction -> bins, relative maps, y_hat, 128x128 f64 log-depth",
             "batch": BATCH, "scales": list(SCALES), "images_per_step_per_gpu": BATCH,
+            "dtype_detail": "f32: 8x8 pair ratios + Lloyd compare, ALS, y_hat; f64: page pair ratios + Lloyd compare, decomposition, logs, recombination",
             "l2_policy": f"inputs larger than L2: ring of {n_plans} resident batches = {ring_in_bytes / 1e6:.0f} MB of inputs (L2 126 MB)",
             "batches_in_flight": args.streams,
             "cuda_graph": f"{args.streams} lanes (streams), one graph launch per {n_plans // args.streams} steps of a lane, 3 kernels per step",
@@ -451,7 +452,7 @@ def run_reference(args):
     out = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
         "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32 (ALS) + f64 (Lloyd compare, decomposition, recombination)", "data": "synthetic",
+        "dtype": "f32+f64", "data": "synthetic",
         "config": {"workload": "BASELINE configs[1] on the host CPU: decoder maps -> pair build + Lloyd + ALS + decompose + weighted "
                                "reconstruction, reference algorithm", "batch": per_step, "scales": list(SCALES),
                    "literal_port_s_per_image": t_lit},

@@ -184,6 +184,33 @@ __device__ __forceinline__ T group_sum4(T v) {
 
 // Partial GEMV of the tile with the lane's 16-float operand slice `op` (4 LDS.128) and the
 // squared norm of the slice: own = full dot of the row this lane owns, nrm = |whole operand|^2.
+// Measured on B200: packed FFMA2 (fma.rn.f32x2) issues only on the fmaheavy sub-pipe, scalar FFMA on both
+// halves; for these GEMVs the scalar form is 12 % faster per launch (78.8 vs 89.3 us) despite twice the
+// FMA instructions.  -DRDM_FFMA2 builds the packed variant for comparison.
+#ifndef RDM_FFMA2
+__device__ __forceinline__ void tile_dot(const float2 (&R)[4][8], uint32_t op, int cb, float& own, float& nrm) {
+  float4 x[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) x[k] = lds_v4f32(op + 16 * k);
+  float a[4][2], n0 = 0.f, n1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) a[j][0] = a[j][1] = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      a[j][0] = fmaf(R[j][2 * k].x, x[k].x, a[j][0]);
+      a[j][1] = fmaf(R[j][2 * k].y, x[k].y, a[j][1]);
+      a[j][0] = fmaf(R[j][2 * k + 1].x, x[k].z, a[j][0]);
+      a[j][1] = fmaf(R[j][2 * k + 1].y, x[k].w, a[j][1]);
+    }
+    n0 = fmaf(x[k].x, x[k].x, fmaf(x[k].z, x[k].z, n0));
+    n1 = fmaf(x[k].y, x[k].y, fmaf(x[k].w, x[k].w, n1));
+  }
+  own = reduce_scatter4(a[0][0] + a[0][1], a[1][0] + a[1][1], a[2][0] + a[2][1], a[3][0] + a[3][1], cb);
+  nrm = group_sum4(n0 + n1);
+}
+#else
 __device__ __forceinline__ void tile_dot(const float2 (&R)[4][8], uint32_t op, int cb, float& own, float& nrm) {
   ulonglong2 x[4];
 #pragma unroll
@@ -210,6 +237,7 @@ __device__ __forceinline__ void tile_dot(const float2 (&R)[4][8], uint32_t op, i
   own = reduce_scatter4(hsum2(a[0][0], a[0][1]), hsum2(a[1][0], a[1][1]), hsum2(a[2][0], a[2][1]), hsum2(a[3][0], a[3][1]), cb);
   nrm = group_sum4(hsum2(n0, n1));
 }
+#endif
 
 // Direct residual of the tile rows: sum_c (p_j q_c - R[j][c])^2 in f32 (what CP:172-173
 // evaluates); lane cb receives the row it owns.
@@ -230,32 +258,28 @@ __device__ __forceinline__ float tile_sse(const float2 (&R)[4][8], uint32_t qop,
   return reduce_scatter4(acc[0], acc[1], acc[2], acc[3], cb);
 }
 
-// The same residual with fused arithmetic (FFMA2): t = R - p q (one rounding), acc += t^2.  Used for
+// The same residual with fused arithmetic: t = R - p q (one rounding), acc += t^2.  Used for
 // the record of iterations k >= 1: as accurate as the reference's own f32 evaluation (~1e-7 after
 // averaging), which matters on smooth maps where the record declines by ~1 f32 ulp per iteration and
 // the arg-min follows that decline.
 __device__ __forceinline__ float tile_sse_fused(const float2 (&R)[4][8], uint32_t qop, const float (&pj)[4], int cb) {
-  ulonglong2 x[4];
+  float4 x[4];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) x[k] = lds_v2u64(qop + 16 * k);
-  u64 acc[4];
+  for (int k = 0; k < 4; ++k) x[k] = lds_v4f32(qop + 16 * k);
+  float acc[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const u64 np2 = as_u64(make_float2(-pj[j], -pj[j]));
-    u64 a0 = 0, a1 = 0;
+    float a0 = 0.f, a1 = 0.f;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const u64 t0 = ffma2(np2, x[k].x, as_u64(R[j][2 * k]));
-      const u64 t1 = ffma2(np2, x[k].y, as_u64(R[j][2 * k + 1]));
-      a0 = ffma2(t0, t0, a0);
-      a1 = ffma2(t1, t1, a1);
+      const float t0 = fmaf(-pj[j], x[k].x, R[j][2 * k].x), t1 = fmaf(-pj[j], x[k].y, R[j][2 * k].y);
+      const float t2 = fmaf(-pj[j], x[k].z, R[j][2 * k + 1].x), t3 = fmaf(-pj[j], x[k].w, R[j][2 * k + 1].y);
+      a0 = fmaf(t2, t2, fmaf(t0, t0, a0));
+      a1 = fmaf(t3, t3, fmaf(t1, t1, a1));
     }
-    acc[j] = a0;
-    // fold the second chain in with a packed add
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(acc[j]) : "l"(a0), "l"(a1));
+    acc[j] = a0 + a1;
   }
-  const float2 f0 = as_f2(acc[0]), f1 = as_f2(acc[1]), f2 = as_f2(acc[2]), f3 = as_f2(acc[3]);
-  return reduce_scatter4(f0.x + f0.y, f1.x + f1.y, f2.x + f2.y, f3.x + f3.y, cb);
+  return reduce_scatter4(acc[0], acc[1], acc[2], acc[3], cb);
 }
 
 // ---------------------------------------------------------------------------------------------
