@@ -121,7 +121,7 @@ __device__ __forceinline__ ulonglong2 lds_v2u64(uint32_t a) {
 }
 
 #ifndef RDM_EXP
-#define RDM_EXP 0   // timing experiments only (wrong results): 1 no SSE, 2 no divisions, 4 no barriers, 16 no reduce-scatter
+#define RDM_EXP 0   // timing experiments only (wrong results): 1 no record, 2 no reciprocals, 4 no barriers, 8 no iterate history, 16 no reduce-scatter
 #endif
 constexpr int kExp = RDM_EXP;
 
@@ -524,7 +524,7 @@ __device__ __forceinline__ void als_iterate(const float2 (&R)[4][8], AlsSmem& sm
   for (int k = 1; k <= n_iter; ++k) {
     p = s * invA;                                // (R q) @ inverse(A)
     sts_f32(ps + 4 * m.row_own, p);
-    hist[(k - 1) * NT + m.row_own] = p;          // fire-and-forget: phase 1 picks p_k*
+    if (!(kExp & 8)) hist[(k - 1) * NT + m.row_own] = p;   // fire-and-forget: phase 1 picks p_k*
     if (!(kExp & 4)) unit_barrier(bar_id, NT);   // A: p visible
     float ef = 0.f;
     if (RECORD) {   // algebraic residual of this row (f32 pair arithmetic: error-free product and sum); straight-line

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Build instrumented / experimental variants of librdm_b200.so and print their ALS loop timings on the
 GPU (under gpurun).  RDM_TIMING adds clock64 printouts per CTA; RDM_EXP removes pieces of the iteration
-(wrong results, timing only): 1 record, 2 reciprocals, 4 barriers, 16 reduce-scatter.
+(wrong results, timing only): 1 record, 2 reciprocals, 4 barriers, 8 iterate history, 16 reduce-scatter.
 
     python tools/als_variants.py build          # here (nvcc), writes md_rdm_b200/variants/*.so (git-ignored)
     python tools/als_variants.py run            # on the GPU box
@@ -13,7 +13,7 @@ import sys
 ROOT = os.path.normpath(os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 sys.path.insert(0, ROOT)
 VAR = os.path.join(ROOT, "md_rdm_b200", "variants")
-EXPS = [0, 1, 2, 4, 7]
+EXPS = [0, 1, 2, 4, 8, 15]
 
 
 def name(x):
