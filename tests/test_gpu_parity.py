@@ -673,3 +673,29 @@ def test_relative_tail_128_and_fuse_maps(dev, books):
     assert _depth_ok(depth.cpu(), o["depth"]) and len(y_hat) == 5
     for a, b in zip(filled, o["rel"]):
         assert _rel_err(a.cpu(), b) < REL_MAP
+
+
+def test_codebook_fallbacks(dev, books):
+    """Arbitrary caller codebooks: unsorted thresholds (the reference's 40 compares do not care about order)
+    take the literal-compare path; thresholds closer than a lookup cell take the binary search.  Both must
+    still give the reference's bins, stand-alone and inside the fused ALS kernel."""
+    from md_rdm_b200 import _cabi
+    g = torch.Generator().manual_seed(77)
+    q, lv = books[16]
+    x = torch.exp(0.5 * torch.randn(4, 256, 64, generator=g, dtype=torch.float64))
+    perm = torch.randperm(40, generator=g)
+    tight = q.clone()
+    tight[21] = tight[20] * (1 + 1e-6)          # two thresholds inside one 2^-10 cell
+    tight, _ = torch.sort(tight)
+    for thr in (q[perm], tight):
+        rv, rb = fr.lloyd(x, thr, lv)
+        v, b = R.lloyd_quantize(x.to(dev), thr.to(dev), lv.to(dev))
+        assert torch.equal(b.cpu(), rb) and torch.equal(v.cpu(), rv)
+        xf = x.float()
+        rvf, rbf = fr.lloyd(xf, thr, lv)
+        vf, bf = R.lloyd_quantize(xf.to(dev), thr.to(dev), lv.to(dev))
+        assert torch.equal(bf.cpu(), rbf) and torch.equal(vf.cpu(), rvf)
+        m, _, _, k, bins, _ = R.als_rank1(x.to(dev), _cabi.SRC_RAW_F64, 256, 16, 100, 4, thr.to(dev), lv.to(dev), True, False)
+        assert torch.equal(bins.view(4, 256, 64).cpu(), rb)
+        ref_map, _, k_ref = fr.als_rank1(rv, 100)
+        assert int(k.item()) == k_ref and _rel_err(m.cpu(), ref_map) < REL_MAP
