@@ -148,8 +148,11 @@ __device__ __forceinline__ float rcp_newton(float x) {
 }
 
 // Thread <-> tile mapping of a unit.  lt = thread index inside the unit (0 .. 64G-1).
-// Rows of the tile: row(j) = G (ib + j) + rp, j = 0..3; columns 16 cb .. 16 cb + 15.
-// After a reduce-scatter, lane cb of the group owns row(cb).
+// The four lanes cb = 0..3 of a lane group share the rows G (ib + 0..3) + rp and hold the columns
+// 16 cb .. 16 cb + 15 of each.  A lane keeps them in the lane-specific slot order
+// slot t <-> row(t) = G (ib + (t ^ cb)) + rp, so that slot 0 is the row the lane owns after a
+// reduce-scatter and the "keep"/"send" halves of every exchange step are fixed register slots
+// (no selects): see reduce_scatter4.
 template <int G>
 struct TileMap {
   int lane, lw, cb, rp, ib, row_own;
@@ -161,19 +164,17 @@ struct TileMap {
     ib = (lw / G) * 32 + 4 * (lane >> 2);
     row_own = G * (ib + cb) + rp;
   }
-  __device__ __forceinline__ int row(int j) const { return G * (ib + j) + rp; }
+  __device__ __forceinline__ int row(int t) const { return G * (ib + (t ^ cb)) + rp; }
 };
 
-// Sum v[j] over the 4 lanes of a lane group; lane cb receives the total of v[cb] (3 shuffles).
+// Sum the per-slot partials over the 4 lanes of a lane group; every lane receives the total of its
+// slot 0, i.e. of the row it owns (3 shuffles).  With slot t <-> row (t ^ cb): the partner cb^2 holds our
+// rows of slots 0,1 in its slots 2,3, and the partner cb^1 holds our slot-0 row in its slot 1.
 template <typename T>
-__device__ __forceinline__ T reduce_scatter4(T v0, T v1, T v2, T v3, int cb) {
-  const bool hi = cb & 2, odd = cb & 1;
-  const T s0 = hi ? v0 : v2, s1 = hi ? v1 : v3;
-  const T k0 = hi ? v2 : v0, k1 = hi ? v3 : v1;
-  const T r0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 2);
-  const T r1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 2);
-  const T snd = odd ? r0 : r1, kp = odd ? r1 : r0;
-  return kp + __shfl_xor_sync(0xffffffffu, snd, 1);
+__device__ __forceinline__ T reduce_scatter4(T v0, T v1, T v2, T v3, int /*cb*/) {
+  const T r0 = v0 + __shfl_xor_sync(0xffffffffu, v2, 2);
+  const T r1 = v1 + __shfl_xor_sync(0xffffffffu, v3, 2);
+  return r0 + __shfl_xor_sync(0xffffffffu, r1, 1);
 }
 template <typename T>
 __device__ __forceinline__ T group_sum4(T v) {
