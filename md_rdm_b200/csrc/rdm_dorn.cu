@@ -12,6 +12,14 @@ namespace rdm {
 
 constexpr double kClampLo = 1e-8, kClampHi = 1e4;   // RN:334 torch.clamp(C, min=1e-8, max=1e4)
 
+static int grid_cap2(int64_t items) {
+  int64_t blocks = (items + 255) / 256;
+  if (blocks > (int64_t)kNumSMs * 8) blocks = (int64_t)kNumSMs * 8;
+  return blocks < 1 ? 1 : (int)blocks;
+}
+
+
+
 // softmax over the pair (A, B) as ATen computes it: exp(x - max) / sum, in f64; returns P(B).
 __device__ __forceinline__ double pair_softmax_b(double a, double b) {
   const double m = fmax(a, b);
@@ -19,26 +27,31 @@ __device__ __forceinline__ double pair_softmax_b(double a, double b) {
   return eb / (ea + eb);
 }
 
-// One CTA per image: ord[n,k,hw] = softmax(clamp(x[n,2k,hw]), clamp(x[n,2k+1,hw]))[1] (f64),
-// decode[n,hw] = #{k : ord > 0.5}.  hw is the fastest index of both tensors: coalesced.
-__global__ void __launch_bounds__(256) dorn_regression_kernel(const float* __restrict__ x, int K, int HW, int64_t* __restrict__ decode,
-                                                              double* __restrict__ ord) {
-  extern __shared__ int cnt[];   // HW counters
-  const int64_t n = blockIdx.x;
-  for (int i = threadIdx.x; i < HW; i += blockDim.x) cnt[i] = 0;
-  __syncthreads();
-  const float* xn = x + n * 2 * (int64_t)K * HW;
-  double* on = ord + n * (int64_t)K * HW;
-  for (int idx = threadIdx.x; idx < K * HW; idx += blockDim.x) {
-    const int k = idx / HW, hw = idx - k * HW;
-    const double a = fmin(fmax((double)xn[(2 * k) * (int64_t)HW + hw], kClampLo), kClampHi);
-    const double b = fmin(fmax((double)xn[(2 * k + 1) * (int64_t)HW + hw], kClampLo), kClampHi);
-    const double p = pair_softmax_b(a, b);
-    on[idx] = p;
-    if (p > 0.5) atomicAdd(&cnt[hw], 1);   // RN:342 sum(ord_c1 > 0.5)
+// ord[n,k,hw] = softmax(clamp(x[n,2k,hw]), clamp(x[n,2k+1,hw]))[1] (f64): one element per thread,
+// hw fastest in both tensors (coalesced).  Two f64 exp() per element: the kernel is bound by the FP64
+// pipe, not by HBM, so it is spread over the whole chip rather than one CTA per image.
+__global__ void __launch_bounds__(256) dorn_ord_kernel(const float* __restrict__ x, uint32_t total, uint32_t K, uint32_t HW,
+                                                       double* __restrict__ ord) {
+  for (uint32_t o = blockIdx.x * blockDim.x + threadIdx.x; o < total; o += gridDim.x * blockDim.x) {
+    const uint32_t hw = o % HW, nk = o / HW;
+    const uint32_t k = nk % K, n = nk / K;
+    const size_t ia = ((size_t)n * 2 * K + 2 * k) * HW + hw;
+    const double a = fmin(fmax((double)x[ia], kClampLo), kClampHi);
+    const double b = fmin(fmax((double)x[ia + HW], kClampLo), kClampHi);
+    ord[o] = pair_softmax_b(a, b);
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < HW; i += blockDim.x) decode[n * HW + i] = cnt[i];
+}
+
+// decode[n,hw] = #{k : ord[n,k,hw] > 0.5} (RN:342): one thread per (n, hw), k strided by HW.
+__global__ void __launch_bounds__(256) dorn_decode_kernel(const double* __restrict__ ord, uint32_t total_nhw, uint32_t K, uint32_t HW,
+                                                          int64_t* __restrict__ decode) {
+  for (uint32_t o = blockIdx.x * blockDim.x + threadIdx.x; o < total_nhw; o += gridDim.x * blockDim.x) {
+    const uint32_t hw = o % HW, n = o / HW;
+    const double* p = ord + (size_t)n * K * HW + hw;
+    int c = 0;
+    for (uint32_t k = 0; k < K; ++k) c += (p[(size_t)k * HW] > 0.5) ? 1 : 0;
+    decode[o] = c;
+  }
 }
 
 // backward: d ord / dB = ord (1 - ord), d ord / dA = -ord (1 - ord), gated by the clamp (RN:334).
@@ -46,10 +59,11 @@ __global__ void __launch_bounds__(256) dorn_regression_bwd_kernel(const float* _
                                                                   const double* __restrict__ g_ord, int64_t total, int K, int HW,
                                                                   float* __restrict__ gx) {
   for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
-    const int hw = (int)(o % HW);
-    const int64_t nk = o / HW;
-    const int k = (int)(nk % K);
-    const int64_t n = nk / K;
+    const uint32_t o32 = (uint32_t)o;   // total < 2^31 is checked on the host: 32-bit index arithmetic
+    const int hw = (int)(o32 % (uint32_t)HW);
+    const uint32_t nk = o32 / (uint32_t)HW;
+    const int k = (int)(nk % (uint32_t)K);
+    const int64_t n = nk / (uint32_t)K;
     const int64_t ia = (n * 2 * K + 2 * k) * HW + hw, ib = ia + HW;
     const double p = ord[o];
     const double g = g_ord[o] * p * (1.0 - p);
@@ -65,10 +79,11 @@ __global__ void __launch_bounds__(256) ordinal_loss_kernel(const double* __restr
   __shared__ double part[8];
   double acc = 0.0;
   for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
-    const int hw = (int)(o % HW);
-    const int64_t nk = o / HW;
-    const int k = (int)(nk % K);
-    const int64_t n = nk / K;
+    const uint32_t o32 = (uint32_t)o;   // total < 2^31 is checked on the host: 32-bit index arithmetic
+    const int hw = (int)(o32 % (uint32_t)HW);
+    const uint32_t nk = o32 / (uint32_t)HW;
+    const int k = (int)(nk % (uint32_t)K);
+    const int64_t n = nk / (uint32_t)K;
     const int t = target[n * HW + hw];
     const double p = ord[o];
     const double v = (k <= t) ? p : 1.0 - p;
@@ -97,10 +112,11 @@ __global__ void __launch_bounds__(256) ordinal_loss_bwd_kernel(const double* __r
                                                                double* __restrict__ g_ord) {
   const double g = (double)g_loss[0] * scale;
   for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
-    const int hw = (int)(o % HW);
-    const int64_t nk = o / HW;
-    const int k = (int)(nk % K);
-    const int64_t n = nk / K;
+    const uint32_t o32 = (uint32_t)o;   // total < 2^31 is checked on the host: 32-bit index arithmetic
+    const int hw = (int)(o32 % (uint32_t)HW);
+    const uint32_t nk = o32 / (uint32_t)HW;
+    const int k = (int)(nk % (uint32_t)K);
+    const int64_t n = nk / (uint32_t)K;
     const int t = target[n * HW + hw];
     const double p = ord[o];
     const double v = (k <= t) ? p : 1.0 - p;
@@ -108,12 +124,6 @@ __global__ void __launch_bounds__(256) ordinal_loss_bwd_kernel(const double* __r
     double d = (v >= 1e-8 && v <= 1e8) ? 1.0 / (double)(float)v : 0.0;
     g_ord[o] = g * ((k <= t) ? d : -d);
   }
-}
-
-static int grid_cap2(int64_t items) {
-  int64_t blocks = (items + 255) / 256;
-  if (blocks > (int64_t)kNumSMs * 8) blocks = (int64_t)kNumSMs * 8;
-  return blocks < 1 ? 1 : (int)blocks;
 }
 
 }  // namespace rdm
@@ -126,8 +136,14 @@ extern "C" int rdm_dorn_regression_f32(const float* x, int64_t n_images, int32_t
   RDM_REQUIRE(K >= 1 && HW >= 1 && HW <= 8192, "rdm_dorn_regression_f32: bad K / HW");
   RDM_REQUIRE(n_images >= 0 && n_images < (1ll << 31), "rdm_dorn_regression_f32: bad n_images");
   if (n_images == 0) return 0;
-  dorn_regression_kernel<<<(unsigned)n_images, 256, HW * sizeof(int), (cudaStream_t)stream>>>(x, K, HW, decode_out, ord_out);
-  return launch_status("dorn_regression_kernel");
+  const int64_t total = n_images * (int64_t)K * HW;
+  RDM_REQUIRE(total < (1ll << 31), "rdm_dorn_regression_f32: N*K*H*W must be below 2^31");
+  dorn_ord_kernel<<<grid_cap2(total), 256, 0, (cudaStream_t)stream>>>(x, (uint32_t)total, (uint32_t)K, (uint32_t)HW, ord_out);
+  int rc = launch_status("dorn_ord_kernel");
+  if (rc) return rc;
+  dorn_decode_kernel<<<grid_cap2(n_images * HW), 256, 0, (cudaStream_t)stream>>>(ord_out, (uint32_t)(n_images * HW), (uint32_t)K,
+                                                                                 (uint32_t)HW, decode_out);
+  return launch_status("dorn_decode_kernel");
 }
 
 extern "C" int rdm_dorn_regression_bwd(const float* x, const double* ord, const double* grad_ord, int64_t n_images, int32_t K, int32_t HW,
@@ -136,6 +152,7 @@ extern "C" int rdm_dorn_regression_bwd(const float* x, const double* ord, const 
   RDM_REQUIRE(K >= 1 && HW >= 1 && n_images >= 0, "rdm_dorn_regression_bwd: bad shape");
   if (n_images == 0) return 0;
   const int64_t total = n_images * K * HW;
+  RDM_REQUIRE(total < (1ll << 31), "rdm_dorn_regression_bwd: N*K*H*W must be below 2^31");
   dorn_regression_bwd_kernel<<<grid_cap2(total), 256, 0, (cudaStream_t)stream>>>(x, ord, grad_ord, total, K, HW, grad_x);
   return launch_status("dorn_regression_bwd_kernel");
 }
@@ -147,6 +164,7 @@ extern "C" int rdm_ordinal_loss_f64(const double* ord, const int32_t* target, in
   RDM_REQUIRE(ord && target && ws && loss_out, "rdm_ordinal_loss_f64: null pointer");
   RDM_REQUIRE(K >= 1 && HW >= 1 && n_images >= 1, "rdm_ordinal_loss_f64: bad shape");
   const int64_t total = n_images * K * HW;
+  RDM_REQUIRE(total < (1ll << 31), "rdm_ordinal_loss_f64: N*K*H*W must be below 2^31");
   const int grid = grid_cap2(total);
   ordinal_loss_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(ord, target, total, K, HW, ws);
   int rc = launch_status("ordinal_loss_kernel");
@@ -160,6 +178,7 @@ extern "C" int rdm_ordinal_loss_bwd(const double* ord, const int32_t* target, co
   RDM_REQUIRE(ord && target && grad_loss && grad_ord, "rdm_ordinal_loss_bwd: null pointer");
   RDM_REQUIRE(K >= 1 && HW >= 1 && n_images >= 1, "rdm_ordinal_loss_bwd: bad shape");
   const int64_t total = n_images * K * HW;
+  RDM_REQUIRE(total < (1ll << 31), "rdm_ordinal_loss_bwd: N*K*H*W must be below 2^31");
   ordinal_loss_bwd_kernel<<<grid_cap2(total), 256, 0, (cudaStream_t)stream>>>(ord, target, grad_loss, total, K, HW,
                                                                               -1.0 / ((double)n_images * HW), grad_ord);
   return launch_status("ordinal_loss_bwd_kernel");

@@ -51,6 +51,29 @@ template <typename TAcc>
 __device__ __forceinline__ TAcc pow_as(TAcc v, double e) {
   return (TAcc)pow((double)v, e);
 }
+// f64 rows (the ground truth, 16 384 values): prod_i x_i^e = exp(e * sum_i log x_i).  One log per
+// element instead of a pow (log + exp), and closer to the exact product than multiplying 16 384
+// individually rounded powers (2e-16 against ~1e-14 relative); it differs from the reference's
+// own product by that ~1e-14.  Accumulated as (sum of logs) in the "product" slot.
+template <typename TAcc>
+struct GmAcc {
+  static constexpr bool kLogSum = false;
+};
+template <>
+struct GmAcc<double> {
+  static constexpr bool kLogSum = true;
+};
+template <typename T>
+__device__ __forceinline__ T block_sum(T v, T* scratch /* >= 32 */) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if (lane == 0) scratch[w] = v;
+  __syncthreads();
+  T r = scratch[0];
+  for (int i = 1; i < nw; ++i) r += scratch[i];
+  return r;
+}
 
 // one CTA per batch row: gm[b] = prod_i pow(t[b,i], e);  optional normalised copy x / gm
 template <typename TIn, typename TAcc>
@@ -59,9 +82,19 @@ __global__ void __launch_bounds__(256) gm_kernel(const TIn* __restrict__ t, int6
   __shared__ TAcc scratch[32];
   const int64_t b = blockIdx.x;
   const TIn* row = t + b * n;
-  TAcc prod = (TAcc)1;
-  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) prod *= pow_as<TAcc>((TAcc)row[i], e);
-  const TAcc gm = block_prod<TAcc>(prod, scratch);
+  TAcc gm;
+  if constexpr (GmAcc<TAcc>::kLogSum) {
+    double a0 = 0.0, a1 = 0.0;   // two chains: independent log() calls in flight
+    for (int64_t i = threadIdx.x; i < n; i += 2 * blockDim.x) {
+      a0 += log((double)row[i]);
+      if (i + blockDim.x < n) a1 += log((double)row[i + blockDim.x]);
+    }
+    gm = (TAcc)exp(e * block_sum<double>(a0 + a1, reinterpret_cast<double*>(scratch)));
+  } else {
+    TAcc prod = (TAcc)1;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) prod *= pow_as<TAcc>((TAcc)row[i], e);
+    gm = block_prod<TAcc>(prod, scratch);
+  }
   if (gm_out && threadIdx.x == 0) gm_out[b] = gm;
   if (norm_out)
     for (int64_t i = threadIdx.x; i < n; i += blockDim.x) norm_out[b * n + i] = (TAcc)row[i] / gm;
@@ -82,13 +115,27 @@ __global__ void __launch_bounds__(256) gm_cluster_kernel(const TIn* __restrict__
   const int64_t b = blockIdx.x / kGmCluster;
   const int64_t chunk = n / kGmCluster;
   const TIn* row = t + b * n + rank * chunk;
-  TAcc prod = (TAcc)1;
-  for (int64_t i = threadIdx.x; i < chunk; i += blockDim.x) prod *= pow_as<TAcc>((TAcc)row[i], e);
-  const TAcc mine = block_prod<TAcc>(prod, scratch);
+  TAcc mine;
+  if constexpr (GmAcc<TAcc>::kLogSum) {
+    double a0 = 0.0, a1 = 0.0;
+    for (int64_t i = threadIdx.x; i < chunk; i += 2 * blockDim.x) {
+      a0 += log((double)row[i]);
+      if (i + blockDim.x < chunk) a1 += log((double)row[i + blockDim.x]);
+    }
+    mine = (TAcc)block_sum<double>(a0 + a1, reinterpret_cast<double*>(scratch));   // sum of logs of this eighth
+  } else {
+    TAcc prod = (TAcc)1;
+    for (int64_t i = threadIdx.x; i < chunk; i += blockDim.x) prod *= pow_as<TAcc>((TAcc)row[i], e);
+    mine = block_prod<TAcc>(prod, scratch);
+  }
   if (threadIdx.x == 0) part = mine;
   cluster.sync();
-  TAcc gm = (TAcc)1;
-  for (int r = 0; r < kGmCluster; ++r) gm *= *cluster.map_shared_rank(&part, r);   // rank order: deterministic
+  TAcc gm = GmAcc<TAcc>::kLogSum ? (TAcc)0 : (TAcc)1;
+  for (int r = 0; r < kGmCluster; ++r) {   // rank order: deterministic
+    const TAcc other = *cluster.map_shared_rank(&part, r);
+    gm = GmAcc<TAcc>::kLogSum ? gm + other : gm * other;
+  }
+  if constexpr (GmAcc<TAcc>::kLogSum) gm = (TAcc)exp(e * (double)gm);
   cluster.sync();   // nobody leaves while its `part` may still be read
   if (gm_out && rank == 0 && threadIdx.x == 0) gm_out[b] = gm;
   if (norm_out) {
@@ -419,11 +466,56 @@ __global__ void __launch_bounds__(512) make_pred_bwd_w_kernel(const double* __re
 
 // ---------------------------------------------------------------------------------------------
 // recombination: comps (in list order) d0? then sides 2,4,...; out side S = 2^n.
+// Four horizontally adjacent output pixels per thread (two 128-bit streaming stores; a warp writes
+// 1 KB contiguous): every component coarser than the last two levels contributes ONE gathered value
+// to all four, so the gather count per output pixel drops ~4x against a pixel-per-thread kernel.
 template <typename TC>
 __global__ void __launch_bounds__(256) recombination_kernel(PtrList comps, int n_comps, int has_d0, int n, int64_t batch,
                                                             double* __restrict__ out) {
+  const int S = 1 << n, Q = S >> 2;          // Q quads per row (S >= 4)
+  const int64_t per = (int64_t)S * Q;
+  const int64_t total = batch * per;
+  for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = o / per;
+    const int rem = (int)(o - b * per);
+    const int y = rem / Q, x = (rem - y * Q) << 2;
+    double a[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int j = has_d0; j < n_comps; ++j) {
+      const int cs = comps.side[j];
+      const int sh = n - (31 - __clz(cs));
+      const TC* c = reinterpret_cast<const TC*>(comps.p[j]) + b * (int64_t)cs * cs + (y >> sh) * cs + (x >> sh);
+      double v[4];
+      if (sh >= 2) {
+        v[0] = v[1] = v[2] = v[3] = (double)c[0];
+      } else if (sh == 1) {
+        v[0] = v[1] = (double)c[0];
+        v[2] = v[3] = (double)c[1];
+      } else {
+        v[0] = (double)c[0];
+        v[1] = (double)c[1];
+        v[2] = (double)c[2];
+        v[3] = (double)c[3];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = (j == has_d0) ? v[i] : a[i] + v[i];
+    }
+    if (has_d0) {
+      const double d0 = (double)reinterpret_cast<const TC*>(comps.p[0])[b];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = d0 + a[i];
+    }
+    double* dst = out + b * (int64_t)S * S + (int64_t)y * S + x;
+    stg_stream_f64x2(dst, a[0], a[1]);
+    stg_stream_f64x2(dst + 2, a[2], a[3]);
+  }
+}
+
+// Small outputs (side 2): two pixels per thread.
+template <typename TC>
+__global__ void __launch_bounds__(256) recombination_small_kernel(PtrList comps, int n_comps, int has_d0, int n, int64_t batch,
+                                                                  double* __restrict__ out) {
   const int S = 1 << n;
-  const int64_t per = (int64_t)S * S / 2;   // two horizontally adjacent pixels per thread
+  const int64_t per = (int64_t)S * S / 2;
   const int64_t total = batch * per;
   for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
     const int64_t b = o / per;
@@ -435,13 +527,8 @@ __global__ void __launch_bounds__(256) recombination_kernel(PtrList comps, int n
       const int sh = n - (31 - __clz(cs));
       const TC* c = reinterpret_cast<const TC*>(comps.p[j]) + b * (int64_t)cs * cs + (y >> sh) * cs;
       const double v0 = (double)c[x >> sh], v1 = (double)c[(x + 1) >> sh];
-      if (j == has_d0) {
-        a0 = v0;
-        a1 = v1;
-      } else {
-        a0 += v0;
-        a1 += v1;
-      }
+      a0 = (j == has_d0) ? v0 : a0 + v0;
+      a1 = (j == has_d0) ? v1 : a1 + v1;
     }
     if (has_d0) {
       const double d0 = (double)reinterpret_cast<const TC*>(comps.p[0])[b];
@@ -737,7 +824,7 @@ __global__ void __launch_bounds__(RDM_TAIL_THREADS) fuse_tail_kernel(const __gri
 
 static int grid_cap(int64_t items, int per_block) {
   int64_t blocks = (items + per_block - 1) / per_block;
-  if (blocks > (int64_t)kNumSMs * 8) blocks = (int64_t)kNumSMs * 8;
+  if (blocks > (int64_t)kNumSMs * 16) blocks = (int64_t)kNumSMs * 16;   // 8 resident CTAs of 256 threads per SM, two waves
   return blocks < 1 ? 1 : (int)blocks;
 }
 
@@ -974,11 +1061,20 @@ extern "C" int rdm_recombination_f64(const void* const* comps, const int32_t* si
     pl.p[j] = comps[j];
     pl.side[j] = sides[j];
   }
-  const int64_t items = batch * ((int64_t)1 << (2 * n)) / 2;
-  if (comps_are_f64)
-    recombination_kernel<double><<<grid_cap(items, 256), 256, 0, (cudaStream_t)stream>>>(pl, n_comps, has_d0, n, batch, out);
-  else
-    recombination_kernel<float><<<grid_cap(items, 256), 256, 0, (cudaStream_t)stream>>>(pl, n_comps, has_d0, n, batch, out);
+  if (n >= 2) {
+    const int64_t items = batch * ((int64_t)1 << (2 * n)) / 4;
+    const int grid = grid_cap(items, 256);
+    if (comps_are_f64)
+      recombination_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>(pl, n_comps, has_d0, n, batch, out);
+    else
+      recombination_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(pl, n_comps, has_d0, n, batch, out);
+  } else {
+    const int64_t items = batch * ((int64_t)1 << (2 * n)) / 2;
+    if (comps_are_f64)
+      recombination_small_kernel<double><<<grid_cap(items, 256), 256, 0, (cudaStream_t)stream>>>(pl, n_comps, has_d0, n, batch, out);
+    else
+      recombination_small_kernel<float><<<grid_cap(items, 256), 256, 0, (cudaStream_t)stream>>>(pl, n_comps, has_d0, n, batch, out);
+  }
   return launch_status("recombination_kernel");
 }
 

@@ -62,4 +62,12 @@ out["gt_normalize+decompose_128"] = dict(us=t * 1e6, gbs=B * (131072 * 3 + 17476
 comps = [torch.randn(B, 1, 2 ** k, 2 ** k, generator=g).to(dev) for k in range(8)]
 t = timeit(lambda: R.recombination(comps, 7), flush=flush)
 out["recombination_128"] = dict(us=t * 1e6, gbs=B * (131072 + 4 * 21845) / t / 1e9)
+# SURVEY 8f "next" row: DORN head + ordinal loss (K = 90 ordinal bins on the 8x8 map)
+xh = torch.randn(B, 180, 8, 8, generator=g).to(dev)
+t = timeit(lambda: R.dorn_regression(xh), flush=flush)
+out["dorn_regression"] = dict(us=t * 1e6, gbs=B * (180 * 64 * 4 + 90 * 64 * 8 + 64 * 8) / t / 1e9)
+_, ordp = R.dorn_regression(xh)
+tgt = torch.randint(0, 90, (B, 1, 8, 8), generator=g).to(dev)
+t = timeit(lambda: R.ordinal_loss(ordp, tgt), flush=flush)
+out["ordinal_loss"] = dict(us=t * 1e6, gbs=B * (90 * 64 * 8 + 64 * 4) / t / 1e9)
 print(json.dumps(out, indent=1))
