@@ -232,6 +232,51 @@ def time_serial(fns, reps):
     return start.elapsed_time(end) / (rounds * n) * 1e-3   # seconds per launch
 
 
+def stage_kernel_table(dev, batch):
+    """Stand-alone streaming kernels of the path (the drop-in ops), graph-timed (8 calls per graph, no host
+    dispatch in the timed region): algorithmic GB/s per kernel (SURVEY 8d byte formulas)."""
+    import md_rdm_b200.ops  # noqa: F401
+    from md_rdm_b200.codebooks import default_quantization
+    R = torch.ops.rdm
+    g = torch.Generator().manual_seed(7)
+    q = default_quantization()
+    x8 = torch.exp(0.3 * torch.randn(batch, 1, 8, 8, generator=g)).to(dev)
+    x32 = torch.exp(0.3 * torch.randn(batch, 1, 32, 32, generator=g)).to(dev)
+    raw32, _ = R.pair_id(x32)
+    thr, lvl = q.device_tables(32, dev)
+    y = (0.5 + 9.5 * torch.rand(batch, 1, 128, 128, generator=g, dtype=torch.float64)).to(dev)
+    comps = [torch.randn(batch, 1, 2 ** k, 2 ** k, generator=g).to(dev) for k in range(8)]
+    cases = {
+        "pair_v1": (lambda: R.pair_v1(x8), batch * (256 + 16384)),
+        "pair_id_32": (lambda: R.pair_id(x32), batch * (4096 + 2048 + 4 * 131072)),
+        "lloyd_quantize_f64_32": (lambda: R.lloyd_quantize(raw32, thr, lvl), raw32.numel() * 17),
+        "gm_normalize+decompose_gt128": (lambda: R.decompose(R.gm_normalize(y), False), batch * (3 * 131072 + 174760)),
+        "recombination_128": (lambda: R.recombination(comps, 7), batch * (131072 + 4 * 21845)),
+    }
+    out = {}
+    for name, (fn, nbytes) in cases.items():
+        stream = torch.cuda.Stream()
+        with torch.cuda.stream(stream):
+            fn()
+        stream.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr, stream=stream):
+            for _ in range(8):
+                fn()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            gr.replay()
+            s0.record(stream)
+            for _ in range(4):
+                gr.replay()
+            s1.record(stream)
+        stream.synchronize()
+        t = s0.elapsed_time(s1) / 32 * 1e-3
+        out[name] = {"us": round(t * 1e6, 2), "gbs": round(nbytes / t / 1e9, 1)}
+        del gr
+    return out
+
+
 def cpu_baseline_port(images: int):
     """The reference's CPU algorithm (literal port) on a bounded sample of the same workload."""
     from oracle import fusion_ref as fr
@@ -355,6 +400,9 @@ def run_ours(args):
         reps = max(K // nb, 1)
         eb_dev_ms, eb_wall_ms = timed(K, lambda k: [e2e_graph.replay() for _ in range(reps)])
         eb_ms = dist_max(max(eb_dev_ms, eb_wall_ms), dev) / (reps * nb) * K
+        stage = {}
+        if rank == 0 and not args.no_stage_table:
+            stage = {"batch_16": stage_kernel_table(dev, 16), "batch_256": stage_kernel_table(dev, 256)}
     clocks = clk.summary()
 
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -388,6 +436,9 @@ def run_ours(args):
             "kernel_gbs": {"als_iterate": achieved, "als_select": ab["als_select_kernel"] * BATCH / t_sel / 1e9,
                            "fuse_tail": ab["tail_kernel"] * BATCH / t_tail / 1e9},
             "path_gbs_at_value": ab["path"] * BATCH * K / (dev_ms * 1e-3) / 1e9,
+            "stage_kernels": stage,
+            "stage_kernels_note": "stand-alone drop-in ops, CUDA-graph timed, algorithmic GB/s; at batch 16 the inputs are L2-resident "
+                                  "and the kernels are launch-latency bound, at batch 256 they stream from HBM",
         },
         "clocks": clocks,
         "e2e": {"value": world * K * BATCH / (e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": e2e_ring[0].h2d_bytes(),
@@ -473,6 +524,7 @@ def main():
     ap.add_argument("--ring", type=int, default=32, help="resident input batches (ring > L2)")
     ap.add_argument("--cpu-images", type=int, default=48)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-stage-table", action="store_true")
     ap.add_argument("--scales", default="8,16,32", help="relative decoder scales (default: BASELINE configs[1]); "
                     "8,16,32,64 is the configuration network/RDM_Net.py:96-97 names")
     ap.add_argument("--ref-budget-s", type=float, default=200.0, help="--impl reference: wall-clock budget for the literal port")
