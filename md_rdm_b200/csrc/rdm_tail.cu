@@ -904,30 +904,35 @@ extern "C" int rdm_decompose(const void* in, int32_t in_is_f64, int64_t n_images
   if (len == 0) return 0;
   const size_t smem = kPyrDoubles * sizeof(double);
   cudaError_t e;
-  if (side == 128) {
-    // banded top level over the whole chip, then the per-image kernel on D_6 (parked in the F_6 slot)
-    const size_t tsm = (10 * 128 + 4 * 64) * sizeof(double);
-    const unsigned ctas = (unsigned)(n_images * 16);
-    RDM_REQUIRE(n_images * 16 < (1ll << 31), "rdm_decompose: too many images");
-    if (in_is_f64)
-      decompose_top_kernel<double><<<ctas, 256, tsm, (cudaStream_t)stream>>>((const double*)in, 128, 7, relative_map, pyramid_out, n_images);
+  // Levels of side >= 64 are banded over the whole chip (8 output rows per CTA, 128-bit accesses); each such
+  // launch parks D_{k-1} in the F_{k-1} slot of the output, where the next launch reads it.  The remaining
+  // 32x32 (or smaller) pyramid is one CTA per image in shared memory.
+  const void* cur = in;
+  int cur_f64 = in_is_f64, s = side, nc = n;
+  const int base = relative_map ? 0 : 1;
+  while (s >= 64) {
+    const size_t tsm = (size_t)(10 * s + 4 * (s / 2)) * sizeof(double);
+    RDM_REQUIRE(n_images * (s / 8) < (1ll << 31), "rdm_decompose: too many images");
+    const unsigned ctas = (unsigned)(n_images * (s / 8));
+    if (cur_f64)
+      decompose_top_kernel<double><<<ctas, 256, tsm, (cudaStream_t)stream>>>((const double*)cur, s, nc, relative_map, pyramid_out, n_images);
     else
-      decompose_top_kernel<float><<<ctas, 256, tsm, (cudaStream_t)stream>>>((const float*)in, 128, 7, relative_map, pyramid_out, n_images);
+      decompose_top_kernel<float><<<ctas, 256, tsm, (cudaStream_t)stream>>>((const float*)cur, s, nc, relative_map, pyramid_out, n_images);
     int rc = launch_status("decompose_top_kernel");
     if (rc) return rc;
-    e = ensure_dyn_smem(decompose_kernel<double>, smem, smem_set_decompose_kernel_double_);
-    if (e == cudaSuccess) {
-      const double* d6 = pyramid_out + n_images * ((relative_map ? 0 : 1) + off_fine(6));
-      decompose_kernel<double><<<(unsigned)n_images, 256, smem, (cudaStream_t)stream>>>(d6, 64, 6, relative_map, pyramid_out, n_images);
-    }
-  } else if (in_is_f64) {
+    cur = pyramid_out + n_images * (base + off_fine(nc - 1));
+    cur_f64 = 1;
+    s >>= 1;
+    --nc;
+  }
+  if (cur_f64) {
     e = ensure_dyn_smem(decompose_kernel<double>, smem, smem_set_decompose_kernel_double_);
     if (e == cudaSuccess)
-      decompose_kernel<double><<<(unsigned)n_images, 256, smem, (cudaStream_t)stream>>>((const double*)in, side, n, relative_map, pyramid_out, n_images);
+      decompose_kernel<double><<<(unsigned)n_images, 256, smem, (cudaStream_t)stream>>>((const double*)cur, s, nc, relative_map, pyramid_out, n_images);
   } else {
     e = ensure_dyn_smem(decompose_kernel<float>, smem, smem_set_decompose_kernel_float_);
     if (e == cudaSuccess)
-      decompose_kernel<float><<<(unsigned)n_images, 256, smem, (cudaStream_t)stream>>>((const float*)in, side, n, relative_map, pyramid_out, n_images);
+      decompose_kernel<float><<<(unsigned)n_images, 256, smem, (cudaStream_t)stream>>>((const float*)cur, s, nc, relative_map, pyramid_out, n_images);
   }
   if (e != cudaSuccess) {
     set_error("rdm_decompose: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
