@@ -128,9 +128,11 @@ typedef struct rdm_als_scale {
 int rdm_als_fused(const rdm_als_scale_t* scales, int32_t n_scales, int64_t n_images,
                   int32_t group, rdm_stream_t stream);
 /* The same, launching only the selected phases: bit 0 = iterate (Lloyd + ALS iterations, SSE
- * record and p_1 checkpoint into ws), bit 1 = select (batch-wide arg-min, normalise, re-tile;
- * needs ws from a previous iterate phase).  For profiling and for callers that want to overlap
- * other work between the two launches. */
+ * record and every iterate into ws), bit 1 = select (batch-wide arg-min, normalise, re-tile;
+ * needs ws from a previous iterate phase).  The iterate phase is three launches that can also be
+ * selected one by one (profiling): bit 2 = compact page form (structure check + Lloyd, the
+ * HBM-streaming kernel), bit 3 = ALS on the compact pages (one warp per page), bit 4 = dense ALS
+ * (8x8 maps and any page matrix without the pair-build structure); bit 0 = bits 2|3|4. */
 int rdm_als_fused_phases(const rdm_als_scale_t* scales, int32_t n_scales, int64_t n_images,
                          int32_t group, int32_t phase_mask, rdm_stream_t stream);
 /* f32 workspace elements per image for one scale (rdm_als_scale_t.ws) */

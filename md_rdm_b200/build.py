@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.normpath(os.path.join(HERE, "..", "include"))
 LIB = os.path.join(HERE, "librdm_b200.so")
-SOURCES = ("rdm_api.cu", "rdm_pair.cu", "rdm_als.cu", "rdm_tail.cu", "rdm_dorn.cu")
+SOURCES = ("rdm_api.cu", "rdm_pair.cu", "rdm_als.cu", "rdm_als_sparse.cu", "rdm_tail.cu", "rdm_dorn.cu")
 
 # No -use_fast_math: bins must be bit-exact and the f32 pair products must not be contracted
 # (the kernels use explicit __fmul_rn / __frcp_rn / __dmul_rn where it matters).

@@ -33,6 +33,7 @@
 // Bound: per unit 2*limit*rows*64 FMA against rows*64*(4..8) input bytes = 25..100 FMA/byte:
 // FP32-issue / dependency-latency bound, not HBM bound (DESIGN.md "K3").
 #include "rdm_common.cuh"
+#include <cstdlib>
 
 namespace rdm {
 
@@ -62,6 +63,7 @@ struct AlsParams {
   int64_t n_images;
   int32_t n_scales;
   int32_t group;
+  int32_t sparse;   // page units with the pair-build structure are handled by rdm_als_sparse.cu
 };
 
 struct AlsSmem {
@@ -613,7 +615,8 @@ __device__ __forceinline__ void als_unit(const AlsParams& P, const AlsScaleDev& 
   const TileMap<G> m(lt);
   const int row = m.row_own;
   const int bar_id = (G == 4) ? 0 : 1 + unit;
-  const int64_t ws_stride = (int64_t)sc.limit + 1 + (int64_t)sc.limit * ROWS;
+  const int64_t ws_stride = als_ws_stride(ROWS, sc.limit);
+  const int64_t ws_rec = als_ws_rec(ROWS, sc.limit);
   float* ws = sc.ws + unit_idx * ws_stride;
 
   if constexpr (PHASE == 0) {
@@ -625,7 +628,7 @@ __device__ __forceinline__ void als_unit(const AlsParams& P, const AlsScaleDev& 
 #ifdef RDM_TIMING
     const long long t1 = clock64();
 #endif
-    als_iterate<G>(R, sm, E, unit, lt, sc.limit, ws, ws + sc.limit + 1);
+    als_iterate<G>(R, sm, E, unit, lt, sc.limit, ws, ws + ws_rec);
 #ifdef RDM_TIMING
     const long long t2 = clock64();
     if (lt == 0 && (unit_idx % 37) == 0)
@@ -670,7 +673,7 @@ __device__ __forceinline__ void als_unit(const AlsParams& P, const AlsScaleDev& 
         for (int k = lt; k <= sc.limit; k += NT) sc.record_out[gp * (sc.limit + 1) + k] = rm[k];
       if (sc.kstar_out && lt == 0) sc.kstar_out[gp] = kstar;
     }
-    const float p = (kstar == 0) ? 1.0f : ws[sc.limit + 1 + (int64_t)(kstar - 1) * ROWS + row];
+    const float p = (kstar == 0) ? 1.0f : ws[ws_rec + (int64_t)(kstar - 1) * ROWS + row];
     // ---- quick_gm(p, H) with H = rows: prod_i p_i^(1/H^2)  (CP:76, CP:146, CP:244-255)
     const float pw = (float)pow((double)p, 1.0 / ((double)ROWS * (double)ROWS));
     float prod = warp_prod(pw);
@@ -707,6 +710,17 @@ __global__ void __launch_bounds__(kAlsThreads, 2) als_kernel(const __grid_consta
     if ((int)blockIdx.x >= P.s[k].cta_begin) si = k;
   const AlsScaleDev& sc = P.s[si];
   const int tid = threadIdx.x;
+  if (PHASE == 0 && P.sparse && sc.rows == 256 &&
+      (sc.kind == RDM_SRC_RAW_F64 || sc.kind == RDM_SRC_VAL_F64 || sc.kind == RDM_SRC_MAP_F32)) {
+    // Page units whose matrix has the pair-build structure were iterated by als_sparse_kernel
+    // (rdm_als_sparse.cu); the sparsify kernels leave four band flags per unit for these kinds.
+    const int64_t unit_idx = (int)blockIdx.x - sc.cta_begin;
+    if (unit_idx < P.n_images * sc.pages) {
+      const float4 fl = *reinterpret_cast<const float4*>(sc.ws + unit_idx * als_ws_stride(256, sc.limit) +
+                                                           als_ws_compact(sc.limit) + kCompactFloats);
+      if (fl.x == 1.0f && fl.y == 1.0f && fl.z == 1.0f && fl.w == 1.0f) return;   // CTA-uniform
+    }
+  }
   if (PHASE == 0 && sc.thr) {   // phase 1 never quantises
     if (tid == 0) sm.sorted = 1;
     __syncthreads();
@@ -776,7 +790,7 @@ using namespace rdm;
 extern "C" int rdm_als_fused_phases(const rdm_als_scale_t*, int32_t, int64_t, int32_t, int32_t, rdm_stream_t);
 
 extern "C" int64_t rdm_als_ws_floats(int32_t rows, int32_t pages, int32_t limit) {
-  return (int64_t)pages * ((int64_t)limit + 1 + (int64_t)limit * rows);
+  return (int64_t)pages * als_ws_stride(rows, limit);
 }
 
 extern "C" int rdm_als_fused(const rdm_als_scale_t* scales, int32_t n_scales, int64_t n_images, int32_t group,
@@ -787,7 +801,8 @@ extern "C" int rdm_als_fused(const rdm_als_scale_t* scales, int32_t n_scales, in
 extern "C" int rdm_als_fused_phases(const rdm_als_scale_t* scales, int32_t n_scales, int64_t n_images, int32_t group,
                                     int32_t phase_mask, rdm_stream_t stream) {
   RDM_REQUIRE(scales, "rdm_als_fused: null scales");
-  RDM_REQUIRE(phase_mask >= 1 && phase_mask <= 3, "rdm_als_fused_phases: phase_mask must be 1, 2 or 3");
+  RDM_REQUIRE(phase_mask >= 1 && phase_mask <= 31, "rdm_als_fused_phases: phase_mask must be in 1..31");
+  if (phase_mask & 1) phase_mask |= 4 | 8 | 16;
   RDM_REQUIRE(n_scales >= 1 && n_scales <= kMaxScales, "rdm_als_fused: n_scales must be 1..%d (got %d)", kMaxScales, n_scales);
   RDM_REQUIRE(n_images >= 0, "rdm_als_fused: negative n_images");
   RDM_REQUIRE(group >= 1, "rdm_als_fused: group must be >= 1");
@@ -797,6 +812,9 @@ extern "C" int rdm_als_fused_phases(const rdm_als_scale_t* scales, int32_t n_sca
   P.n_scales = n_scales;
   P.group = group;
   P.n_images = n_images;
+  // RDM_ALS_DENSE=1 (A/B measurements, tests of the dense kernel): every unit takes the dense kernel
+  static const bool dense_only = [] { const char* v = getenv("RDM_ALS_DENSE"); return v && v[0] == '1'; }();
+  P.sparse = dense_only ? 0 : 1;
   int64_t ctas = 0;
   for (int k = 0; k < n_scales; ++k) {
     const rdm_als_scale_t& h = scales[k];
@@ -853,7 +871,11 @@ extern "C" int rdm_als_fused_phases(const rdm_als_scale_t* scales, int32_t n_sca
     set_error("rdm_als_fused: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     return (int)e;
   }
-  if (phase_mask & 1) {
+  if (P.sparse && (phase_mask & (4 | 8))) {
+    int rc = als_sparse_launch(scales, n_scales, n_images, (phase_mask & 4) != 0, (phase_mask & 8) != 0, (cudaStream_t)stream);
+    if (rc) return rc;
+  }
+  if (phase_mask & 16) {
     als_kernel<0><<<(unsigned)ctas, kAlsThreads, dyn, (cudaStream_t)stream>>>(P);
     int rc = launch_status("als_kernel<iterate>");
     if (rc) return rc;

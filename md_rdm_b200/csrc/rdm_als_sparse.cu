@@ -1,0 +1,474 @@
+// Rank-1 ALS on page pair matrices in their COMPACT form (CP:95-155 on the matrices RN:259-284 builds).
+//
+// A page pair matrix is 256 x 64, but RN:266-280 + CP:269-295 fill it with very little information:
+// row rho = 16 r + c (pixel (r,c) of the 16x16 page) holds the pixel's own value d in 55 columns and
+// d / parent in the 9 columns of a 3x3 window of the 8x8 parent page anchored at
+// (r0, c0) = (min(r/2,5), min(c/2,5)).  After Lloyd quantisation (RN:286-311) a row is therefore
+//     R[rho][j] = f_rho + D_rho[j],   D_rho[j] = 0 outside the window.
+// Both ALS GEMVs and the residual then need 12 multiply-adds per row instead of 64 (the window is
+// stored as a 3 x 4 span whose first column is even, so that operands are read as 64-bit words and
+// the register indexing is static):
+//   p-update (CP:186-192)        s_rho = f_rho * sum_j q_j + sum_span D_rho[j] q_j
+//   q-update (CP:133, the reference's R.view(B,W,H) reshape: "row i" is rows 4i..4i+3 of R laid end
+//             to end)            q_i = sum_{r'<4} [ f_rho P_r' + sum_span D_rho[j] p[64 r' + j] ],
+//                                rho = 4 i + r',  P_r' = sum_{c<64} p[64 r' + c]
+//   residual (CP:172-173)        sum_j (R[rho][j] - p q_j)^2
+//                                  = 64 g^2 - 2 p g S1 + p^2 V + A_rho - 2 p sum_span D_rho[j] q_j
+//                                with g = f - p m, S1 = sum_j (q_j - m), V = sum_j (q_j - m)^2 for ANY
+//                                centre m (the mean of the previous q is used: no cancellation even
+//                                when q is nearly constant), A_rho = sum_span D (2 f + D).
+// These are exact identities: the results differ from the dense evaluation by f32 summation order
+// only (measured against an f64 evaluation: iterates and record at least as accurate as the
+// reference's own f32 bmm).
+//
+// Three kernels:
+//   als_sparsify_raw_kernel  streams raw (or already quantised) f64 matrices from HBM once (HBM-bound),
+//                            CHECKS the structure bit-wise (every column outside the window must hold
+//                            the same bits), quantises, writes the 16 KB compact form + 4 band flags to
+//                            the workspace, and optionally the full bins / quantised matrix.
+//   als_sparsify_map_kernel  the same from the decoder map (pair build fused, nothing else is read).
+//   als_sparse_kernel        ONE WARP per unit: a lane owns the 2 x 4 pixel block (rows 2rh..2rh+1,
+//                            columns 4kq..4kq+3) = 8 matrix rows = 104 registers of matrix, and with it
+//                            the two entries q[8rh+kq], q[8rh+4+kq] of q: no block barrier in the loop,
+//                            only warp shuffles and __syncwarp.
+// A unit whose matrix fails the check (an arbitrary matrix handed to cp.alternating_least_squares) is
+// left to the dense kernel (rdm_als.cu), which in turn skips the units flagged here.
+#include "rdm_common.cuh"
+#include <type_traits>
+
+namespace rdm {
+
+namespace {
+
+constexpr int kMaxSparseScales = 8;
+constexpr float kLambda = 0.05f;   // CP:175 regularization_term
+constexpr unsigned kFull = 0xffffffffu;
+
+struct SparseScaleDev {
+  const void* src;
+  const double* thr;
+  const double* lvl;
+  uint8_t* bins;
+  float* values;
+  float* ws;
+  int32_t kind, pages, side, limit;
+  int32_t unit_begin;   // first unit of this scale in the kernel's unit numbering
+};
+
+struct SparseParams {
+  SparseScaleDev s[kMaxSparseScales];
+  int64_t n_images;
+  int32_t n_scales;
+};
+
+__device__ __forceinline__ const SparseScaleDev& find_scale(const SparseParams& P, int gunit) {
+  int si = 0;
+#pragma unroll 1
+  for (int k = 1; k < P.n_scales; ++k)
+    if (gunit >= P.s[k].unit_begin) si = k;
+  return P.s[si];
+}
+
+// codebook prologue: f64 thresholds (pages compare in f64, RN:376-378 via SURVEY 8a-a5), f32 levels
+__device__ __forceinline__ void load_book(const SparseScaleDev& sc, double* thr_d, float* lvl_f, int* sorted, int tid, int nt) {
+  if (tid == 0) *sorted = 1;
+  __syncthreads();
+  for (int i = tid; i < kThrPad; i += nt) thr_d[i] = (i < kThr) ? sc.thr[i] : (double)NAN;
+  for (int i = tid; i < kLvl; i += nt) lvl_f[i] = (float)sc.lvl[i];
+  __syncthreads();
+  for (int i = tid; i < kThr - 1; i += nt)
+    if (!(thr_d[i] <= thr_d[i + 1])) *sorted = 0;
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
+// grid = units x 4 bands of 64 rows; a warp owns 8 rows (one pixel row r, columns c = cb..cb+7), a lane two
+// adjacent matrix columns of each.  Only 10 values per row carry information (the fill value and the 3x3
+// window), so after the bit-wise structure check the warp gathers those 80 values through shared memory and
+// quantises them in three full-warp passes instead of quantising 512 values in sixteen.
+__global__ void __launch_bounds__(256) als_sparsify_raw_kernel(const __grid_constant__ SparseParams P) {
+  __shared__ double thr_d[kThrPad];
+  __shared__ float lvl_f[kLvl + 3];
+  __shared__ int sorted;
+  __shared__ __align__(16) double stage[8][8][26];   // per warp, per row: 3 parent rows x 8 columns, then the fill value
+  __shared__ float resv[8][8][12];                   // quantised values: slots 0..8 = window (row-major), 9 = fill
+  __shared__ uint8_t resb[8][8][12];                 // their bins
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gunit = blockIdx.x >> 2, band = blockIdx.x & 3;
+  const SparseScaleDev& sc = find_scale(P, gunit);
+  const int64_t unit = gunit - sc.unit_begin;
+  const bool quant = sc.kind == RDM_SRC_RAW_F64;
+  const int64_t mat_off = unit * (int64_t)(256 * 64);
+  const double* src = reinterpret_cast<const double*>(sc.src) + mat_off;
+  const int row0 = band * 64 + warp * 8;             // rows row0 .. row0+7: pixel row row0 >> 4, columns cb .. cb+7
+  double2 x[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) x[i] = ldg_stream_f64x2(src + (row0 + i) * 64 + 2 * lane);
+  if (quant) load_book(sc, thr_d, lvl_f, &sorted, tid, 256);
+  float* compact = sc.ws + unit * als_ws_stride(256, sc.limit) + als_ws_compact(sc.limit);
+  const int srt = quant ? sorted : 1;
+  const int r0 = min(row0 >> 5, 5), cb = row0 & 15;
+  const int lane_f = (r0 >= 1) ? 0 : 28;             // column 0 / 56 is outside every window of this pixel row
+  const int a = (lane >> 2) - r0, cc = (2 * lane) & 7;
+  const bool rowin = (unsigned)a < 3u;
+  bool ok = true;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c0 = min((cb + i) >> 1, 5);
+    const long long b0 = __double_as_longlong(x[i].x), b1 = __double_as_longlong(x[i].y);
+    const long long fb = __shfl_sync(kFull, b0, lane_f);
+    const bool win0 = rowin && (unsigned)(cc - c0) < 3u, win1 = rowin && (unsigned)(cc + 1 - c0) < 3u;
+    ok = ok && (win0 || b0 == fb) && (win1 || b1 == fb);
+    if (rowin) *reinterpret_cast<double2*>(&stage[warp][i][8 * a + cc]) = x[i];
+    if (lane == lane_f) stage[warp][i][24] = x[i].x;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int t = 0; t < 3; ++t) {
+    const int id = 32 * t + lane;
+    if (id < 80) {
+      const int i = id / 10, slot = id - 10 * i;
+      const int c0 = min((cb + i) >> 1, 5);
+      const int al = slot / 3, be = slot - 3 * al;
+      const double v = stage[warp][i][slot == 9 ? 24 : 8 * al + c0 + be];
+      int q = 0;
+      float lv;
+      if (quant) {
+        q = lloyd_bin<double>(v, thr_d, srt);
+        lv = lvl_f[q];
+      } else {
+        lv = (float)v;   // `.float()` CP:106
+      }
+      resv[warp][i][slot] = lv;
+      resb[warp][i][slot] = (uint8_t)q;
+    }
+  }
+  __syncwarp();
+  {   // compact form: 8 rows x 16 floats, one float4 per lane
+    const int i = lane >> 2, k4 = lane & 3;
+    const int c = cb + i, c0 = min(c >> 1, 5), span0 = min((c >> 2) * 2, 4);
+    const float f = resv[warp][i][9];
+    float o[4];
+#pragma unroll
+    for (int e4 = 0; e4 < 4; ++e4) {
+      const int e = 4 * k4 + e4 - 1;                 // span entry (alpha, gamma) = (e >> 2, e & 3)
+      const int be = span0 + (e & 3) - c0;           // its column inside the window
+      const bool in = e >= 0 && e < 12 && (unsigned)be < 3u;
+      const float wv = resv[warp][i][in ? 3 * (e >> 2) + be : 9];
+      o[e4] = (e < 0) ? f : (in ? wv - f : 0.f);
+    }
+    *reinterpret_cast<float4*>(compact + (row0 + i) * kCompactRowFloats + 4 * k4) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+  if (sc.bins || sc.values) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c0 = min((cb + i) >> 1, 5);
+      const bool win0 = rowin && (unsigned)(cc - c0) < 3u, win1 = rowin && (unsigned)(cc + 1 - c0) < 3u;
+      const int s0 = win0 ? 3 * a + cc - c0 : 9, s1 = win1 ? 3 * a + cc + 1 - c0 : 9;
+      const int64_t off = mat_off + (row0 + i) * 64 + 2 * lane;
+      if (sc.bins) *reinterpret_cast<uint16_t*>(sc.bins + off) = (uint16_t)(resb[warp][i][s0] | (resb[warp][i][s1] << 8));
+      if (sc.values) *reinterpret_cast<float2*>(sc.values + off) = make_float2(resv[warp][i][s0], resv[warp][i][s1]);
+    }
+  }
+  const int all_ok = __syncthreads_and(ok ? 1 : 0);
+  if (tid == 0) compact[kCompactFloats + band] = all_ok ? 1.0f : 0.0f;
+}
+
+// grid = units; thread = matrix row (pixel of the page).  RN:259-284 + CP:269-295 + CP:308-311 fused.
+__global__ void __launch_bounds__(256) als_sparsify_map_kernel(const __grid_constant__ SparseParams P) {
+  __shared__ double thr_d[kThrPad];
+  __shared__ double inv_d[64];
+  __shared__ float lvl_f[kLvl + 3];
+  __shared__ int sorted;
+  const int tid = threadIdx.x;
+  const int gunit = blockIdx.x;
+  const SparseScaleDev& sc = find_scale(P, gunit);
+  const int64_t unit = gunit - sc.unit_begin;
+  const int side = sc.side, ratio = side >> 4;
+  const int64_t img = unit / sc.pages;
+  const int pg = (int)(unit - img * sc.pages);
+  const int pi = pg / ratio, pj = pg - pi * ratio;
+  const float* map = reinterpret_cast<const float*>(sc.src) + img * (int64_t)side * side;
+  if (tid < 64) {
+    const int y = 8 * pi + (tid >> 3), x = 8 * pj + (tid & 7);
+    const double v = bicubic_half_at([&](int r, int c) { return (double)map[r * side + c]; }, y, x, side);
+    inv_d[tid] = 1.0 / v;   // torch.pow(area,-1): IEEE reciprocal
+  }
+  load_book(sc, thr_d, lvl_f, &sorted, tid, 256);   // ends with __syncthreads
+  const int srt = sorted;
+  const int row = tid;
+  const double d = (double)map[(16 * pi + (row >> 4)) * side + 16 * pj + (row & 15)];
+  const int r0 = min(row >> 5, 5), c0 = min((row & 15) >> 1, 5), span0 = min(((row & 15) >> 2) * 2, 4);
+  const int bf = lloyd_bin<double>(d, thr_d, srt);   // 55 of 64 columns hold d itself
+  const float f = lvl_f[bf];
+  float* compact = sc.ws + unit * als_ws_stride(256, sc.limit) + als_ws_compact(sc.limit);
+  float o[16];
+  o[0] = f;
+  o[13] = o[14] = o[15] = 0.f;
+  int wb[9];   // window bins, row-major over the 3x3 window
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = 0; b < 3; ++b) wb[3 * a + b] = lloyd_bin<double>(__dmul_rn(d, inv_d[8 * (r0 + a) + c0 + b]), thr_d, srt);
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int b = span0 + g - c0;   // window column of span column g
+      float v = 0.f;
+#pragma unroll
+      for (int bb = 0; bb < 3; ++bb)
+        if (b == bb) v = lvl_f[wb[3 * a + bb]] - f;
+      o[1 + 4 * a + g] = v;
+    }
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    *reinterpret_cast<float4*>(compact + row * kCompactRowFloats + 4 * k) = make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+  if (tid < 4) compact[kCompactFloats + tid] = 1.0f;
+  if (sc.bins || sc.values) {
+    const int64_t off = unit * (int64_t)(256 * 64) + row * 64;
+    for (int c4 = 0; c4 < 16; ++c4) {
+      uint32_t pk = 0;
+      float v[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int c = 4 * c4 + e;
+        const int a = (c >> 3) - r0, b = (c & 7) - c0;
+        int bin = bf;
+        if ((unsigned)a < 3u && (unsigned)b < 3u) {
+#pragma unroll
+          for (int w = 0; w < 9; ++w)
+            if (w == 3 * a + b) bin = wb[w];
+        }
+        pk |= (uint32_t)bin << (8 * e);
+        v[e] = lvl_f[bin];
+      }
+      if (sc.bins) *reinterpret_cast<uint32_t*>(sc.bins + off + 4 * c4) = pk;
+      if (sc.values) *reinterpret_cast<float4*>(sc.values + off + 4 * c4) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float rcp_newton(float x) {   // see rdm_als.cu
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return fmaf(fmaf(-x, r, 1.0f), r, r);
+}
+
+__device__ __forceinline__ void load_span(const float* base, float (&v)[12]) {
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const float2 lo = *reinterpret_cast<const float2*>(base + 8 * a);
+    const float2 hi = *reinterpret_cast<const float2*>(base + 8 * a + 2);
+    v[4 * a] = lo.x;
+    v[4 * a + 1] = lo.y;
+    v[4 * a + 2] = hi.x;
+    v[4 * a + 3] = hi.y;
+  }
+}
+
+// sum_span D v as one FMA chain (eight independent rows interleave).  FROM = 1 skips the span's first
+// column: rows of pixel columns 4kq+2, 4kq+3 have their window in span columns 1..3 for every kq.
+template <int FROM>
+__device__ __forceinline__ float span_dot(const float (&D)[12], const float (&v)[12]) {
+  float acc = D[FROM] * v[FROM];
+#pragma unroll
+  for (int e = FROM + 1; e < 12; ++e)
+    if ((e & 3) >= FROM) acc = fmaf(D[e], v[e], acc);
+  return acc;
+}
+template <int T>   // row slot T = 4 dr + cc
+__device__ __forceinline__ float row_dot(const float (&D)[12], const float (&v)[12]) {
+  return span_dot<((T & 3) >= 2) ? 1 : 0>(D, v);
+}
+
+// One warp per unit.  Dynamic shared memory: (limit + 1) x 32 floats (per-lane residuals of every iteration).
+__global__ void __launch_bounds__(32) als_sparse_kernel(const __grid_constant__ SparseParams P) {
+  __shared__ __align__(16) float qs[64];
+  __shared__ __align__(16) float ps[256];
+  extern __shared__ __align__(16) float E[];
+  const int lane = threadIdx.x;
+  const int gunit = blockIdx.x;
+  const SparseScaleDev& sc = find_scale(P, gunit);
+  const int64_t unit = gunit - sc.unit_begin;
+  const int limit = sc.limit;
+  float* wsu = sc.ws + unit * als_ws_stride(256, limit);
+  const float* compact = wsu + als_ws_compact(limit);
+  {
+    const float4 fl = *reinterpret_cast<const float4*>(compact + kCompactFloats);
+    if (!(fl.x == 1.0f && fl.y == 1.0f && fl.z == 1.0f && fl.w == 1.0f)) return;   // dense kernel takes it
+  }
+  float* rec = wsu;
+  float* hist = wsu + als_ws_rec(256, limit);
+  const int rh = lane >> 2, kq = lane & 3;
+  const int r0 = min(rh, 5), span0 = min(2 * kq, 4);
+  const int sp = 8 * r0 + span0;            // first span column
+  const int row_base = 32 * rh + 4 * kq;    // matrix row of (dr, cc): row_base + 16 dr + cc
+
+  float f[8], D[8][12];
+#pragma unroll
+  for (int dr = 0; dr < 2; ++dr)
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+      const int t = 4 * dr + cc;
+      const float4* c4 = reinterpret_cast<const float4*>(compact + (row_base + 16 * dr + cc) * kCompactRowFloats);
+      const float4 a = c4[0], b = c4[1], c = c4[2], d = c4[3];
+      f[t] = a.x;
+      D[t][0] = a.y; D[t][1] = a.z; D[t][2] = a.w;
+      D[t][3] = b.x; D[t][4] = b.y; D[t][5] = b.z; D[t][6] = b.w;
+      D[t][7] = c.x; D[t][8] = c.y; D[t][9] = c.z; D[t][10] = c.w;
+      D[t][11] = d.x;
+    }
+  // A = sum over this lane's rows of A_rho, and the record of iteration 0 (p = q = 1, CP:123):
+  // sum_j fl(1 - R)^2 with 52 columns outside the span
+  double e0 = 0.0, asum = 0.0;
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    const float u = __fsub_rn(1.0f, f[t]);
+    double acc = 52.0 * ((double)u * (double)u);
+#pragma unroll
+    for (int e = 0; e < 12; ++e) {
+      asum = fma((double)D[t][e], 2.0 * (double)f[t] + (double)D[t][e], asum);
+      const float w = __fsub_rn(1.0f, __fadd_rn(f[t], D[t][e]));
+      acc = fma((double)w, (double)w, acc);
+    }
+    e0 += acc;
+  }
+  const float A = (float)asum;
+  E[lane] = (float)e0;
+
+  float qa = 1.0f, qb = 1.0f, m = 1.0f;   // this lane's q[8rh+kq], q[8rh+4+kq]; centre of the q statistics
+  qs[lane] = 1.0f;
+  qs[lane + 32] = 1.0f;
+  __syncwarp();
+  for (int k = 1; k <= limit; ++k) {
+    // ---- statistics of q_{k-1} about m: S1 = sum (q - m), V = sum (q - m)^2
+    const float da = qa - m, db = qb - m;
+    float S1 = da + db, V = fmaf(da, da, db * db);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      S1 += __shfl_xor_sync(kFull, S1, o);
+      V += __shfl_xor_sync(kFull, V, o);
+    }
+    const float Q = fmaf(64.0f, m, S1);                                   // sum q
+    const float QQ = fmaf(64.0f * m, m, fmaf(2.0f * m, S1, V));           // |q|^2
+    const float invA = rcp_newton(QQ + kLambda);                           // torch.inverse of the 1x1 matrix
+    // ---- p-update, and the residual of these rows against q_{k-1} (header comment) summed over the rows:
+    //      64 sum g^2 + V sum p^2 + A - 2 (S1 sum p g + sum p sD)
+    float v[12];
+    load_span(qs + sp, v);
+    float p[8], gg = 0.f, pg = 0.f, psd = 0.f, pp = 0.f, psum = 0.f;
+    auto p_row = [&](auto tc) {
+      constexpr int t = decltype(tc)::value;
+      const float sD = row_dot<t>(D[t], v);
+      p[t] = fmaf(f[t], Q, sD) * invA;
+      const float g = fmaf(-p[t], m, f[t]);
+      gg = fmaf(g, g, gg);
+      pg = fmaf(p[t], g, pg);
+      psd = fmaf(p[t], sD, psd);
+      pp = fmaf(p[t], p[t], pp);
+      psum += p[t];
+    };
+    p_row(std::integral_constant<int, 0>{}); p_row(std::integral_constant<int, 1>{});
+    p_row(std::integral_constant<int, 2>{}); p_row(std::integral_constant<int, 3>{});
+    p_row(std::integral_constant<int, 4>{}); p_row(std::integral_constant<int, 5>{});
+    p_row(std::integral_constant<int, 6>{}); p_row(std::integral_constant<int, 7>{});
+    E[k * 32 + lane] = fmaf(-2.0f, fmaf(S1, pg, psd), fmaf(64.0f, gg, fmaf(V, pp, A)));
+#pragma unroll
+    for (int dr = 0; dr < 2; ++dr) {
+      const float4 pv = make_float4(p[4 * dr], p[4 * dr + 1], p[4 * dr + 2], p[4 * dr + 3]);
+      *reinterpret_cast<float4*>(ps + row_base + 16 * dr) = pv;
+      *reinterpret_cast<float4*>(hist + (int64_t)(k - 1) * 256 + row_base + 16 * dr) = pv;   // phase 1 picks p_k*
+    }
+    __syncwarp();
+    if (k == limit) break;   // the reference's last q-update is never used
+    // ---- q-update: |p|^2, the four segment sums P_r' (segment r' = rows 64r'..64r'+63 = lanes 8r'..8r'+7)
+#pragma unroll
+    for (int o = 1; o <= 4; o <<= 1) {
+      pp += __shfl_xor_sync(kFull, pp, o);
+      psum += __shfl_xor_sync(kFull, psum, o);
+    }
+    pp += __shfl_xor_sync(kFull, pp, 8);
+    pp += __shfl_xor_sync(kFull, pp, 16);
+    const float invB = rcp_newton(pp + kLambda);
+    float ua[4], ub[4];
+    auto q_seg = [&](auto cc_c) {   // row (dr, cc) has rho % 4 = cc: it meets p[64 cc + j]
+      constexpr int cc = decltype(cc_c)::value;
+      const float Pseg = __shfl_sync(kFull, psum, 8 * cc);
+      load_span(ps + 64 * cc + sp, v);
+      ua[cc] = fmaf(f[cc], Pseg, row_dot<cc>(D[cc], v));
+      ub[cc] = fmaf(f[4 + cc], Pseg, row_dot<4 + cc>(D[4 + cc], v));
+    };
+    q_seg(std::integral_constant<int, 0>{}); q_seg(std::integral_constant<int, 1>{});
+    q_seg(std::integral_constant<int, 2>{}); q_seg(std::integral_constant<int, 3>{});
+    m = Q * (1.0f / 64.0f);
+    qa = ((ua[0] + ua[1]) + (ua[2] + ua[3])) * invB;
+    qb = ((ub[0] + ub[1]) + (ub[2] + ub[3])) * invB;
+    qs[8 * rh + kq] = qa;
+    qs[8 * rh + 4 + kq] = qb;
+    __syncwarp();
+  }
+  __syncwarp();
+  for (int k = lane; k <= limit; k += 32) {
+    double t = 0.0;
+#pragma unroll 8
+    for (int l = 0; l < 32; ++l) t += (double)E[k * 32 + ((l + lane) & 31)];
+    rec[k] = (float)t;
+  }
+}
+
+}  // namespace
+
+// Launch the compact path for every eligible scale (256-row units given as f64 matrices or as maps).
+int als_sparse_launch(const rdm_als_scale_t* scales, int32_t n_scales, int64_t n_images, bool sparsify, bool iterate, cudaStream_t stream) {
+  SparseParams raw{}, map{}, all{};
+  raw.n_images = map.n_images = all.n_images = n_images;
+  int64_t n_raw = 0, n_map = 0, n_all = 0;
+  int max_limit = 0;
+  for (int k = 0; k < n_scales; ++k) {
+    const rdm_als_scale_t& h = scales[k];
+    if (h.rows != 256) continue;
+    const bool is_map = h.src_kind == RDM_SRC_MAP_F32;
+    if (!(is_map || h.src_kind == RDM_SRC_RAW_F64 || h.src_kind == RDM_SRC_VAL_F64)) continue;
+    const bool quant = h.src_kind != RDM_SRC_VAL_F64;
+    SparseScaleDev d;
+    d.src = h.src;
+    d.thr = quant ? h.thresholds : nullptr;
+    d.lvl = quant ? h.levels : nullptr;
+    d.bins = h.bins_out;
+    d.values = h.values_out;
+    d.ws = h.ws;
+    d.kind = h.src_kind;
+    d.pages = h.pages;
+    d.side = h.side;
+    d.limit = h.limit;
+    const int64_t units = n_images * h.pages;
+    SparseParams& part = is_map ? map : raw;
+    int64_t& n_part = is_map ? n_map : n_raw;
+    d.unit_begin = (int32_t)n_part;
+    part.s[part.n_scales++] = d;
+    n_part += units;
+    d.unit_begin = (int32_t)n_all;
+    all.s[all.n_scales++] = d;
+    n_all += units;
+    if (h.limit > max_limit) max_limit = h.limit;
+  }
+  if (n_all == 0) return 0;
+  RDM_REQUIRE(n_all < (1ll << 28), "rdm_als_fused: too many work units");
+  if (n_raw && sparsify) {
+    als_sparsify_raw_kernel<<<(unsigned)(4 * n_raw), 256, 0, stream>>>(raw);
+    int rc = launch_status("als_sparsify_raw_kernel");
+    if (rc) return rc;
+  }
+  if (n_map && sparsify) {
+    als_sparsify_map_kernel<<<(unsigned)n_map, 256, 0, stream>>>(map);
+    int rc = launch_status("als_sparsify_map_kernel");
+    if (rc) return rc;
+  }
+  if (!iterate) return 0;
+  als_sparse_kernel<<<(unsigned)n_all, 32, (size_t)(max_limit + 1) * 32 * sizeof(float), stream>>>(all);
+  return launch_status("als_sparse_kernel");
+}
+
+}  // namespace rdm

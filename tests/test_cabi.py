@@ -30,7 +30,8 @@ def test_abi_version_and_sizes(lib):
     assert lib.rdm_pyramid_len(128, 0) == 21845
     assert lib.rdm_pyramid_len(8, 1) == 84
     assert lib.rdm_pyramid_len(12, 0) == -1
-    assert lib.rdm_als_ws_floats(256, 4, 100) == 4 * (101 + 100 * 256)
+    assert lib.rdm_als_ws_floats(256, 4, 100) == 4 * (104 + 100 * 256 + 256 * 16 + 4)   # record (padded), iterates, compact page form, band flags
+    assert lib.rdm_als_ws_floats(64, 1, 30) == 31 + 30 * 64
     sides = (ctypes.c_int32 * 3)(8, 16, 32)
     assert lib.rdm_fuse_tail_weight_count(sides, 3) == 4 + 3 + 4 + 5
     assert ctypes.sizeof(_cabi.AlsScale) == 8 + 6 * 4 + 9 * 8
