@@ -588,9 +588,11 @@ __global__ void __launch_bounds__(256) recombination_bwd_kernel(const double* __
 }
 
 // ---------------------------------------------------------------------------------------------
-// Fused tail.  Grid = n_images * bands; every CTA rebuilds the (tiny) pyramids of its image in
-// shared memory and writes one horizontal band of the 128x128 f64 log-depth map, so the 128 KB
-// per image output - the only significant HBM traffic of stages 4+5 - is spread over the chip.
+// Fused tail.  Grid = n_images * bands, one thread-block CLUSTER of `bands` CTAs per image; every CTA
+// holds the (tiny) pyramids of its image in shared memory and writes one horizontal band of the
+// 128x128 f64 log-depth map, so the 128 KB per image output - the only significant HBM traffic of
+// stages 4+5 - is spread over the chip.  The cheap bicubic levels are redone by every CTA; the f64
+// logs are split over the cluster and exchanged through distributed shared memory.
 // All decoders descend their pyramids TOGETHER, one level per stage (5-6 stages of two barriers
 // instead of one barrier-separated stage per decoder and level), and the expensive f64 log() calls
 // of a level are spread over all threads before the per-slot weighted sum is formed in candidate
@@ -626,7 +628,9 @@ __global__ void __launch_bounds__(RDM_TAIL_THREADS) fuse_tail_kernel(const __gri
   extern __shared__ __align__(16) double D[];                // P.dtotal doubles
   float* yh = reinterpret_cast<float*>(D + P.dtotal);         // slot k at off_level(k)
   const int ylen = off_level(P.kmax + 1);
-  float* L = yh + ylen;                                       // P.lmax floats: f32(log F) of the current level
+  float* L = yh + ylen;                                       // 2 x P.lmax floats: f32(log F) of the current level, double buffered
+  int lbuf = 0;
+  cg::cluster_group cluster = cg::this_cluster();             // the P.bands CTAs of one image
   __shared__ float scratch[32];
   __shared__ float wsm[64];                                   // the (<= 4 + 6*6) weights, read from HBM once
   __shared__ float wl[8][kMaxDec];                            // wl[k][a]: weight of the a-th active decoder of slot k
@@ -661,19 +665,27 @@ __global__ void __launch_bounds__(RDM_TAIL_THREADS) fuse_tail_kernel(const __gri
       for (int idx = tid; idx < side * side; idx += blockDim.x) dn[idx] = (double)src[idx];
     }
   }
-  __syncthreads();
+  cluster.sync();   // every CTA of the cluster is running: its shared memory may be written from here on
 #ifdef RDM_TIMING
   tt[ti++] = clock64();
 #endif
-  // F_k = D_k / up2(D_{k-1}) (CP:389) and its log (CP:478-480) for `n` items of level k starting at L[lofs];
-  // four independent log() chains per thread (a f64 log is ~1000 cycles of dependent latency).
+  // The f64 div + log of the fine-detail values is the expensive part of the pyramids (~110 instructions per
+  // value): it is SPLIT over the CTAs of the cluster and every result is stored into the log buffer of all of
+  // them through distributed shared memory, instead of every band redoing all of it.  The buffer is double
+  // buffered, so one cluster barrier per stage orders both the remote writes and the local reads.
+  const int nb = P.bands, gthreads = blockDim.x * nb, gtid = band * blockDim.x + tid;
+  auto put_log = [&](float* dst, float v) {
+    for (int b = 0; b < nb; ++b) *cluster.map_shared_rank(dst, b) = v;
+  };
+  // F_k = D_k / up2(D_{k-1}) (CP:389) and its log (CP:478-480) for the items of level k, into L[lofs...];
+  // up to four independent log() chains per thread (a f64 log is ~1000 cycles of dependent latency).
   auto log_level = [&](int k, int lofs) {
     const int side = 1 << k, half = side >> 1, n = P.nact[k] * side * side;
-    for (int base = tid; base < n; base += 4 * blockDim.x) {
+    for (int base = gtid; base < n; base += 4 * gthreads) {
       double lg[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int item = base + j * blockDim.x;
+        const int item = base + j * gthreads;
         if (item < n) {
           const int a = item >> (2 * k), idx = item & (side * side - 1);
           const double* bp = D + P.doff[P.act[k][a]];
@@ -683,12 +695,12 @@ __global__ void __launch_bounds__(RDM_TAIL_THREADS) fuse_tail_kernel(const __gri
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int item = base + j * blockDim.x;
+        const int item = base + j * gthreads;
         if (item < n) {
           const int a = item >> (2 * k), idx = item & (side * side - 1);
           const int d = P.act[k][a];
-          if (lead && P.A_out[k]) P.A_out[k][(img * P.K[k] + P.cand[d][k]) * (int64_t)(side * side) + idx] = lg[j];
-          L[lofs + item] = (float)lg[j];
+          if (P.A_out[k]) P.A_out[k][(img * P.K[k] + P.cand[d][k]) * (int64_t)(side * side) + idx] = lg[j];
+          put_log(L + lofs + item, (float)lg[j]);
         }
       }
     }
@@ -717,12 +729,13 @@ __global__ void __launch_bounds__(RDM_TAIL_THREADS) fuse_tail_kernel(const __gri
 #ifdef RDM_TIMING
     if (ti < 11) tt[ti++] = clock64();
 #endif
-    log_level(k, 0);
-    __syncthreads();
+    log_level(k, lbuf * P.lmax);
+    cluster.sync();
 #ifdef RDM_TIMING
     if (ti < 11) tt[ti++] = clock64();
 #endif
-    sum_level(k, 0);
+    sum_level(k, lbuf * P.lmax);
+    lbuf ^= 1;
 #ifdef RDM_TIMING
     if (ti < 11) tt[ti++] = clock64();
 #endif
@@ -735,7 +748,7 @@ __global__ void __launch_bounds__(RDM_TAIL_THREADS) fuse_tail_kernel(const __gri
       bicubic_level(k, tid, 32);
       __syncwarp();
     }
-  __syncthreads();   // also orders the last large-level sum_level before L is rewritten
+  __syncthreads();
 #ifdef RDM_TIMING
   if (ti < 11) tt[ti++] = clock64();
 #endif
@@ -744,7 +757,7 @@ __global__ void __launch_bounds__(RDM_TAIL_THREADS) fuse_tail_kernel(const __gri
     if (ksmall >= 3) n3 = P.nact[3] << 6;
     if (ksmall >= 2) n2 = P.nact[2] << 4;
     n1 = P.nact[1] << 2;
-    for (int t = tid; t < n3 + n2 + n1; t += blockDim.x) {
+    for (int t = gtid; t < n3 + n2 + n1; t += gthreads) {
       const int k = (t < n3) ? 3 : (t < n3 + n2 ? 2 : 1);
       const int item = t - (k == 3 ? 0 : (k == 2 ? n3 : n3 + n2));
       const int side = 1 << k, half = side >> 1;
@@ -753,13 +766,13 @@ __global__ void __launch_bounds__(RDM_TAIL_THREADS) fuse_tail_kernel(const __gri
       const double* bp = D + P.doff[d];
       const int y = idx >> k, x = idx & (side - 1);
       const double lg = log(bp[off_level(k) + idx] / bp[off_level(k - 1) + (y >> 1) * half + (x >> 1)]);
-      if (lead && P.A_out[k]) P.A_out[k][(img * P.K[k] + P.cand[d][k]) * (int64_t)(side * side) + idx] = lg;
-      L[t] = (float)lg;   // level 3 first, then 2, then 1: the offsets sum_level() is given below
+      if (P.A_out[k]) P.A_out[k][(img * P.K[k] + P.cand[d][k]) * (int64_t)(side * side) + idx] = lg;
+      put_log(L + lbuf * P.lmax + t, (float)lg);   // level 3 first, then 2, then 1: the offsets sum_level() is given below
     }
   }
-  __syncthreads();
+  cluster.sync();   // last remote access: a CTA may leave the cluster afterwards
   {
-    int lofs = 0;
+    int lofs = lbuf * P.lmax;
     for (int k = ksmall; k >= 1; --k) {
       sum_level(k, lofs);
       lofs += P.nact[k] << (2 * k);
@@ -1182,16 +1195,32 @@ extern "C" int rdm_fuse_tail(const int64_t* x_d1, const float* const* rel, const
   // bands: enough CTAs to spread the 128 KB/image output, few enough that the pyramid work (redone
   // by every band) stays small: >= 64 CTAs in total
   int bands = 1;   // a band must hold whole constant blocks: rows per band >= 2^(7-kmax)
-  while (bands < 16 && bands < (1 << P.kmax) && n_images * bands < 64) bands <<= 1;
+  while (bands < 8 && bands < (1 << P.kmax) && n_images * bands < 64) bands <<= 1;   // one thread-block cluster per image
   P.bands = bands;
   RDM_REQUIRE(n_images * bands < (1ll << 31), "rdm_fuse_tail: too many images");
-  const size_t smem = (size_t)P.dtotal * sizeof(double) + ((size_t)off_level(P.kmax + 1) + lmax) * sizeof(float);
+  const size_t smem = (size_t)P.dtotal * sizeof(double) + ((size_t)off_level(P.kmax + 1) + 2 * (size_t)lmax) * sizeof(float);
   RDM_REQUIRE(smem <= 220 * 1024, "rdm_fuse_tail: decoder pyramids need %zu bytes of shared memory (max 220 KB)", smem);
   cudaError_t e = ensure_dyn_smem(fuse_tail_kernel, smem, smem_set_fuse_tail_kernel);
   if (e != cudaSuccess) {
     set_error("rdm_fuse_tail: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     return (int)e;
   }
-  fuse_tail_kernel<<<(unsigned)(n_images * bands), RDM_TAIL_THREADS, smem, (cudaStream_t)stream>>>(P);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(n_images * bands));
+  cfg.blockDim = dim3(RDM_TAIL_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)bands;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, fuse_tail_kernel, P);
+  if (e != cudaSuccess) {
+    set_error("fuse_tail_kernel: %s", cudaGetErrorString(e));
+    return (int)e;
+  }
   return launch_status("fuse_tail_kernel");
 }

@@ -184,6 +184,57 @@ def test_als_f64_input_and_step(dev):
     assert _rel_err(step, fr._ridge_step(Rq.float(), q)) < 1e-5
 
 
+def test_als_compact_pages_vs_dense_and_oracle(dev, books):
+    """Page pair matrices take the compact-form kernels (rdm_als_sparse.cu); anything else takes the dense
+    kernel.  Same matrices through every entry: raw f64 (quantised on the fly, bins + values emitted),
+    quantised f64 (structure found by the bit-wise check), quantised f32 (always dense), a group in which
+    ONE matrix has one entry outside its window changed (that unit alone goes dense), all against the
+    oracle."""
+    from md_rdm_b200 import _cabi
+    g = torch.Generator().manual_seed(77)
+    x = torch.exp(0.3 * torch.randn(3, 1, 32, 32, generator=g))
+    q, lv = books[32]
+    thr, lvl = _dev_books(books, dev)[32]
+    dn1 = fr.resize_half(x)
+    raw = torch.stack([fr.pair_id(pg, par) for pg, par in fr.split_pages(x, dn1)], 1)          # (3,4,256,64) f64
+    vals, bins = fr.lloyd(raw, q, lv)
+    ref = [fr.als_rank1(vals[:, pi], 100) for pi in range(4)]
+
+    def check(out, tag):
+        m, pages, rec, k, b, v = out
+        for pi in range(4):
+            assert int(k.reshape(-1)[pi]) == ref[pi][2], (tag, pi)
+            assert np.allclose(rec[0, pi].cpu().numpy(), np.array(ref[pi][1], dtype=np.float32), rtol=1e-5, atol=1e-7), (tag, pi)
+            assert _rel_err(pages[:, pi].cpu().view(-1), ref[pi][0].reshape(-1)) < REL_MAP, (tag, pi)
+        return b, v
+
+    b, v = check(R.als_rank1(raw.to(dev), _cabi.SRC_RAW_F64, 256, 32, 100, 3, thr, lvl, True, True), "raw_f64")
+    assert torch.equal(b.cpu(), bins)
+    assert torch.equal(v.cpu(), vals.float())
+    check(R.als_rank1(vals.to(dev), _cabi.SRC_VAL_F64, 256, 32, 100, 3, None, None, False, False), "val_f64")
+    check(R.als_rank1(vals.float().to(dev), _cabi.SRC_VAL_F32, 256, 32, 100, 3, None, None, False, False), "val_f32 (dense)")
+    b, _ = check(R.als_rank1(x.to(dev), _cabi.SRC_MAP_F32, 256, 32, 100, 3, thr, lvl, True, False), "map")
+    assert torch.equal(b.cpu(), bins)
+
+    # one unit of the group loses the structure: column 0 of row 200 is outside that row's window
+    mixed = vals.clone()
+    assert not fr.window_mask(8, 16)[200, 0]
+    mixed[1, 2, 200, 0] = float(lv[3])
+    ref_mixed = fr.als_rank1(mixed[:, 2], 100)
+    m, pages, rec, k, _, _ = R.als_rank1(mixed.to(dev), _cabi.SRC_VAL_F64, 256, 32, 100, 3, None, None, False, False)
+    assert int(k.reshape(-1)[2]) == ref_mixed[2]
+    assert np.allclose(rec[0, 2].cpu().numpy(), np.array(ref_mixed[1], dtype=np.float32), rtol=1e-5, atol=1e-7)
+    assert _rel_err(pages[:, 2].cpu().view(-1), ref_mixed[0].reshape(-1)) < REL_MAP
+    # ... and a window entry may hold anything (here: another level) without leaving the compact path
+    assert fr.window_mask(8, 16)[0, 0]
+    wdw = vals.clone()
+    wdw[0, 0, 0, 0] = float(lv[30])
+    ref_w = fr.als_rank1(wdw[:, 0], 100)
+    _, pages, rec, k, _, _ = R.als_rank1(wdw.to(dev), _cabi.SRC_VAL_F64, 256, 32, 100, 3, None, None, False, False)
+    assert int(k.reshape(-1)[0]) == ref_w[2]
+    assert _rel_err(pages[:, 0].cpu().view(-1), ref_w[0].reshape(-1)) < REL_MAP
+
+
 @pytest.mark.parametrize("s", [8, 16, 32])
 def test_relative_tail_golden(dev, books, s):
     """Fused pair build + Lloyd + ALS (MAP source) against the reference's Ordinal_Layer.forward."""
