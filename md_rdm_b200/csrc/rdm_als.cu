@@ -657,16 +657,28 @@ __device__ __forceinline__ void als_unit(const AlsParams& P, const AlsScaleDev& 
       for (; b < P.group; ++b) t += (double)col[b * gstride];
       rm[k] = (float)sqrt(t * inv_cnt);
     }
-    unit_barrier(bar_id, NT);
-    int kstar = 0;
-    float best = rm[0];
-    for (int k = 1; k <= sc.limit; ++k) {
-      float v = rm[k];
-      if (v < best) {
-        best = v;
-        kstar = k;
-      }
+    // first arg-min (CP:74, CP:143) as a parallel min over (value bits, index) keys: rmse values are
+    // >= 0, so their bit patterns order like the values and ties resolve to the smaller index
+    // (limit <= 127: threads 0..127 hold one key each, NT >= 64 threads take two)
+    unsigned long long key = ~0ull;
+    for (int k = lt; k <= sc.limit; k += NT) {
+      const unsigned long long kk = ((unsigned long long)__float_as_uint(rm[k]) << 32) | (unsigned)k;
+      key = kk < key ? kk : key;
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+      key = other < key ? other : key;
+    }
+    unsigned long long* kscr = reinterpret_cast<unsigned long long*>(sm.qpart) + unit * 8;   // 8 keys per unit
+    if (m.lane == 0) kscr[m.lw] = key;
+    unit_barrier(bar_id, NT);
+#pragma unroll
+    for (int w = 0; w < 2 * G; ++w) {
+      const unsigned long long other = kscr[w];
+      key = other < key ? other : key;
+    }
+    const int kstar = (int)(key & 0xffffffffu);
     if (img == g0) {
       const int64_t gp = (img / P.group) * sc.pages + pg;
       if (sc.record_out)
@@ -674,8 +686,15 @@ __device__ __forceinline__ void als_unit(const AlsParams& P, const AlsScaleDev& 
       if (sc.kstar_out && lt == 0) sc.kstar_out[gp] = kstar;
     }
     const float p = (kstar == 0) ? 1.0f : ws[ws_rec + (int64_t)(kstar - 1) * ROWS + row];
-    // ---- quick_gm(p, H) with H = rows: prod_i p_i^(1/H^2)  (CP:76, CP:146, CP:244-255)
-    const float pw = (float)pow((double)p, 1.0 / ((double)ROWS * (double)ROWS));
+    // ---- quick_gm(p, H) with H = rows: prod_i p_i^(1/H^2)  (CP:76, CP:146, CP:244-255).  The exponent is
+    // 2^-12 or 2^-16, so p^(1/H^2) = exp(x) with |x| = |ln p| / H^2 < 3e-3: 1 + x + x^2/2 + x^3/6 is exact to
+    // f32 rounding (x^4/24 < 4e-12), and p = 1 gives exactly 1.
+    float pw;
+    {
+      const float x = logf(p) * (1.0f / ((float)ROWS * (float)ROWS));
+      pw = 1.0f + fmaf(fmaf(x, 1.0f / 6.0f, 0.5f) * x, x, x);
+      if (!(p > 0.0f) || !(fabsf(x) < 3e-3f)) pw = (float)pow((double)p, 1.0 / ((double)ROWS * (double)ROWS));   // zeros, negatives, NaN, huge ratios
+    }
     float prod = warp_prod(pw);
     unit_barrier(bar_id, NT);   // rm[] no longer needed; reuse p_s as scratch
     float* scratch = sm.p_s + unit * 64;

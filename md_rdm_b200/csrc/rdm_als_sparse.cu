@@ -304,7 +304,11 @@ __global__ void __launch_bounds__(32) als_sparse_kernel(const __grid_constant__ 
   const int rh = lane >> 2, kq = lane & 3;
   const int r0 = min(rh, 5), span0 = min(2 * kq, 4);
   const int sp = 8 * r0 + span0;            // first span column
-  const int row_base = 32 * rh + 4 * kq;    // matrix row of (dr, cc): row_base + 16 dr + cc
+  const int row_base = 32 * rh + 4 * kq;    // matrix row of pixel (2rh + dr, 4kq + cc): row_base + 16 dr + cc
+  // Register slot t = 4 ds + cc holds pixel row dr = ds ^ (rh & 1): lanes of odd rh keep their two pixel rows
+  // in the opposite order, so that the 128-bit stores of p (8 lanes = rh, rh+1 per wavefront) hit 32 distinct
+  // banks.  Nothing else depends on the order: both pixel rows share the window.
+  const int off_s[2] = {row_base + 16 * (rh & 1), row_base + 16 * ((rh & 1) ^ 1)};
 
   float f[8], D[8][12];
 #pragma unroll
@@ -312,7 +316,7 @@ __global__ void __launch_bounds__(32) als_sparse_kernel(const __grid_constant__ 
 #pragma unroll
     for (int cc = 0; cc < 4; ++cc) {
       const int t = 4 * dr + cc;
-      const float4* c4 = reinterpret_cast<const float4*>(compact + (row_base + 16 * dr + cc) * kCompactRowFloats);
+      const float4* c4 = reinterpret_cast<const float4*>(compact + (off_s[dr] + cc) * kCompactRowFloats);
       const float4 a = c4[0], b = c4[1], c = c4[2], d = c4[3];
       f[t] = a.x;
       D[t][0] = a.y; D[t][1] = a.z; D[t][2] = a.w;
@@ -338,7 +342,7 @@ __global__ void __launch_bounds__(32) als_sparse_kernel(const __grid_constant__ 
   const float A = (float)asum;
   E[lane] = (float)e0;
 
-  float qa = 1.0f, qb = 1.0f, m = 1.0f;   // this lane's q[8rh+kq], q[8rh+4+kq]; centre of the q statistics
+  float qa = 1.0f, qb = 1.0f, m = 1.0f;   // this lane's two entries of q (slot rows >> 2); centre of the q statistics
   qs[lane] = 1.0f;
   qs[lane + 32] = 1.0f;
   __syncwarp();
@@ -378,8 +382,8 @@ __global__ void __launch_bounds__(32) als_sparse_kernel(const __grid_constant__ 
 #pragma unroll
     for (int dr = 0; dr < 2; ++dr) {
       const float4 pv = make_float4(p[4 * dr], p[4 * dr + 1], p[4 * dr + 2], p[4 * dr + 3]);
-      *reinterpret_cast<float4*>(ps + row_base + 16 * dr) = pv;
-      *reinterpret_cast<float4*>(hist + (int64_t)(k - 1) * 256 + row_base + 16 * dr) = pv;   // phase 1 picks p_k*
+      *reinterpret_cast<float4*>(ps + off_s[dr]) = pv;
+      *reinterpret_cast<float4*>(hist + (int64_t)(k - 1) * 256 + off_s[dr]) = pv;   // phase 1 picks p_k*
     }
     __syncwarp();
     if (k == limit) break;   // the reference's last q-update is never used
@@ -405,8 +409,8 @@ __global__ void __launch_bounds__(32) als_sparse_kernel(const __grid_constant__ 
     m = Q * (1.0f / 64.0f);
     qa = ((ua[0] + ua[1]) + (ua[2] + ua[3])) * invB;
     qb = ((ub[0] + ub[1]) + (ub[2] + ub[3])) * invB;
-    qs[8 * rh + kq] = qa;
-    qs[8 * rh + 4 + kq] = qb;
+    qs[off_s[0] >> 2] = qa;   // q index of row rho is rho >> 2
+    qs[off_s[1] >> 2] = qb;
     __syncwarp();
   }
   __syncwarp();
