@@ -33,6 +33,7 @@
 // Bound: per unit 2*limit*rows*64 FMA against rows*64*(4..8) input bytes = 25..100 FMA/byte:
 // FP32-issue / dependency-latency bound, not HBM bound (DESIGN.md "K3").
 #include "rdm_common.cuh"
+#include <algorithm>
 #include <cstdlib>
 
 namespace rdm {
@@ -55,7 +56,9 @@ struct AlsScaleDev {
   float* record_out;
   int32_t* kstar_out;
   int32_t kind, rows, pages, side, limit;
-  int32_t cta_begin;   // first blockIdx.x of this scale
+  int32_t cta_begin;   // first blockIdx.x of this scale in the select launch (one CTA per 256-row unit / four 64-row units)
+  int32_t cta_begin0;  // ... and in the dense iterate launch, where a compact-eligible page scale gets only
+  int32_t cta_count0;  //     cta_count0 CTAs that walk its units with that stride (most units need nothing: rdm_als_sparse.cu)
 };
 
 struct AlsParams {
@@ -726,19 +729,24 @@ __global__ void __launch_bounds__(kAlsThreads, 2) als_kernel(const __grid_consta
   int si = 0;
 #pragma unroll 1
   for (int k = 1; k < P.n_scales; ++k)
-    if ((int)blockIdx.x >= P.s[k].cta_begin) si = k;
+    if ((int)blockIdx.x >= (PHASE == 0 ? P.s[k].cta_begin0 : P.s[k].cta_begin)) si = k;
   const AlsScaleDev& sc = P.s[si];
   const int tid = threadIdx.x;
-  if (PHASE == 0 && P.sparse && sc.rows == 256 &&
-      (sc.kind == RDM_SRC_RAW_F64 || sc.kind == RDM_SRC_VAL_F64 || sc.kind == RDM_SRC_MAP_F32)) {
-    // Page units whose matrix has the pair-build structure were iterated by als_sparse_kernel
-    // (rdm_als_sparse.cu); the sparsify kernels leave four band flags per unit for these kinds.
-    const int64_t unit_idx = (int)blockIdx.x - sc.cta_begin;
-    if (unit_idx < P.n_images * sc.pages) {
-      const float4 fl = *reinterpret_cast<const float4*>(sc.ws + unit_idx * als_ws_stride(256, sc.limit) +
-                                                           als_ws_compact(sc.limit) + kCompactFloats);
-      if (fl.x == 1.0f && fl.y == 1.0f && fl.z == 1.0f && fl.w == 1.0f) return;   // CTA-uniform
-    }
+  const int64_t n_units = P.n_images * sc.pages;
+  const int local_cta = (int)blockIdx.x - (PHASE == 0 ? sc.cta_begin0 : sc.cta_begin);
+  const int unit_stride = PHASE == 0 ? sc.cta_count0 : 1 << 30;   // phase 1: one unit per CTA
+  // Page units whose matrix has the pair-build structure were iterated by als_sparse_kernel
+  // (rdm_als_sparse.cu); the sparsify kernels leave four band flags per unit for these kinds.
+  const bool flagged = PHASE == 0 && P.sparse && sc.rows == 256 &&
+                       (sc.kind == RDM_SRC_RAW_F64 || sc.kind == RDM_SRC_VAL_F64 || sc.kind == RDM_SRC_MAP_F32);
+  auto is_compact = [&](int64_t unit_idx) {
+    const float4 fl = *reinterpret_cast<const float4*>(sc.ws + unit_idx * als_ws_stride(256, sc.limit) + als_ws_compact(sc.limit) + kCompactFloats);
+    return fl.x == 1.0f && fl.y == 1.0f && fl.z == 1.0f && fl.w == 1.0f;
+  };
+  if (flagged) {   // nothing to do for this CTA?  leave before the codebook prologue (CTA-uniform)
+    bool any = false;
+    for (int64_t u = local_cta; u < n_units; u += unit_stride) any |= !is_compact(u);
+    if (!any) return;
   }
   if (PHASE == 0 && sc.thr) {   // phase 1 never quantises
     if (tid == 0) sm.sorted = 1;
@@ -763,12 +771,13 @@ __global__ void __launch_bounds__(kAlsThreads, 2) als_kernel(const __grid_consta
     sm.lut.ncell = 0;
   }
   __syncthreads();
-  const int64_t n_units = P.n_images * sc.pages;
-  const int local_cta = (int)blockIdx.x - sc.cta_begin;
   if (sc.rows == 256) {
-    const int64_t unit_idx = local_cta;
     // 256-row unit: the record scratch E aliases the staging tile (dead once the rows are in registers)
-    if (unit_idx < n_units) als_unit<4, PHASE>(P, sc, sm, tile, tile, unit_idx, 0, tid);
+    for (int64_t unit_idx = local_cta; unit_idx < n_units; unit_idx += unit_stride) {
+      if (flagged && is_compact(unit_idx)) continue;
+      als_unit<4, PHASE>(P, sc, sm, tile, tile, unit_idx, 0, tid);
+      __syncthreads();   // E (= tile) is read until the end of a unit
+    }
   } else {
     const int unit = tid >> 6;
     const int64_t unit_idx = (int64_t)local_cta * 4 + unit;
@@ -834,7 +843,7 @@ extern "C" int rdm_als_fused_phases(const rdm_als_scale_t* scales, int32_t n_sca
   // RDM_ALS_DENSE=1 (A/B measurements, tests of the dense kernel): every unit takes the dense kernel
   static const bool dense_only = [] { const char* v = getenv("RDM_ALS_DENSE"); return v && v[0] == '1'; }();
   P.sparse = dense_only ? 0 : 1;
-  int64_t ctas = 0;
+  int64_t ctas = 0, ctas0 = 0;
   for (int k = 0; k < n_scales; ++k) {
     const rdm_als_scale_t& h = scales[k];
     RDM_REQUIRE(h.src && h.ws, "rdm_als_fused: scale %d: src and ws are required", k);
@@ -873,8 +882,18 @@ extern "C" int rdm_als_fused_phases(const rdm_als_scale_t* scales, int32_t n_sca
     d.side = h.side;
     d.limit = h.limit;
     d.cta_begin = (int32_t)ctas;
+    d.cta_begin0 = (int32_t)ctas0;
     const int64_t units = n_images * h.pages;
-    ctas += (h.rows == 256) ? units : (units + 3) / 4;
+    const int64_t n1 = (h.rows == 256) ? units : (units + 3) / 4;
+    ctas += n1;
+    // dense iterate launch: a compact-eligible page scale keeps few CTAs (each walks up to 8 units and
+    // normally finds nothing to do); every such CTA reserves 100 KB of shared memory and 32 K registers
+    const bool eligible = P.sparse && h.rows == 256 &&
+                          (h.src_kind == RDM_SRC_RAW_F64 || h.src_kind == RDM_SRC_VAL_F64 || h.src_kind == RDM_SRC_MAP_F32);
+    int64_t n0 = n1;
+    if (eligible) n0 = std::min<int64_t>(units, std::max<int64_t>(8, (units + 7) / 8));
+    d.cta_count0 = (h.rows == 256) ? (int32_t)n0 : 1;
+    ctas0 += n0;
     RDM_REQUIRE(ctas < (1ll << 30), "rdm_als_fused: too many work units");
   }
   // dynamic shared memory: staging tile, plus the record scratch E of phase 0
@@ -895,7 +914,7 @@ extern "C" int rdm_als_fused_phases(const rdm_als_scale_t* scales, int32_t n_sca
     if (rc) return rc;
   }
   if (phase_mask & 16) {
-    als_kernel<0><<<(unsigned)ctas, kAlsThreads, dyn, (cudaStream_t)stream>>>(P);
+    als_kernel<0><<<(unsigned)ctas0, kAlsThreads, dyn, (cudaStream_t)stream>>>(P);
     int rc = launch_status("als_kernel<iterate>");
     if (rc) return rc;
   }
