@@ -31,7 +31,7 @@ LIMIT_PAGE = 100
 class FusionPlan:
     def __init__(self, n_images: int, scales: Sequence[int] = (8, 16, 32), source: str = "map", group: Optional[int] = None,
                  device="cuda", quant: Optional[Quantization] = None, want_bins: bool = True, want_values: bool = False,
-                 want_A: bool = False, limit_8: int = LIMIT_8, limit_page: int = LIMIT_PAGE):
+                 want_A: bool = False, limit_8: int = LIMIT_8, limit_page: int = LIMIT_PAGE, overlap: bool = False):
         if source not in ("map", "raw"):
             raise ValueError("source must be 'map' or 'raw'")
         self.lib = load()                      # raises if librdm_b200.so is missing: no fallback
@@ -82,6 +82,8 @@ class FusionPlan:
         self.record: Dict[int, torch.Tensor] = {}
         self.kstar: Dict[int, torch.Tensor] = {}
         self._ws: Dict[int, torch.Tensor] = {}
+        self._side: Optional[torch.cuda.Stream] = None   # fork/join branch of run()
+        self.overlap = bool(overlap)
         self._tables = {}
         G = N // self.group
         descs = (AlsScale * len(self.scales))()
@@ -130,12 +132,35 @@ class FusionPlan:
         return {key: buf[off:off + nbytes].view(dt).view(shape) for key, shape, dt, off, nbytes in self._layout}
 
     # ------------------------------------------------------------------ device path
-    def run(self) -> torch.Tensor:
-        """Enqueue the whole path on the current stream; returns the (N,1,128,128) f64 log-depth buffer."""
-        st = c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+    def run(self, overlap: Optional[bool] = None) -> torch.Tensor:
+        """Enqueue the whole path on the current stream; returns the (N,1,128,128) f64 log-depth buffer.
+
+        After the compact page form is built (phase bit 4) the iterate phase is two independent launches -
+        the ALS on the compact pages (bit 8) and the dense ALS of the 8x8 maps plus the fallback for pages
+        without pair structure (bit 16, reads the flags bit 4 wrote) - so with `overlap` the dense launch goes
+        to a side stream that forks from and joins the current one (plain events: capturable into a CUDA
+        graph, where it becomes two parallel branches).  The select launch needs both.  Measured on B200
+        (batch 16, scales 8/16/32): one step alone 103 -> 77 us, but with 16 batches in flight 7 % FEWER maps/s
+        (the join costs more than the idle SMs it fills), so it is off unless the plan was built with
+        `overlap=True` (latency-bound callers)."""
+        overlap = self.overlap if overlap is None else overlap
+        cur = torch.cuda.current_stream(self.device)
+        st = c_void_p(cur.cuda_stream)
         lib = self.lib
         if self.scales:
-            check(lib.rdm_als_fused(self._descs, len(self.scales), self.N, self.group, st), "rdm_als_fused")
+            n, descs = len(self.scales), self._descs
+            if overlap and any(s > 8 for s in self.scales) and 8 in self.scales:
+                if self._side is None:
+                    self._side = torch.cuda.Stream(self.device)
+                side = self._side
+                check(lib.rdm_als_fused_phases(descs, n, self.N, self.group, 4, st), "rdm_als_fused_phases")
+                side.wait_stream(cur)
+                check(lib.rdm_als_fused_phases(descs, n, self.N, self.group, 16, c_void_p(side.cuda_stream)), "rdm_als_fused_phases")
+                check(lib.rdm_als_fused_phases(descs, n, self.N, self.group, 8, st), "rdm_als_fused_phases")
+                cur.wait_stream(side)
+                check(lib.rdm_als_fused_phases(descs, n, self.N, self.group, 2, st), "rdm_als_fused_phases")
+            else:
+                check(lib.rdm_als_fused(descs, n, self.N, self.group, st), "rdm_als_fused")
         check(lib.rdm_fuse_tail(c_void_p(self.x_d1.data_ptr()), self._rel_ptrs, self._sides, len(self.scales),
                                 c_void_p(self.weights.data_ptr()), self.N, c_void_p(self.yhat.data_ptr()),
                                 c_void_p(self.depth.data_ptr()), self._a_ptrs, st), "rdm_fuse_tail")
