@@ -284,6 +284,25 @@ def stage_kernel_table(dev, batch):
     return out
 
 
+def pcie_d2h_peak(dev):
+    """Measured device->host copy rate of this box (pinned memory): large copies, and copies of the e2e result
+    size (2 MB) issued back to back - the ceiling of any path that returns 128 KB of f64 log-depth per image."""
+    out = {}
+    for name, nbytes, reps in (("d2h_64MB_gbs", 64 << 20, 10), ("d2h_2MB_gbs", 2 << 20, 200)):
+        src = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        dst = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(reps):
+            dst.copy_(src, non_blocking=True)
+        s1.record()
+        torch.cuda.synchronize()
+        out[name] = round(nbytes * reps / (s0.elapsed_time(s1) * 1e-3) / 1e9, 2)
+    return out
+
+
 def cpu_baseline_port(images: int):
     """The reference's CPU algorithm (literal port) on a bounded sample of the same workload."""
     from oracle import fusion_ref as fr
@@ -410,6 +429,7 @@ def run_ours(args):
         reps = max(K // nb, 1)
         eb_dev_ms, eb_wall_ms = timed(K, lambda k: [e2e_graph.replay() for _ in range(reps)])
         eb_ms = dist_max(max(eb_dev_ms, eb_wall_ms), dev) / (reps * nb) * K
+        pcie = pcie_d2h_peak(dev) if rank == 0 else {}
         stage = {}
         if rank == 0 and not args.no_stage_table:
             stage = {"batch_16": stage_kernel_table(dev, 16), "batch_256": stage_kernel_table(dev, 256)}
@@ -461,6 +481,8 @@ def run_ours(args):
                 "d2h_bytes_per_step": e2e_ring[0].d2h_bytes(),
                 "api": "FusionPlan.submit_pinned (source='map'): one CUDA-graph launch per call = H2D copy of the pinned decoder maps, "
                        "pair build + Lloyd + ALS + decompose + reconstruction, D2H copy of the log-depth maps",
+                "d2h_gbs_at_value": world * K * e2e_ring[0].d2h_bytes() / (e_ms * 1e-3) / 1e9 / world,
+                "pcie_measured": pcie,
                 "batched_value": world * K * BATCH / (eb_ms * 1e-3),
                 "batched_note": "same calls with one graph launch per pass over the ring (host launch rate removed)"},
         "gpu_launches": K * LAUNCHES_PER_STEP,

@@ -283,7 +283,8 @@ __device__ __forceinline__ float row_dot(const float (&D)[12], const float (&v)[
   return span_dot<((T & 3) >= 2) ? 1 : 0>(D, v);
 }
 
-// One warp per unit.  Dynamic shared memory: (limit + 1) x 32 floats (per-lane residuals of every iteration).
+// One warp per unit (capping it at 128 registers for 16 warps per SM was measured 7 % slower).  Dynamic shared memory: (limit + 1) x 16 floats
+// (residuals of every iteration, summed over lane pairs).
 __global__ void __launch_bounds__(32) als_sparse_kernel(const __grid_constant__ SparseParams P) {
   __shared__ __align__(16) float qs[64];
   __shared__ __align__(16) float ps[256];
@@ -340,7 +341,11 @@ __global__ void __launch_bounds__(32) als_sparse_kernel(const __grid_constant__ 
     e0 += acc;
   }
   const float A = (float)asum;
-  E[lane] = (float)e0;
+  {
+    float e = (float)e0;
+    e += __shfl_xor_sync(kFull, e, 1);
+    if (!(lane & 1)) E[lane >> 1] = e;
+  }
 
   float qa = 1.0f, qb = 1.0f, m = 1.0f;   // this lane's two entries of q (slot rows >> 2); centre of the q statistics
   qs[lane] = 1.0f;
@@ -378,7 +383,11 @@ __global__ void __launch_bounds__(32) als_sparse_kernel(const __grid_constant__ 
     p_row(std::integral_constant<int, 2>{}); p_row(std::integral_constant<int, 3>{});
     p_row(std::integral_constant<int, 4>{}); p_row(std::integral_constant<int, 5>{});
     p_row(std::integral_constant<int, 6>{}); p_row(std::integral_constant<int, 7>{});
-    E[k * 32 + lane] = fmaf(-2.0f, fmaf(S1, pg, psd), fmaf(64.0f, gg, fmaf(V, pp, A)));
+    {
+      float e = fmaf(-2.0f, fmaf(S1, pg, psd), fmaf(64.0f, gg, fmaf(V, pp, A)));
+      e += __shfl_xor_sync(kFull, e, 1);
+      if (!(lane & 1)) E[k * 16 + (lane >> 1)] = e;
+    }
 #pragma unroll
     for (int dr = 0; dr < 2; ++dr) {
       const float4 pv = make_float4(p[4 * dr], p[4 * dr + 1], p[4 * dr + 2], p[4 * dr + 3]);
@@ -417,7 +426,7 @@ __global__ void __launch_bounds__(32) als_sparse_kernel(const __grid_constant__ 
   for (int k = lane; k <= limit; k += 32) {
     double t = 0.0;
 #pragma unroll 8
-    for (int l = 0; l < 32; ++l) t += (double)E[k * 32 + ((l + lane) & 31)];
+    for (int l = 0; l < 16; ++l) t += (double)E[k * 16 + ((l + lane) & 15)];
     rec[k] = (float)t;
   }
 }
@@ -471,7 +480,7 @@ int als_sparse_launch(const rdm_als_scale_t* scales, int32_t n_scales, int64_t n
     if (rc) return rc;
   }
   if (!iterate) return 0;
-  als_sparse_kernel<<<(unsigned)n_all, 32, (size_t)(max_limit + 1) * 32 * sizeof(float), stream>>>(all);
+  als_sparse_kernel<<<(unsigned)n_all, 32, (size_t)(max_limit + 1) * 16 * sizeof(float), stream>>>(all);
   return launch_status("als_sparse_kernel");
 }
 
