@@ -57,6 +57,32 @@ class Quantization:
         self._dev.clear()
         return self
 
+    def to_mat_dir(self, directory: str, scales=SCALES) -> None:
+        """Write the tables in the reference's wire format (RN:403-418): one MATLAB v5 file per scale,
+        `depth_ratio_XXX_XXX_quant.mat` with keys `<tag>` (40,1) and `<tag>_inv` (41,1), float64.  The
+        reference constructor finds them in its working directory."""
+        import scipy.io
+        os.makedirs(directory, exist_ok=True)
+        for s in scales:
+            scipy.io.savemat(os.path.join(directory, _tag(s) + ".mat"),
+                             {_tag(s): getattr(self, _tag(s)), _tag(s) + "_inv": getattr(self, _tag(s) + "_inv")})
+
+    def derive(self, scale: int, from_scale: int) -> Tuple[np.ndarray, np.ndarray]:
+        """Generate the table of `scale` from the table of `from_scale` with the relation the shipped
+        tables satisfy to 1e-14: codebook(s) == codebook(2s)**2 elementwise, i.e. the
+        log-ratio range doubles every time the resolution halves.  Installs the result (marked derived)
+        and returns (thresholds (40,1), levels (41,1))."""
+        if scale not in SCALES or from_scale not in SCALES:
+            raise ValueError(f"scales must be in {SCALES}")
+        expo = float(from_scale) / float(scale)          # 2s -> s: square; s -> 2s: square root
+        q = np.power(getattr(self, _tag(from_scale)), expo)
+        inv = np.power(getattr(self, _tag(from_scale) + "_inv"), expo)
+        setattr(self, _tag(scale), q)
+        setattr(self, _tag(scale) + "_inv", inv)
+        self.derived[scale] = True
+        self._dev = {k: v for k, v in self._dev.items() if k[0] != scale}
+        return q, inv
+
     # ---- reference surface (RN:420-442)
     def get_with_id(self, id):
         if 3 <= id <= 7:

@@ -82,55 +82,109 @@ __device__ __forceinline__ void load_book(const SparseScaleDev& sc, double* thr_
 }
 
 // ---------------------------------------------------------------------------------------------
-// grid = units x 4 bands of 64 rows; a warp owns 8 rows (one pixel row r, columns c = cb..cb+7), a lane two
-// adjacent matrix columns of each.  Only 10 values per row carry information (the fill value and the 3x3
-// window), so after the bit-wise structure check the warp gathers those 80 values through shared memory and
-// quantises them in three full-warp passes instead of quantising 512 values in sixteen.
+// Geometry tables of the sparsify kernel (built at compile time).  A warp owns 8 matrix rows = pixels
+// (r, cb..cb+7) of the page, cb in {0, 8}; all share r0 = min(r/2, 5); pixel column c has c0 = min(c/2, 5) and
+// span0 = min(2 (c/4), 4).  "Slot" numbers the 10 informative values of a row: 0..8 the 3x3 window (row-major),
+// 9 the fill value.
+struct SparsifyTables {
+  // lane_slots[cb/8][r0][lane]: byte i = slot of matrix column 2*lane (low nibble) and 2*lane+1 (high nibble) in row i
+  unsigned long long lane_slots[2][6][32];
+  // item[cb/8][id], id = 10 i + slot < 80: index into the row's staging line (0..23 parent rows x columns, 24 fill)
+  // | i << 5 | slot << 8 | valid << 12
+  unsigned short item[2][96];
+  // compact[c][e]: source of entry e of the 16-float compact row of pixel column c: 0..8 window slot (value - f),
+  // 9 the fill value itself, 15 zero
+  unsigned char compact[16][16];
+};
+constexpr SparsifyTables make_sparsify_tables() {
+  SparsifyTables t{};
+  for (int h = 0; h < 2; ++h)
+    for (int r0 = 0; r0 < 6; ++r0)
+      for (int lane = 0; lane < 32; ++lane) {
+        unsigned long long w = 0;
+        for (int i = 0; i < 8; ++i) {
+          const int c = 8 * h + i, c0 = (c >> 1) < 5 ? (c >> 1) : 5;
+          const int a = (lane >> 2) - r0, cc = (2 * lane) & 7;
+          unsigned long long sl[2] = {9, 9};
+          for (int e = 0; e < 2; ++e)
+            if (a >= 0 && a < 3 && cc + e - c0 >= 0 && cc + e - c0 < 3) sl[e] = (unsigned long long)(3 * a + cc + e - c0);
+          w |= (sl[0] | (sl[1] << 4)) << (8 * i);
+        }
+        t.lane_slots[h][r0][lane] = w;
+      }
+  for (int h = 0; h < 2; ++h)
+    for (int id = 0; id < 96; ++id) {
+      if (id >= 80) { t.item[h][id] = 0; continue; }
+      const int i = id / 10, slot = id % 10;
+      const int c = 8 * h + i, c0 = (c >> 1) < 5 ? (c >> 1) : 5;
+      const int src = slot == 9 ? 24 : 8 * (slot / 3) + c0 + slot % 3;
+      t.item[h][id] = (unsigned short)(src | (i << 5) | (slot << 8) | (1 << 12));
+    }
+  for (int c = 0; c < 16; ++c) {
+    const int c0 = (c >> 1) < 5 ? (c >> 1) : 5, span0 = 2 * (c >> 2) < 4 ? 2 * (c >> 2) : 4;
+    for (int e = 0; e < 16; ++e) {
+      unsigned char code = 15;
+      if (e == 0) code = 9;
+      else if (e <= 12) {
+        const int be = span0 + ((e - 1) & 3) - c0;
+        if (be >= 0 && be < 3) code = (unsigned char)(3 * ((e - 1) >> 2) + be);
+      }
+      t.compact[c][e] = code;
+    }
+  }
+  return t;
+}
+__device__ const SparsifyTables kSparsifyTables = make_sparsify_tables();
+
+// grid = units x 4 bands of 64 rows; a warp owns 8 rows, a lane two adjacent matrix columns of each.  Only 10
+// values per row carry information, so after the bit-wise structure check the warp gathers those 80 values
+// through shared memory and quantises them in three full-warp passes instead of quantising 512 values in
+// sixteen.  The per-lane geometry comes from kSparsifyTables (three small loads per warp).
 __global__ void __launch_bounds__(256) als_sparsify_raw_kernel(const __grid_constant__ SparseParams P) {
   __shared__ double thr_d[kThrPad];
   __shared__ float lvl_f[kLvl + 3];
   __shared__ int sorted;
   __shared__ __align__(16) double stage[8][8][26];   // per warp, per row: 3 parent rows x 8 columns, then the fill value
-  __shared__ float resv[8][8][12];                   // quantised values: slots 0..8 = window (row-major), 9 = fill
-  __shared__ uint8_t resb[8][8][12];                 // their bins
+  __shared__ float resv[8][8][12];                   // quantised values by slot
+  __shared__ uint8_t resb[8][8][16];                 // their bins
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gunit = blockIdx.x >> 2, band = blockIdx.x & 3;
   const SparseScaleDev& sc = find_scale(P, gunit);
   const int64_t unit = gunit - sc.unit_begin;
   const bool quant = sc.kind == RDM_SRC_RAW_F64;
   const int64_t mat_off = unit * (int64_t)(256 * 64);
-  const double* src = reinterpret_cast<const double*>(sc.src) + mat_off;
   const int row0 = band * 64 + warp * 8;             // rows row0 .. row0+7: pixel row row0 >> 4, columns cb .. cb+7
+  const double* src = reinterpret_cast<const double*>(sc.src) + mat_off + row0 * 64 + 2 * lane;
   double2 x[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) x[i] = ldg_stream_f64x2(src + (row0 + i) * 64 + 2 * lane);
+  for (int i = 0; i < 8; ++i) x[i] = ldg_stream_f64x2(src + i * 64);
+  const int r0 = min(row0 >> 5, 5), h = (row0 >> 3) & 1;
+  const unsigned long long slots = kSparsifyTables.lane_slots[h][r0][lane];
+  const unsigned it0 = kSparsifyTables.item[h][lane], it1 = kSparsifyTables.item[h][32 + lane], it2 = kSparsifyTables.item[h][64 + lane];
+  const unsigned centry = *reinterpret_cast<const unsigned*>(&kSparsifyTables.compact[8 * h + (lane >> 2)][4 * (lane & 3)]);
   if (quant) load_book(sc, thr_d, lvl_f, &sorted, tid, 256);
   float* compact = sc.ws + unit * als_ws_stride(256, sc.limit) + als_ws_compact(sc.limit);
   const int srt = quant ? sorted : 1;
-  const int r0 = min(row0 >> 5, 5), cb = row0 & 15;
   const int lane_f = (r0 >= 1) ? 0 : 28;             // column 0 / 56 is outside every window of this pixel row
-  const int a = (lane >> 2) - r0, cc = (2 * lane) & 7;
+  const int a = (lane >> 2) - r0;
   const bool rowin = (unsigned)a < 3u;
+  double* my_stage = &stage[warp][0][rowin ? 8 * a + ((2 * lane) & 7) : 24];
+  const unsigned slo = (unsigned)slots, shi = (unsigned)(slots >> 32);
   bool ok = true;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const int c0 = min((cb + i) >> 1, 5);
+    const unsigned sb = ((i < 4 ? slo : shi) >> (8 * (i & 3))) & 0xffu;   // slots of this lane's two columns in row i
     const long long b0 = __double_as_longlong(x[i].x), b1 = __double_as_longlong(x[i].y);
     const long long fb = __shfl_sync(kFull, b0, lane_f);
-    const bool win0 = rowin && (unsigned)(cc - c0) < 3u, win1 = rowin && (unsigned)(cc + 1 - c0) < 3u;
-    ok = ok && (win0 || b0 == fb) && (win1 || b1 == fb);
-    if (rowin) *reinterpret_cast<double2*>(&stage[warp][i][8 * a + cc]) = x[i];
-    if (lane == lane_f) stage[warp][i][24] = x[i].x;
+    ok = ok && ((sb & 15u) != 9u || b0 == fb) && ((sb >> 4) != 9u || b1 == fb);
+    if (rowin) *reinterpret_cast<double2*>(my_stage + 26 * i) = x[i];
+    else if (lane == lane_f) my_stage[26 * i] = x[i].x;
   }
   __syncwarp();
-#pragma unroll
-  for (int t = 0; t < 3; ++t) {
-    const int id = 32 * t + lane;
-    if (id < 80) {
-      const int i = id / 10, slot = id - 10 * i;
-      const int c0 = min((cb + i) >> 1, 5);
-      const int al = slot / 3, be = slot - 3 * al;
-      const double v = stage[warp][i][slot == 9 ? 24 : 8 * al + c0 + be];
+  auto quantise_item = [&](unsigned g) {
+    if (g & 0x1000u) {
+      const int i = (g >> 5) & 7, slot = (g >> 8) & 15;
+      const double v = stage[warp][i][g & 31u];
       int q = 0;
       float lv;
       if (quant) {
@@ -142,29 +196,28 @@ __global__ void __launch_bounds__(256) als_sparsify_raw_kernel(const __grid_cons
       resv[warp][i][slot] = lv;
       resb[warp][i][slot] = (uint8_t)q;
     }
-  }
+  };
+  quantise_item(it0);
+  quantise_item(it1);
+  quantise_item(it2);
   __syncwarp();
   {   // compact form: 8 rows x 16 floats, one float4 per lane
-    const int i = lane >> 2, k4 = lane & 3;
-    const int c = cb + i, c0 = min(c >> 1, 5), span0 = min((c >> 2) * 2, 4);
+    const int i = lane >> 2;
     const float f = resv[warp][i][9];
     float o[4];
 #pragma unroll
     for (int e4 = 0; e4 < 4; ++e4) {
-      const int e = 4 * k4 + e4 - 1;                 // span entry (alpha, gamma) = (e >> 2, e & 3)
-      const int be = span0 + (e & 3) - c0;           // its column inside the window
-      const bool in = e >= 0 && e < 12 && (unsigned)be < 3u;
-      const float wv = resv[warp][i][in ? 3 * (e >> 2) + be : 9];
-      o[e4] = (e < 0) ? f : (in ? wv - f : 0.f);
+      const unsigned code = (centry >> (8 * e4)) & 15u;
+      const float wv = resv[warp][i][code == 15u ? 9 : code];
+      o[e4] = code == 9u ? f : (code == 15u ? 0.f : wv - f);
     }
-    *reinterpret_cast<float4*>(compact + (row0 + i) * kCompactRowFloats + 4 * k4) = make_float4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<float4*>(compact + (row0 + i) * kCompactRowFloats + 4 * (lane & 3)) = make_float4(o[0], o[1], o[2], o[3]);
   }
   if (sc.bins || sc.values) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const int c0 = min((cb + i) >> 1, 5);
-      const bool win0 = rowin && (unsigned)(cc - c0) < 3u, win1 = rowin && (unsigned)(cc + 1 - c0) < 3u;
-      const int s0 = win0 ? 3 * a + cc - c0 : 9, s1 = win1 ? 3 * a + cc + 1 - c0 : 9;
+      const unsigned sb = ((i < 4 ? slo : shi) >> (8 * (i & 3))) & 0xffu;
+      const int s0 = sb & 15u, s1 = sb >> 4;
       const int64_t off = mat_off + (row0 + i) * 64 + 2 * lane;
       if (sc.bins) *reinterpret_cast<uint16_t*>(sc.bins + off) = (uint16_t)(resb[warp][i][s0] | (resb[warp][i][s1] << 8));
       if (sc.values) *reinterpret_cast<float2*>(sc.values + off) = make_float2(resv[warp][i][s0], resv[warp][i][s1]);
@@ -283,8 +336,9 @@ __device__ __forceinline__ float row_dot(const float (&D)[12], const float (&v)[
   return span_dot<((T & 3) >= 2) ? 1 : 0>(D, v);
 }
 
-// One warp per unit (capping it at 128 registers for 16 warps per SM was measured 7 % slower).  Dynamic shared memory: (limit + 1) x 16 floats
-// (residuals of every iteration, summed over lane pairs).
+// One warp per unit.  Dynamic shared memory: (limit + 1) x 32 floats (per-lane residuals of every iteration).
+// Measured and rejected: capping the kernel at 128 registers (16 warps per SM) and pre-summing the residuals
+// over lane pairs to halve the scratch - both lengthen the iteration (47 -> 52..54 us per launch).
 __global__ void __launch_bounds__(32) als_sparse_kernel(const __grid_constant__ SparseParams P) {
   __shared__ __align__(16) float qs[64];
   __shared__ __align__(16) float ps[256];
@@ -341,11 +395,7 @@ __global__ void __launch_bounds__(32) als_sparse_kernel(const __grid_constant__ 
     e0 += acc;
   }
   const float A = (float)asum;
-  {
-    float e = (float)e0;
-    e += __shfl_xor_sync(kFull, e, 1);
-    if (!(lane & 1)) E[lane >> 1] = e;
-  }
+  E[lane] = (float)e0;
 
   float qa = 1.0f, qb = 1.0f, m = 1.0f;   // this lane's two entries of q (slot rows >> 2); centre of the q statistics
   qs[lane] = 1.0f;
@@ -383,11 +433,7 @@ __global__ void __launch_bounds__(32) als_sparse_kernel(const __grid_constant__ 
     p_row(std::integral_constant<int, 2>{}); p_row(std::integral_constant<int, 3>{});
     p_row(std::integral_constant<int, 4>{}); p_row(std::integral_constant<int, 5>{});
     p_row(std::integral_constant<int, 6>{}); p_row(std::integral_constant<int, 7>{});
-    {
-      float e = fmaf(-2.0f, fmaf(S1, pg, psd), fmaf(64.0f, gg, fmaf(V, pp, A)));
-      e += __shfl_xor_sync(kFull, e, 1);
-      if (!(lane & 1)) E[k * 16 + (lane >> 1)] = e;
-    }
+    E[k * 32 + lane] = fmaf(-2.0f, fmaf(S1, pg, psd), fmaf(64.0f, gg, fmaf(V, pp, A)));
 #pragma unroll
     for (int dr = 0; dr < 2; ++dr) {
       const float4 pv = make_float4(p[4 * dr], p[4 * dr + 1], p[4 * dr + 2], p[4 * dr + 3]);
@@ -426,7 +472,7 @@ __global__ void __launch_bounds__(32) als_sparse_kernel(const __grid_constant__ 
   for (int k = lane; k <= limit; k += 32) {
     double t = 0.0;
 #pragma unroll 8
-    for (int l = 0; l < 16; ++l) t += (double)E[k * 16 + ((l + lane) & 15)];
+    for (int l = 0; l < 32; ++l) t += (double)E[k * 32 + ((l + lane) & 31)];
     rec[k] = (float)t;
   }
 }
@@ -480,7 +526,7 @@ int als_sparse_launch(const rdm_als_scale_t* scales, int32_t n_scales, int64_t n
     if (rc) return rc;
   }
   if (!iterate) return 0;
-  als_sparse_kernel<<<(unsigned)n_all, 32, (size_t)(max_limit + 1) * 16 * sizeof(float), stream>>>(all);
+  als_sparse_kernel<<<(unsigned)n_all, 32, (size_t)(max_limit + 1) * 32 * sizeof(float), stream>>>(all);
   return launch_status("als_sparse_kernel");
 }
 

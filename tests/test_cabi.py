@@ -97,3 +97,26 @@ def test_quantization_surface_and_mat_loader(tmp_path):
     q2 = Quantization.from_mat_dir(str(tmp_path))
     assert not q2.derived[8] and q2.depth_ratio_008_008_quant[0, 0] == 0.5
     assert np.array_equal(q2.depth_ratio_016_016_quant, q.depth_ratio_016_016_quant)
+
+
+def test_codebook_tooling(tmp_path):
+    """.mat wire format round trip (RN:403-418) and the generator for missing scales."""
+    import numpy as np
+    from md_rdm_b200.codebooks import Quantization
+    q = Quantization()
+    shipped16 = q.depth_ratio_016_016_quant.copy(), q.depth_ratio_016_016_quant_inv.copy()
+    shipped64 = q.depth_ratio_064_064_quant.copy(), q.depth_ratio_064_064_quant_inv.copy()
+    t, lv = q.derive(16, 32)                              # codebook(s) == codebook(2s)**2
+    assert t.shape == (40, 1) and lv.shape == (41, 1) and q.derived[16]
+    assert np.allclose(t, shipped16[0], rtol=1e-13, atol=0) and np.allclose(lv, shipped16[1], rtol=1e-13, atol=0)
+    t, lv = q.derive(64, 32)                              # ... and the square root going up
+    assert np.allclose(t, shipped64[0], rtol=1e-13, atol=0) and np.allclose(lv, shipped64[1], rtol=1e-13, atol=0)
+    assert Quantization().derived[8] and not Quantization().derived[16]   # only the missing 008 file is derived in the package
+    fresh = Quantization()
+    fresh.to_mat_dir(str(tmp_path))
+    back = Quantization.from_mat_dir(str(tmp_path))
+    for s in (8, 16, 32, 64, 128):
+        tag = f"depth_ratio_{s:03d}_{s:03d}_quant"
+        assert np.array_equal(getattr(back, tag), getattr(fresh, tag)) and np.array_equal(getattr(back, tag + "_inv"), getattr(fresh, tag + "_inv"))
+        assert getattr(back, tag).shape == (40, 1) and not back.derived[s]
+    assert back.get_size_id(5) == 32 and back.get_with_id(5)[0] is getattr(back, "depth_ratio_032_032_quant")
