@@ -8,7 +8,7 @@ ours      : BASELINE.json configs[1] - standalone fusion path on B200, batch 16,
             inputs (ordinary map + raw pair matrices: 1 f32 64x64 + 5 f64 256x64 per image)
             resident in HBM, one step = quantize + ALS + decompose + weighted reconstruction of one
             batch (5 kernel launches replayed from a CUDA graph).  Steps rotate over a ring of
-            resident batches larger than L2 and over 16 streams (batches in flight).
+            resident batches larger than L2 and over 32 streams (batches in flight).
             e2e = the public host API (FusionPlan.run_pinned: decoder maps in pinned host memory
             -> fused 128x128 log-depth maps in pinned host memory), H2D and D2H copies inside
             the timed region, pair build fused in front.
@@ -568,8 +568,8 @@ def main():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--streams", type=int, default=16, help="batches in flight (CUDA stream branches)")
-    ap.add_argument("--ring", type=int, default=64, help="resident input batches (ring > L2)")
+    ap.add_argument("--streams", type=int, default=32, help="batches in flight (CUDA stream branches)")
+    ap.add_argument("--ring", type=int, default=128, help="resident input batches (ring > L2)")
     ap.add_argument("--cpu-images", type=int, default=48)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stage-table", action="store_true")

@@ -233,7 +233,7 @@ class FusionPlan:
         hb["depth"].copy_(self.depth, non_blocking=True)          # D2H of the fused log-depth maps
 
     def capture_e2e(self) -> None:
-        """CUDA graph of the whole host call: H2D copy node, the three kernels, D2H copy node."""
+        """CUDA graph of the whole host call: H2D copy node, the kernels of run(), D2H copy node."""
         self._host_buffers()
         with torch.cuda.device(self.device):
             s = torch.cuda.Stream()
