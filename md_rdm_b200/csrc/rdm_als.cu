@@ -847,6 +847,7 @@ extern "C" int rdm_als_fused_phases(const rdm_als_scale_t* scales, int32_t n_sca
   for (int k = 0; k < n_scales; ++k) {
     const rdm_als_scale_t& h = scales[k];
     RDM_REQUIRE(h.src && h.ws, "rdm_als_fused: scale %d: src and ws are required", k);
+    RDM_REQUIRE(aligned16(h.ws), "rdm_als_fused: scale %d: ws must be 16-byte aligned", k);
     RDM_REQUIRE(h.rows == 64 || h.rows == 256, "rdm_als_fused: scale %d: rows must be 64 or 256 (got %d)", k, h.rows);
     RDM_REQUIRE(h.src_kind >= RDM_SRC_RAW_F64 && h.src_kind <= RDM_SRC_MAP_F32, "rdm_als_fused: scale %d: bad src_kind %d", k, h.src_kind);
     RDM_REQUIRE(h.limit >= 0 && h.limit <= (h.rows == 64 ? 63 : 127), "rdm_als_fused: scale %d: limit %d out of range", k, h.limit);

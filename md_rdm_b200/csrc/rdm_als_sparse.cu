@@ -331,10 +331,29 @@ __device__ __forceinline__ float span_dot(const float (&D)[12], const float (&v)
     if ((e & 3) >= FROM) acc = fmaf(D[e], v[e], acc);
   return acc;
 }
+#ifdef RDM_SPARSE_FFMA2
+// Variant for A/B measurements: the 12-entry dot as six packed fma.rn.f32x2 (even / odd partial sums) + one add.
+// The register pairs (D[2e], D[2e+1]) and (v[2e], v[2e+1]) are contiguous, so the compiler needs no moves.
+template <int T>
+__device__ __forceinline__ float row_dot(const float (&D)[12], const float (&v)[12]) {
+  unsigned long long acc = 0ull;   // (0.f, 0.f)
+#pragma unroll
+  for (int e = 0; e < 12; e += 2) {
+    unsigned long long d, x;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(D[e]), "f"(D[e + 1]));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(v[e]), "f"(v[e + 1]));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(d), "l"(x));
+  }
+  float lo, hi;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc));
+  return lo + hi;
+}
+#else
 template <int T>   // row slot T = 4 dr + cc
 __device__ __forceinline__ float row_dot(const float (&D)[12], const float (&v)[12]) {
   return span_dot<((T & 3) >= 2) ? 1 : 0>(D, v);
 }
+#endif
 
 // One warp per unit.  Dynamic shared memory: (limit + 1) x 32 floats (per-lane residuals of every iteration).
 // Measured and rejected: capping the kernel at 128 registers (16 warps per SM) and pre-summing the residuals

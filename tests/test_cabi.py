@@ -52,6 +52,12 @@ def test_argument_errors_do_not_launch(lib):
     sc.rows = 256
     rc = lib.rdm_als_fused(sc, 1, 6, 4, null)
     assert rc < 0 and b"multiple of group" in lib.rdm_last_error()
+    sc.ws = 20
+    rc = lib.rdm_als_fused(sc, 1, 4, 4, null)
+    assert rc < 0 and b"ws must be 16-byte aligned" in lib.rdm_last_error()
+    sc.ws = 16
+    rc = lib.rdm_als_fused_phases(sc, 1, 4, 4, 32, null)
+    assert rc < 0 and b"phase_mask" in lib.rdm_last_error()
     # empty batches are a no-op, not an error
     assert lib.rdm_pair_v1_f32(one, 0, one, null) == 0
     assert lib.rdm_als_fused(sc, 1, 0, 4, null) == 0
