@@ -113,9 +113,10 @@ typedef struct rdm_als_scale {
   float* map_out;           /* optional (N,side,side) f32: CP:218-238 `reconstruct` re-tiling
                                (bug-compatible: only pages 0..side/16-1 reach the map) */
   float* ws;                /* REQUIRED workspace, N * rdm_als_ws_floats(rows, pages, limit) f32:
-                               per (image, page) the SSE record [limit+1], then every iterate
-                               p_1..p_limit [limit][rows] (the arg-min is batch-wide, so the
-                               iterate to emit is only known after all images have finished) */
+                               16-byte aligned; per (image, page) the SSE record, then every
+                               iterate p_1..p_limit [limit][rows] (the arg-min is batch-wide, so
+                               the iterate to emit is only known after all images have finished),
+                               then for 256-row units the 16 KB compact page form and its flags */
   float* record_out;        /* optional (N/group,P,limit+1) f32 rmse record (CP:53-61) */
   int32_t* kstar_out;       /* optional (N/group,P) i32 selected iteration (CP:74, CP:143) */
 } rdm_als_scale_t;
@@ -132,7 +133,9 @@ int rdm_als_fused(const rdm_als_scale_t* scales, int32_t n_scales, int64_t n_ima
  * needs ws from a previous iterate phase).  The iterate phase is three launches that can also be
  * selected one by one (profiling): bit 2 = compact page form (structure check + Lloyd, the
  * HBM-streaming kernel), bit 3 = ALS on the compact pages (one warp per page), bit 4 = dense ALS
- * (8x8 maps and any page matrix without the pair-build structure); bit 0 = bits 2|3|4. */
+ * (8x8 maps and any page matrix without the pair-build structure); bit 0 = bits 2|3|4.  Bits 3 and
+ * 4 read the per-page structure flags bit 2 leaves in ws, so they must follow a bit-2 launch on
+ * the same inputs (same stream, or ordered by an event); they are independent of each other. */
 int rdm_als_fused_phases(const rdm_als_scale_t* scales, int32_t n_scales, int64_t n_images,
                          int32_t group, int32_t phase_mask, rdm_stream_t stream);
 /* f32 workspace elements per image for one scale (rdm_als_scale_t.ws) */
