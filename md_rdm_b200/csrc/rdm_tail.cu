@@ -593,10 +593,9 @@ __global__ void __launch_bounds__(256) recombination_bwd_kernel(const double* __
 // 128x128 f64 log-depth map, so the 128 KB per image output - the only significant HBM traffic of
 // stages 4+5 - is spread over the chip.  The cheap bicubic levels are redone by every CTA; the f64
 // logs are split over the cluster and exchanged through distributed shared memory.
-// All decoders descend their pyramids TOGETHER, one level per stage (5-6 stages of two barriers
-// instead of one barrier-separated stage per decoder and level), and the expensive f64 log() calls
-// of a level are spread over all threads before the per-slot weighted sum is formed in candidate
-// order (CP:521 sums decoder 1 first).
+// All decoders descend their pyramids TOGETHER down to 1x1 first (one barrier per large level), then
+// the expensive f64 div + log of EVERY level is taken in one stage spread over all threads of the
+// cluster, then the per-slot weighted sums are formed in candidate order (CP:521 sums decoder 1 first).
 constexpr int kMaxRel = 6;
 constexpr int kMaxDec = kMaxRel + 1;
 struct TailParams {
@@ -616,7 +615,8 @@ struct TailParams {
   int32_t act[8][kMaxDec];  // decoders that have level k, in candidate order
   int32_t nact[8];
   int32_t dtotal;           // doubles of pyramid storage
-  int32_t lmax;             // floats of per-stage log scratch
+  int32_t lofs[8];          // first float of level k in the log buffer (levels kmax .. 1, in that order)
+  int32_t ltotal;           // floats of the log buffer = sum_k nact[k] 4^k
   int32_t kmax;
   int32_t bands;
 };
@@ -628,8 +628,7 @@ __global__ void __launch_bounds__(RDM_TAIL_THREADS) fuse_tail_kernel(const __gri
   extern __shared__ __align__(16) double D[];                // P.dtotal doubles
   float* yh = reinterpret_cast<float*>(D + P.dtotal);         // slot k at off_level(k)
   const int ylen = off_level(P.kmax + 1);
-  float* L = yh + ylen;                                       // 2 x P.lmax floats: f32(log F) of the current level, double buffered
-  int lbuf = 0;
+  float* L = yh + ylen;                                       // P.ltotal floats: f32(log F) of every level
   cg::cluster_group cluster = cg::this_cluster();             // the P.bands CTAs of one image
   __shared__ float scratch[32];
   __shared__ float wsm[64];                                   // the (<= 4 + 6*6) weights, read from HBM once
@@ -665,55 +664,12 @@ __global__ void __launch_bounds__(RDM_TAIL_THREADS) fuse_tail_kernel(const __gri
       for (int idx = tid; idx < side * side; idx += blockDim.x) dn[idx] = (double)src[idx];
     }
   }
-  cluster.sync();   // every CTA of the cluster is running: its shared memory may be written from here on
+  __syncthreads();
 #ifdef RDM_TIMING
   tt[ti++] = clock64();
 #endif
-  // The f64 div + log of the fine-detail values is the expensive part of the pyramids (~110 instructions per
-  // value): it is SPLIT over the CTAs of the cluster and every result is stored into the log buffer of all of
-  // them through distributed shared memory, instead of every band redoing all of it.  The buffer is double
-  // buffered, so one cluster barrier per stage orders both the remote writes and the local reads.
-  const int nb = P.bands, gthreads = blockDim.x * nb, gtid = band * blockDim.x + tid;
-  auto put_log = [&](float* dst, float v) {
-    for (int b = 0; b < nb; ++b) *cluster.map_shared_rank(dst, b) = v;
-  };
-  // F_k = D_k / up2(D_{k-1}) (CP:389) and its log (CP:478-480) for the items of level k, into L[lofs...];
-  // up to four independent log() chains per thread (a f64 log is ~1000 cycles of dependent latency).
-  auto log_level = [&](int k, int lofs) {
-    const int side = 1 << k, half = side >> 1, n = P.nact[k] * side * side;
-    for (int base = gtid; base < n; base += 4 * gthreads) {
-      double lg[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int item = base + j * gthreads;
-        if (item < n) {
-          const int a = item >> (2 * k), idx = item & (side * side - 1);
-          const double* bp = D + P.doff[P.act[k][a]];
-          const int y = idx >> k, x = idx & (side - 1);
-          lg[j] = log(bp[off_level(k) + idx] / bp[off_level(k - 1) + (y >> 1) * half + (x >> 1)]);
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int item = base + j * gthreads;
-        if (item < n) {
-          const int a = item >> (2 * k), idx = item & (side * side - 1);
-          const int d = P.act[k][a];
-          if (P.A_out[k]) P.A_out[k][(img * P.K[k] + P.cand[d][k]) * (int64_t)(side * side) + idx] = lg[j];
-          put_log(L + lofs + item, (float)lg[j]);
-        }
-      }
-    }
-  };
-  // slot k of y_hat: sum over candidates in decoder order (CP:521 / CP:526)
-  auto sum_level = [&](int k, int lofs) {
-    const int n = 1 << (2 * k), na = P.nact[k];
-    for (int idx = tid; idx < n; idx += blockDim.x) {
-      float y = 0.f;
-      for (int a = 0; a < na; ++a) y = fmaf(L[lofs + a * n + idx], wl[k][a], y);
-      yh[off_level(k) + idx] = y;
-    }
-  };
+  // ---- all pyramids down to 1x1 first (cheap, redone by every CTA of the cluster): large levels with all
+  // threads, levels <= 3 (at most 84 values per decoder) in warp 0 back to back
   auto bicubic_level = [&](int k, int first, int stride) {   // level k-1 of every decoder that has level k
     const int side = 1 << k, half = side >> 1;
     for (int item = first; item < P.nact[k] * half * half; item += stride) {
@@ -723,59 +679,71 @@ __global__ void __launch_bounds__(RDM_TAIL_THREADS) fuse_tail_kernel(const __gri
           bicubic_half_at([&](int r, int c) { return cur[r * side + c]; }, idx >> (k - 1), idx & (half - 1), side);
     }
   };
-  for (int k = P.kmax; k >= 4; --k) {   // large levels: one stage each
+  for (int k = P.kmax; k >= 4; --k) {
     bicubic_level(k, tid, blockDim.x);
     __syncthreads();
-#ifdef RDM_TIMING
-    if (ti < 11) tt[ti++] = clock64();
-#endif
-    log_level(k, lbuf * P.lmax);
-    cluster.sync();
-#ifdef RDM_TIMING
-    if (ti < 11) tt[ti++] = clock64();
-#endif
-    sum_level(k, lbuf * P.lmax);
-    lbuf ^= 1;
-#ifdef RDM_TIMING
-    if (ti < 11) tt[ti++] = clock64();
-#endif
   }
-  // levels <= 3 (at most 84 values per decoder) in ONE stage: the three tiny bicubic steps run in
-  // warp 0 back to back, then all their logs are taken together
   const int ksmall = P.kmax < 3 ? P.kmax : 3;
   if (tid < 32)
     for (int k = ksmall; k >= 1; --k) {
       bicubic_level(k, tid, 32);
       __syncwarp();
     }
-  __syncthreads();
+  cluster.sync();   // pyramids complete; every CTA of the cluster is running: its shared memory may be written now
 #ifdef RDM_TIMING
   if (ti < 11) tt[ti++] = clock64();
 #endif
-  {   // one flattened item space over levels ksmall..1 so that no thread takes two logs in a row
-    int n3 = 0, n2 = 0, n1 = 0;
-    if (ksmall >= 3) n3 = P.nact[3] << 6;
-    if (ksmall >= 2) n2 = P.nact[2] << 4;
-    n1 = P.nact[1] << 2;
-    for (int t = gtid; t < n3 + n2 + n1; t += gthreads) {
-      const int k = (t < n3) ? 3 : (t < n3 + n2 ? 2 : 1);
-      const int item = t - (k == 3 ? 0 : (k == 2 ? n3 : n3 + n2));
-      const int side = 1 << k, half = side >> 1;
-      const int a = item >> (2 * k), idx = item & (side * side - 1);
-      const int d = P.act[k][a];
-      const double* bp = D + P.doff[d];
-      const int y = idx >> k, x = idx & (side - 1);
-      const double lg = log(bp[off_level(k) + idx] / bp[off_level(k - 1) + (y >> 1) * half + (x >> 1)]);
-      if (P.A_out[k]) P.A_out[k][(img * P.K[k] + P.cand[d][k]) * (int64_t)(side * side) + idx] = lg;
-      put_log(L + lbuf * P.lmax + t, (float)lg);   // level 3 first, then 2, then 1: the offsets sum_level() is given below
+  // ---- ONE log stage for all levels.  F_k = D_k / up2(D_{k-1}) (CP:389) and its log (CP:478-480); the f64
+  // div + log is the expensive part of the tail (~110 instructions and ~1700 cycles of dependent latency per
+  // value), so the items of all levels are SPLIT over the CTAs of the cluster (two independent chains per
+  // thread at scales 8/16/32) and every result is stored into the log buffer of all of them through
+  // distributed shared memory, instead of every band redoing all of it level after level.
+  const int nb = P.bands, gthreads = blockDim.x * nb, gtid = band * blockDim.x + tid;
+  for (int base = gtid; base < P.ltotal; base += 4 * gthreads) {
+    double lg[4];
+    int lev[4], itm[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int t = base + j * gthreads;
+      lev[j] = 0;
+      if (t < P.ltotal) {
+        int k = P.kmax;
+        while (k > 1 && t >= P.lofs[k - 1]) --k;   // levels are laid out kmax first
+        const int item = t - P.lofs[k];
+        const int side = 1 << k, half = side >> 1;
+        const int a = item >> (2 * k), idx = item & (side * side - 1);
+        const double* bp = D + P.doff[P.act[k][a]];
+        const int y = idx >> k, x = idx & (side - 1);
+        lg[j] = log(bp[off_level(k) + idx] / bp[off_level(k - 1) + (y >> 1) * half + (x >> 1)]);
+        lev[j] = k;
+        itm[j] = item;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = lev[j];
+      if (k) {
+        const int side2 = 1 << (2 * k);
+        const int a = itm[j] >> (2 * k), idx = itm[j] & (side2 - 1);
+        const int d = P.act[k][a];
+        if (P.A_out[k]) P.A_out[k][(img * P.K[k] + P.cand[d][k]) * (int64_t)side2 + idx] = lg[j];
+        const float v = (float)lg[j];
+        float* dst = L + base + j * gthreads;
+        for (int b = 0; b < nb; ++b) *cluster.map_shared_rank(dst, b) = v;
+      }
     }
   }
   cluster.sync();   // last remote access: a CTA may leave the cluster afterwards
-  {
-    int lofs = lbuf * P.lmax;
-    for (int k = ksmall; k >= 1; --k) {
-      sum_level(k, lofs);
-      lofs += P.nact[k] << (2 * k);
+#ifdef RDM_TIMING
+  if (ti < 11) tt[ti++] = clock64();
+#endif
+  // slot k of y_hat: sum over candidates in decoder order (CP:521 / CP:526)
+  for (int k = P.kmax; k >= 1; --k) {
+    const int n = 1 << (2 * k), na = P.nact[k], lofs = P.lofs[k];
+    for (int idx = tid; idx < n; idx += blockDim.x) {
+      float y = 0.f;
+      for (int a = 0; a < na; ++a) y = fmaf(L[lofs + a * n + idx], wl[k][a], y);
+      yh[off_level(k) + idx] = y;
     }
   }
 #ifdef RDM_TIMING
@@ -1174,18 +1142,16 @@ extern "C" int rdm_fuse_tail(const int64_t* x_d1, const float* const* rel, const
     dtotal += off_level(n + 1);
   }
   P.dtotal = (dtotal + 1) & ~1;
-  int lmax = 0;
-  for (int k = 1; k <= P.kmax; ++k) {
+  for (int k = 1; k <= P.kmax; ++k)
     for (int d = 0; d <= n_rel; ++d)
       if (P.nlev[d] >= k) P.act[k][P.nact[k]++] = d;
-    lmax = P.nact[k] * (1 << (2 * k)) > lmax ? P.nact[k] * (1 << (2 * k)) : lmax;
+  int ltotal = 0;
+  for (int k = P.kmax; k >= 1; --k) {   // log buffer: level kmax first
+    P.lofs[k] = ltotal;
+    ltotal += P.nact[k] << (2 * k);
   }
-  {
-    int small = 0;   // levels <= 3 are logged together
-    for (int k = 1; k <= (P.kmax < 3 ? P.kmax : 3); ++k) small += P.nact[k] * (1 << (2 * k));
-    if (small > lmax) lmax = small;
-  }
-  P.lmax = lmax;
+  P.lofs[0] = ltotal;
+  P.ltotal = ltotal;
   int woff = 0;
   for (int k = 0; k < 8; ++k) {
     P.w_off[k] = woff;
@@ -1198,7 +1164,7 @@ extern "C" int rdm_fuse_tail(const int64_t* x_d1, const float* const* rel, const
   while (bands < 8 && bands < (1 << P.kmax) && n_images * bands < 64) bands <<= 1;   // one thread-block cluster per image
   P.bands = bands;
   RDM_REQUIRE(n_images * bands < (1ll << 31), "rdm_fuse_tail: too many images");
-  const size_t smem = (size_t)P.dtotal * sizeof(double) + ((size_t)off_level(P.kmax + 1) + 2 * (size_t)lmax) * sizeof(float);
+  const size_t smem = (size_t)P.dtotal * sizeof(double) + ((size_t)off_level(P.kmax + 1) + (size_t)ltotal) * sizeof(float);
   RDM_REQUIRE(smem <= 220 * 1024, "rdm_fuse_tail: decoder pyramids need %zu bytes of shared memory (max 220 KB)", smem);
   cudaError_t e = ensure_dyn_smem(fuse_tail_kernel, smem, smem_set_fuse_tail_kernel);
   if (e != cudaSuccess) {
