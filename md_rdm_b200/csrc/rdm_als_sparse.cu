@@ -369,10 +369,7 @@ __global__ void __launch_bounds__(32) als_sparse_kernel(const __grid_constant__ 
   const int limit = sc.limit;
   float* wsu = sc.ws + unit * als_ws_stride(256, limit);
   const float* compact = wsu + als_ws_compact(limit);
-  {
-    const float4 fl = *reinterpret_cast<const float4*>(compact + kCompactFloats);
-    if (!(fl.x == 1.0f && fl.y == 1.0f && fl.z == 1.0f && fl.w == 1.0f)) return;   // dense kernel takes it
-  }
+  const float4 fl = *reinterpret_cast<const float4*>(compact + kCompactFloats);   // checked after the loads below are in flight
   float* rec = wsu;
   float* hist = wsu + als_ws_rec(256, limit);
   const int rh = lane >> 2, kq = lane & 3;
@@ -398,6 +395,7 @@ __global__ void __launch_bounds__(32) als_sparse_kernel(const __grid_constant__ 
       D[t][7] = c.x; D[t][8] = c.y; D[t][9] = c.z; D[t][10] = c.w;
       D[t][11] = d.x;
     }
+  if (!(fl.x == 1.0f && fl.y == 1.0f && fl.z == 1.0f && fl.w == 1.0f)) return;   // not a pair matrix: the dense kernel takes it
   // A = sum over this lane's rows of A_rho, and the record of iteration 0 (p = q = 1, CP:123):
   // sum_j fl(1 - R)^2 with 52 columns outside the span
   double e0 = 0.0, asum = 0.0;

@@ -650,19 +650,19 @@ __global__ void __launch_bounds__(RDM_TAIL_THREADS) fuse_tail_kernel(const __gri
 
   // ---- top levels: decoder 1 = x / gm(x) in f32 (RN:117); relative decoders as they come
   {
-    float v = 1.f, pw = 1.f;
-    if (tid < 64) {
-      v = (float)P.x_d1[img * 64 + tid];
-      pw = powf(v, 0.015625f);   // torch.pow(int64 -> f32, 1/64) is an f32 pow as well (CP:248-253)
-    }
-    const float gm = block_prod<float>(pw, scratch);
-    if (tid < 64) D[P.doff[0] + off_level(3) + tid] = (double)(v / gm);
+    // the DORN counts are requested first and consumed last, so that their latency overlaps the map loads
+    long long xi = 1;
+    if (tid < 64) xi = P.x_d1[img * 64 + tid];
     for (int r = 0; r < P.n_rel; ++r) {
       const int side = P.side[r];
       const float* src = P.rel[r] + img * (int64_t)side * side;
       double* dn = D + P.doff[r + 1] + off_level(P.nlev[r + 1]);
       for (int idx = tid; idx < side * side; idx += blockDim.x) dn[idx] = (double)src[idx];
     }
+    const float v = (float)xi;
+    const float pw = (tid < 64) ? powf(v, 0.015625f) : 1.f;   // torch.pow(int64 -> f32, 1/64) is an f32 pow as well (CP:248-253)
+    const float gm = block_prod<float>(pw, scratch);
+    if (tid < 64) D[P.doff[0] + off_level(3) + tid] = (double)(v / gm);
   }
   __syncthreads();
 #ifdef RDM_TIMING
