@@ -548,3 +548,18 @@ int als_sparse_launch(const rdm_als_scale_t* scales, int32_t n_scales, int64_t n
 }
 
 }  // namespace rdm
+
+// Host copy of the sparsify kernel's geometry tables (built by the same constexpr function), so that the CPU
+// test suite can check them against the oracle's window mask without a GPU.
+extern "C" int rdm_sparsify_geometry(uint64_t* lane_slots, uint16_t* item, uint8_t* compact) {
+  RDM_REQUIRE(lane_slots && item && compact, "rdm_sparsify_geometry: null pointer");
+  static constexpr rdm::SparsifyTables t = rdm::make_sparsify_tables();
+  for (int h = 0; h < 2; ++h)
+    for (int r0 = 0; r0 < 6; ++r0)
+      for (int l = 0; l < 32; ++l) lane_slots[(h * 6 + r0) * 32 + l] = t.lane_slots[h][r0][l];
+  for (int h = 0; h < 2; ++h)
+    for (int i = 0; i < 96; ++i) item[h * 96 + i] = t.item[h][i];
+  for (int c = 0; c < 16; ++c)
+    for (int e = 0; e < 16; ++e) compact[c * 16 + e] = t.compact[c][e];
+  return 0;
+}
