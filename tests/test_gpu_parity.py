@@ -487,6 +487,39 @@ def test_cuda_graph_replay_equals_eager(dev, books):
     assert torch.equal(host, eager.cpu())
 
 
+def test_plan_overlap_and_multi_group_equal_plain_runs(dev, books):
+    """FusionPlan(overlap=True) (dense 8x8 ALS forked beside the page kernels) and a plan that carries two
+    reference batches per launch (group = 8 of N = 16: one arg-min per group, CP:172-173) give bit-identical
+    results to plain single-batch runs, eagerly and from a CUDA graph."""
+    from md_rdm_b200.fusion import FusionPlan
+    scales = (8, 16, 32)
+    x_d1, rel, weights = fr.synthetic_batch(16, scales, seed=31)
+    rel[1][8:] = 1.0                               # second group: constant 16x16 maps -> a different k*
+    w = torch.cat([t.reshape(-1) for t in weights]).to(dev)
+    halves = []
+    for lo in (0, 8):
+        p = FusionPlan(8, scales, "map", device=dev)
+        p.load_inputs(x_d1[lo:lo + 8].to(dev), [r[lo:lo + 8].to(dev) for r in rel], w)
+        p.run()
+        torch.cuda.synchronize()
+        halves.append((p.depth.clone(), {s: p.kstar[s].clone() for s in scales}))
+    assert halves[0][1][16].view(-1).tolist() != halves[1][1][16].view(-1).tolist()
+    for overlap in (False, True):
+        plan = FusionPlan(16, scales, "map", group=8, device=dev, overlap=overlap)
+        plan.load_inputs(x_d1.to(dev), [r.to(dev) for r in rel], w)
+        plan.run()
+        torch.cuda.synchronize()
+        for gi in range(2):
+            assert torch.equal(plan.depth[8 * gi:8 * gi + 8], halves[gi][0]), (overlap, gi)
+            for s in scales:
+                assert torch.equal(plan.kstar[s][gi], halves[gi][1][s][0]), (overlap, gi, s)
+        eager = plan.depth.clone()
+        plan.depth.zero_()
+        plan.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(plan.depth, eager), overlap
+
+
 def test_weights_gradient_golden(dev):
     """the only gradient the training loss needs (loss = mean(depth^2))."""
     from md_rdm_b200.ops import fuse_tail_autograd
