@@ -76,3 +76,9 @@ def test_algorithmic_bytes_match_survey():
     assert ab["pair"] == 679680 and ab["quantize"] == 1101824 and ab["als"] == 349440
     assert ab["decompose"] == 20872 and ab["reconstruct"] == 151516 and ab["path"] == 1623652
     assert bench.algorithmic_bytes((8, 16, 32, 64))["path"] == 6216612
+    # the per-kernel split reported in config.kernel_gbs / roofline partitions the same contract bytes
+    for scales in ((8, 16, 32), (8, 16, 32, 64)):
+        ab = bench.algorithmic_bytes(scales)
+        assert ab["sparsify_kernel"] + ab["als_sparse_kernel"] + ab["als_dense_kernel"] == ab["quantize"] + ab["als"]
+        assert ab["als_select_kernel"] + ab["tail_kernel"] + ab["quantize"] + ab["als"] >= ab["path"]
+    assert bench.LAUNCHES_PER_STEP == 5
