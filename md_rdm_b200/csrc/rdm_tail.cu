@@ -885,13 +885,16 @@ extern "C" int rdm_decompose(const void* in, int32_t in_is_f64, int64_t n_images
   if (len == 0) return 0;
   const size_t smem = kPyrDoubles * sizeof(double);
   cudaError_t e;
-  // Levels of side >= 64 are banded over the whole chip (8 output rows per CTA, 128-bit accesses); each such
-  // launch parks D_{k-1} in the F_{k-1} slot of the output, where the next launch reads it.  The remaining
-  // 32x32 (or smaller) pyramid is one CTA per image in shared memory.
+  // A top level of side >= 64 is banded over the whole chip (8 output rows per CTA, 128-bit accesses); the
+  // launch parks D_{k-1} in the F_{k-1} slot of the output, where the per-image kernel (one CTA per image, the
+  // remaining <= 64x64 pyramid in shared memory) reads ALL of it before it writes F_{k-1} there.  Only ONE
+  // banded launch: a second one would read its input from the slot its own CTAs overwrite (the bicubic halo
+  // rows of a band belong to the neighbouring band's CTA - a race that showed up on one box as a 4e-5 error in
+  // D_0 of a 128x128 decomposition).
   const void* cur = in;
   int cur_f64 = in_is_f64, s = side, nc = n;
   const int base = relative_map ? 0 : 1;
-  while (s >= 64) {
+  if (s >= 64) {
     const size_t tsm = (size_t)(10 * s + 4 * (s / 2)) * sizeof(double);
     RDM_REQUIRE(n_images * (s / 8) < (1ll << 31), "rdm_decompose: too many images");
     const unsigned ctas = (unsigned)(n_images * (s / 8));

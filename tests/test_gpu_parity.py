@@ -344,6 +344,20 @@ def test_decompose_vs_oracle(dev, side, rel):
         assert _rel_err(a.cpu(), b) < 1e-13
 
 
+def test_decompose_128_many_images_no_interband_race(dev):
+    """Regression: the 128x128 decomposition bands its top level over many CTAs; a second banded launch used to
+    read D_6 from the slot its own CTAs were overwriting with F_6 (halo rows of a band belong to the neighbour's
+    CTA), which showed on some boxes as a 4e-5 error in D_0.  Many images keep every SM busy with bands."""
+    from md_rdm_b200.ops import unpack_pyramid
+    g = torch.Generator().manual_seed(128128)
+    x = torch.exp(0.3 * torch.randn(96, 1, 128, 128, generator=g, dtype=torch.float64))
+    ref = fr.decompose(x, 7, relative_map=False)
+    for _ in range(3):
+        ours = unpack_pyramid(R.decompose(x.to(dev), False), 96, 128, False)
+        for a, b in zip(ours, ref):
+            assert _rel_err(a.cpu(), b) < 1e-13
+
+
 def test_gt_decompose_golden(dev):
     import md_rdm_b200.computations as cp
     g = load_golden("gt_decompose_b2.npz")
