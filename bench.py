@@ -15,6 +15,8 @@ ours      : BASELINE.json configs[1] - standalone fusion path on B200, batch 16,
 reference : the reference's own CPU algorithm for the same path (oracle/literal.py: the
             loop-for-loop restatement of the reference, which is Python and cannot travel to
             the GPU box), one image per step, all host threads.
+A step lasts ~11 us, so the 32-lane pipeline needs a few hundred steps to fill: K = 2000 by default (22 ms);
+with K = 37 the same code reports ~0.8 M maps/s, with K = 5 ~0.3 M (start-up and host launch time dominate).
 One JSON line on stdout (rank 0).  Weak scaling: every rank runs K steps on its own batches;
 no collective on the data path (torch.distributed is used for the barrier and the max only).
 """
@@ -369,15 +371,22 @@ def run_ours(args):
         fork.record(cur)
         for _, st in lanes:
             st.wait_event(fork)
-        n_graphs = k // per_lane
-        for i in range(n_graphs):
-            g, st = lanes[i % S]
-            with torch.cuda.stream(st):
-                g.replay()
-        rem = k - n_graphs * per_lane
-        for i in range(rem):
-            with torch.cuda.stream(lanes[(n_graphs + i) % S][1]):
-                ring[((n_graphs + i) % S)].replay()
+        if k < 3 * per_lane:
+            # a handful of steps: one single-plan graph per step, each on its own lane, instead of serialising them
+            # inside one or two lane graphs (beyond ~12 steps the host cost of the extra launches outweighs that)
+            for i in range(k):
+                with torch.cuda.stream(lanes[i % S][1]):
+                    ring[i % n_plans].replay()
+        else:
+            n_graphs = k // per_lane
+            for i in range(n_graphs):
+                g, st = lanes[i % S]
+                with torch.cuda.stream(st):
+                    g.replay()
+            rem = k - n_graphs * per_lane
+            for i in range(rem):
+                with torch.cuda.stream(lanes[(n_graphs + i) % S][1]):
+                    ring[((n_graphs + i) % S)].replay()
         for _, st in lanes:
             ev = torch.cuda.Event()
             ev.record(st)
