@@ -1,29 +1,36 @@
 #!/usr/bin/env python
 """Benchmark of the MD_RDM depth-map fusion path (BASELINE.json metric: fused depth maps/s).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config fusion|train|kitti]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-ours      : BASELINE.json configs[1] - standalone fusion path on B200, batch 16, scales 8/16/32:
-            inputs (ordinary map + raw pair matrices: 1 f32 64x64 + 5 f64 256x64 per image)
-            resident in HBM, one step = quantize + ALS + decompose + weighted reconstruction of one
-            batch (5 kernel launches replayed from a CUDA graph).  Steps rotate over a ring of
-            resident batches larger than L2 and over 32 streams (batches in flight).
-            e2e = the public host API (FusionPlan.run_pinned: decoder maps in pinned host memory
-            -> fused 128x128 log-depth maps in pinned host memory), H2D and D2H copies inside
-            the timed region, pair build fused in front.
-reference : the reference's own CPU algorithm for the same path (oracle/literal.py: the
-            loop-for-loop restatement of the reference, which is Python and cannot travel to
-            the GPU box), one image per step, all host threads.
-A step lasts ~11 us, so the 32-lane pipeline needs a few hundred steps to fill: K = 2000 by default (22 ms);
-with K = 37 the same code reports ~0.8 M maps/s, with K = 5 ~0.3 M (start-up and host launch time dominate).
-One JSON line on stdout (rank 0).  Weak scaling: every rank runs K steps on its own batches;
-no collective on the data path (torch.distributed is used for the barrier and the max only).
+--config fusion (default) : BASELINE.json configs[1] (and configs[3] at N > 1) - standalone fusion path, batch 16,
+            scales 8/16/32.  One CALL = one reference batch of 16 images = one ALS arg-min group
+            (network/computations.py:172-173): inputs (ordinary 8x8 map + raw pair matrices: 1 f32 64x64 + 5 f64
+            256x64 per image) resident in HBM -> quantize + ALS + decompose + weighted reconstruction.
+            One STEP = one pass over the ring of resident batches: every lane (stream) replays its CUDA graph
+            once = `ring` calls = ring x 16 images (128 calls = 2048 images by default).  The ring of inputs is
+            larger than L2; lanes never join inside the timed region, so `--steps 20` times ~25 ms of steady state.
+            e2e = the public host API (FusionPlan.submit_pinned: decoder maps in pinned host memory -> fused
+            128x128 f64 log-depth maps in pinned host memory), H2D and D2H copies inside the timed region, the
+            same number of calls per step.
+--config train  : BASELINE configs[2] - full training step at batch 16: ground-truth preparation (226->128 bicubic,
+            mask, gm-normalise, decomposition n=7), fusion forward, the module's losses (MSE on the recombined
+            map + per-scale component loss + Ordinal_Loss on a synthetic DORN head), backward to `Weights`.
+--config kitti  : BASELINE configs[4] - KITTI-shaped stress: 4 square tiles per image, 16 images = 64
+            tiles per call, one arg-min group per call.
+--impl reference: the reference's own CPU algorithm for the same path and config (oracle/literal.py: the
+            loop-for-loop restatement of the reference, which is Python and cannot travel to the GPU box), one
+            call of 16 images per step, all host threads.
+One JSON line on stdout (rank 0); the long tables go to gpurun_out/bench_detail.json and stderr.  Weak scaling:
+every rank runs K steps on its own batches; no collective on the data path (torch.distributed is used for the
+barrier and the max only).
 """
 from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import sys
 import threading
@@ -39,13 +46,26 @@ METRIC = "fused_depth_maps_per_sec"
 UNIT = "maps/s"
 BATCH = 16
 SCALES = (8, 16, 32)
-LAUNCHES_PER_STEP = 5   # sparsify, compact-page ALS, dense ALS (8x8 maps), select, fused tail
+
+
+def shared_config(kind: str = "fusion"):
+    """The `config` object both arms print (identical: the driver compares the two lines)."""
+    sc = "/".join(map(str, SCALES))
+    if kind == "train":
+        wl = (f"BASELINE configs[2]: full training step, batch {BATCH}, scales {sc}: GT preparation + decomposition n=7, fusion "
+              "forward, MSE + per-scale component loss + Ordinal_Loss, backward to Weights")
+    elif kind == "kitti":
+        wl = (f"BASELINE configs[4]: KITTI-shaped fusion stress, {BATCH} images = {4 * BATCH} square tiles per call (one arg-min "
+              f"group), scales {sc}; value counts 128x128 tile maps")
+    else:
+        wl = (f"BASELINE configs[1]: standalone fusion path, batch {BATCH} (one call = one arg-min group of {BATCH} images), scales {sc}: "
+              "quantize + ALS + decompose + weighted reconstruction -> 128x128 f64 log-depth")
+    return {"workload": wl, "batch": BATCH, "scales": list(SCALES)}
 
 
 # ----------------------------------------------------------------------------- workload arithmetic
 def algorithmic_bytes(scales=SCALES):
     """Per-image stage contract bytes (SURVEY.md 8d / DESIGN.md 'Algorithmic bytes')."""
-    import math
     E = {s: (64 * 64 if s == 8 else (s // 16) ** 2 * 256 * 64) for s in scales}
     raw = {s: E[s] * (4 if s == 8 else 8) for s in scales}
     Rq = {s: 4 * E[s] for s in scales}
@@ -61,6 +81,7 @@ def algorithmic_bytes(scales=SCALES):
         "als": sum(Rq[s] + mp[s] for s in scales),
         "decompose": sum(mp[s] for s in scales) + 512 + sum(comp[s] for s in scales) + comp_d1,
         "reconstruct": sum(comp[s] for s in scales) + comp_d1 + yhat + 131072,
+        "gt_decompose": 131072 + 174760,
     }
     out["path"] = out["quantize"] + out["als"] + out["decompose"] + out["reconstruct"]
     # per-kernel split of the same contract bytes: the sparsify kernel does the quantize stage of the page
@@ -70,7 +91,6 @@ def algorithmic_bytes(scales=SCALES):
     out["sparsify_kernel"] = sum(raw[s] + Rq[s] + bins[s] for s in pg)
     out["als_sparse_kernel"] = sum(Rq[s] + mp[s] for s in pg)
     out["als_dense_kernel"] = sum(raw[s] + 2 * Rq[s] + bins[s] + mp[s] for s in scales if s == 8)
-    out["als_iterate_kernel"] = out["quantize"] + sum(Rq[s] for s in scales)   # the three iterate-phase kernels together
     out["als_select_kernel"] = sum(mp[s] for s in scales)
     out["tail_kernel"] = out["decompose"] + out["reconstruct"]
     return out
@@ -79,7 +99,6 @@ def algorithmic_bytes(scales=SCALES):
 def synthetic_batch(B: int, scales, seed: int):
     """SURVEY 8d synthetic decoder outputs: x_d1 = randint(1,90) DORN counts, relative maps
     exp(0.3 randn), weights abs(randn(K,1)) as network/RDM_Net.py:449-465 initialises them."""
-    import math
     g = torch.Generator().manual_seed(seed)
     x_d1 = torch.randint(1, 90, (B, 1, 8, 8), generator=g, dtype=torch.int64)
     rel = [torch.exp(0.3 * torch.randn(B, 1, s, s, generator=g)) for s in scales]
@@ -89,6 +108,20 @@ def synthetic_batch(B: int, scales, seed: int):
             K[k] += 1
     weights = [torch.abs(torch.randn(k, 1, generator=g)) for k in K if k > 0]
     return x_d1, rel, weights
+
+
+def synthetic_gt(B: int, seed: int, side: int = 226):
+    """Ground truth of the training-step config: a smooth depth field in 0.5..10 (an 8x8 random field, bilinear
+    to side x side) with 5 % invalid (zero) pixels, f64.  SURVEY 8d's white-noise GT (0.5 + 9.5 rand per pixel)
+    makes the reference's own bicubic 128->8 resize undershoot below zero, so its SID label and the d0 component
+    target are NaN (tests/golden/README.md); the smooth field keeps every loss term finite.  Timing does not
+    depend on the values."""
+    g = torch.Generator().manual_seed(seed)
+    base = 0.5 + 9.5 * torch.rand(B, 1, 8, 8, generator=g, dtype=torch.float64)
+    y = torch.nn.functional.interpolate(base, size=(side, side), mode="bilinear", align_corners=False)
+    y = y * (torch.rand(B, 1, side, side, generator=g) > 0.05)
+    logits = torch.randn(B, 180, 8, 8, generator=g)
+    return y, logits
 
 
 def batch_seed(rank: int, batch_idx: int) -> int:
@@ -114,6 +147,50 @@ def dist_barrier():
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized():
         dist.barrier()
+
+
+def init_dist(dev, world):
+    if world <= 1:
+        return
+    import torch.distributed as dist
+    # NCCL prints its version banner to STDOUT when the first communicator is created: keep stdout for the
+    # one JSON line by pointing fd 1 at stderr until the communicator exists
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        dist.init_process_group("nccl", device_id=dev)
+        dist.all_reduce(torch.zeros(1, device=dev))
+        torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+
+
+def finish_dist(world):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def hbm_peak():
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        return float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def write_detail(name: str, obj) -> None:
+    """Long tables: stderr + gpurun_out/<name> (scratch), so that the JSON line stays short."""
+    try:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", name), "w") as f:
+            json.dump(obj, f, indent=1)
+    except OSError:
+        pass
+    print(f"[bench detail] {name}: " + json.dumps(obj), file=sys.stderr, flush=True)
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -169,16 +246,16 @@ class ClockSampler:
         return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
 
 
-# ----------------------------------------------------------------------------- ours
-def build_ring(dev, rank, n_plans, source):
-    """`n_plans` resident batches (each its own buffers + CUDA graph), inputs generated per SURVEY 8d."""
+# ----------------------------------------------------------------------------- ours: fusion / kitti
+def build_ring(dev, rank, n_plans, source, call_images, want_bins=True):
+    """`n_plans` resident calls (each its own buffers + CUDA graph), inputs generated per SURVEY 8d."""
     import md_rdm_b200.ops  # noqa: F401
     from md_rdm_b200.fusion import FusionPlan
     R = torch.ops.rdm
     ring = []
     for b in range(n_plans):
-        x_d1, rel, weights = synthetic_batch(BATCH, SCALES, seed=batch_seed(rank, b))
-        plan = FusionPlan(BATCH, SCALES, source, device=dev, want_bins=True)
+        x_d1, rel, weights = synthetic_batch(call_images, SCALES, seed=batch_seed(rank, b))
+        plan = FusionPlan(call_images, SCALES, source, device=dev, want_bins=want_bins)
         rel_d = [r.to(dev) for r in rel]
         if source == "raw":   # raw pair matrices derived from the maps with the pair-build kernels (not timed)
             srcs = [R.pair_v1(r) if r.shape[2] == 8 else R.pair_id(r)[0] for r in rel_d]
@@ -192,27 +269,18 @@ def build_ring(dev, rank, n_plans, source):
     return ring
 
 
-def timed_steps(ring, streams, steps, fn):
-    """Run `steps` steps, step i on stream i % S with plan i % len(ring); device time by CUDA events
-    recorded on the current stream around fork/join of the side streams."""
+def timed_region(fn):
+    """Device time (CUDA events on the current stream, which forks to and joins the lanes inside fn) and wall
+    time of fn(), with a synchronize on both sides."""
     cur = torch.cuda.current_stream()
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     start.record(cur)
-    for s in streams:
-        s.wait_event(start)
-    for i in range(steps):
-        with torch.cuda.stream(streams[i % len(streams)]):
-            fn(ring[i % len(ring)])
-    for s in streams:
-        ev = torch.cuda.Event()
-        ev.record(s)
-        cur.wait_event(ev)
+    fn()
     end.record(cur)
     torch.cuda.synchronize()
-    wall_ms = (time.perf_counter() - t0) * 1e3
-    return start.elapsed_time(end), wall_ms
+    return start.elapsed_time(end), (time.perf_counter() - t0) * 1e3
 
 
 def time_serial(fns, reps):
@@ -305,238 +373,355 @@ def pcie_d2h_peak(dev):
     return out
 
 
-def cpu_baseline_port(images: int):
-    """The reference's CPU algorithm (literal port) on a bounded sample of the same workload."""
+def cpu_baseline_port(calls: int):
+    """The reference's CPU algorithm (literal port) on a bounded sample of the same workload: `calls` calls of
+    one batch of 16 images (the arg-min is batch-wide, so a call is the unit of work)."""
     from oracle import fusion_ref as fr
     from oracle import literal as lit
     books = fr.load_codebooks()
-    x_d1, rel, weights = fr.synthetic_batch(images, SCALES, seed=batch_seed(0, 0))
+    batches = [fr.synthetic_batch(BATCH, SCALES, seed=batch_seed(0, i)) for i in range(calls)]
     t0 = time.perf_counter()
-    lit.fusion_forward_literal(x_d1, rel, weights, books)
+    for b in batches:
+        lit.fusion_forward_literal(*b, books)
     dt = time.perf_counter() - t0
     # vectorised restatement (same arithmetic, Python loops removed): the "best-effort CPU" figure
-    x16 = fr.synthetic_batch(BATCH, SCALES, seed=batch_seed(0, 0))
-    fr.fusion_forward(*x16, books)
+    fr.fusion_forward(*batches[0], books)
     t1 = time.perf_counter()
     nb = 5
     for _ in range(nb):
-        fr.fusion_forward(*x16, books)
+        fr.fusion_forward(*batches[0], books)
     dv = time.perf_counter() - t1
-    return images / dt, (nb * BATCH) / dv, dt
+    return calls * BATCH / dt, (nb * BATCH) / dv, dt
 
 
-def run_ours(args):
+def run_fusion(args, kind="fusion"):
     rank, local_rank, world = dist_env()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
-        import torch.distributed as dist
-        # NCCL prints its version banner to STDOUT when the first communicator is created: keep stdout for the
-        # one JSON line by pointing fd 1 at stderr until the communicator exists
-        sys.stdout.flush()
-        saved = os.dup(1)
-        os.dup2(2, 1)
-        try:
-            dist.init_process_group("nccl", device_id=dev)
-            dist.all_reduce(torch.zeros(1, device=dev))
-            torch.cuda.synchronize()
-        finally:
-            sys.stdout.flush()
-            os.dup2(saved, 1)
-            os.close(saved)
+    init_dist(dev, world)
     from md_rdm_b200 import _cabi
     _cabi.load()   # fail loudly before anything is timed
 
-    from md_rdm_b200.fusion import capture_lane, capture_ring
+    from md_rdm_b200.fusion import capture_lane
+    tiles = 4 if kind == "kitti" else 1
+    call_images = BATCH * tiles                 # images (128x128 maps) per call = one arg-min group
     ab = algorithmic_bytes(SCALES)
-    n_plans = max(args.ring // args.streams, 1) * args.streams   # whole plans per lane
-    ring = build_ring(dev, rank, n_plans, "raw")
-    ring_in_bytes = sum(p.h2d_bytes() for p in ring)
-    streams = [torch.cuda.Stream() for _ in range(args.streams)]
-    K, W = args.steps, args.warmup
-    replay = lambda p: p.replay()   # noqa: E731
-    # `streams` independent lanes: lane j owns plans j, j+S, ... of the ring, one stream and one CUDA graph
-    # that runs its plans back to back (3 kernels each).  Lanes are replayed round-robin and never join, so
-    # several batches stay in flight and the host launches K / (ring/S) graphs instead of K.
     S = args.streams
+    ring_calls = max(args.ring // tiles, S)
+    n_plans = max(ring_calls // S, 1) * S       # whole plans per lane
+    source = "raw"
+    ring = build_ring(dev, rank, n_plans, source, call_images)
+    launches_per_call = ring[0].launches_per_run
+    ring_in_bytes = sum(p.h2d_bytes() for p in ring)
+    K, W = args.steps, args.warmup
+    # `S` independent lanes: lane j owns plans j, j+S, ... of the ring, one stream and one CUDA graph that runs
+    # its plans back to back.  A step replays every lane graph once; lanes never join inside the timed region.
     lanes = [capture_lane(ring[j::S]) for j in range(S)]
-    per_lane = n_plans // S
+    images_per_step = n_plans * call_images
 
     def run_steps(k):
-        """Exactly k steps: lane graphs round-robin, then single-plan graphs for the remainder."""
         cur = torch.cuda.current_stream()
         fork = torch.cuda.Event()
         fork.record(cur)
         for _, st in lanes:
             st.wait_event(fork)
-        if k < 3 * per_lane:
-            # a handful of steps: one single-plan graph per step, each on its own lane, instead of serialising them
-            # inside one or two lane graphs (beyond ~12 steps the host cost of the extra launches outweighs that)
-            for i in range(k):
-                with torch.cuda.stream(lanes[i % S][1]):
-                    ring[i % n_plans].replay()
-        else:
-            n_graphs = k // per_lane
-            for i in range(n_graphs):
-                g, st = lanes[i % S]
+        for _ in range(k):
+            for g, st in lanes:
                 with torch.cuda.stream(st):
                     g.replay()
-            rem = k - n_graphs * per_lane
-            for i in range(rem):
-                with torch.cuda.stream(lanes[(n_graphs + i) % S][1]):
-                    ring[((n_graphs + i) % S)].replay()
         for _, st in lanes:
             ev = torch.cuda.Event()
             ev.record(st)
             cur.wait_event(ev)
 
-    def timed(k, fn):
-        cur = torch.cuda.current_stream()
-        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        start.record(cur)
-        fn(k)
-        end.record(cur)
-        torch.cuda.synchronize()
-        return start.elapsed_time(end), (time.perf_counter() - t0) * 1e3
-
     with ClockSampler(local_rank) as clk:
-        # warm-up: at least W steps, and long enough for NVML to see the clocks under load
-        timed(max(W, 3), run_steps)
+        # warm-up: W steps, and long enough for NVML to see the clocks under load
+        timed_region(lambda: run_steps(W))
         t_end = time.perf_counter() + 0.4
         while time.perf_counter() < t_end:
-            timed(10 * n_plans, run_steps)
+            timed_region(lambda: run_steps(5))
         dist_barrier()
-        dev_ms, wall_ms = timed(K, run_steps)
+        dev_ms, wall_ms = timed_region(lambda: run_steps(K))
         dist_barrier()
         dev_ms = dist_max(max(dev_ms, wall_ms), dev)
 
-        # single-stream latency of one step, and per-kernel launch durations (one stream, back to back)
-        lat_ms, _ = timed_steps(ring, streams[:1], max(K, 50), replay)
-        lat_ms /= max(K, 50)
-        reps = max(K, 100)
-        t_iter = time_serial([(lambda p=p: p.run_als_phase(1)) for p in ring], reps)
-        t_spf = time_serial([(lambda p=p: p.run_als_phase(4)) for p in ring], reps)
-        t_sps = time_serial([(lambda p=p: p.run_als_phase(8)) for p in ring], reps)
-        t_dns = time_serial([(lambda p=p: p.run_als_phase(16)) for p in ring], reps)
-        t_sel = time_serial([(lambda p=p: p.run_als_phase(2)) for p in ring], reps)
-        t_tail = time_serial([(lambda p=p: p.run_tail()) for p in ring], reps)
+        # single-stream latency of one call, and per-kernel launch durations (one stream, back to back)
+        reps = 2 * n_plans
+        lat_s = time_serial([(lambda p=p: p.run()) for p in ring], reps)
+        kernel_s = {name: time_serial([(lambda p=p, m=mask: p.run_als_phase(m)) for p in ring], reps)
+                    for name, mask in ring[0].phase_masks().items()}
+        kernel_s["fuse_tail"] = time_serial([(lambda p=p: p.run_tail()) for p in ring], reps)
 
-        # end-to-end through the public host API: pinned host maps -> pinned host log-depth
-        # One step = one user call FusionPlan.submit_pinned(): a graph of [H2D copy of the packed inputs,
-        # the three kernels, D2H copy of the log-depth maps], calls issued round-robin on the streams
-        # (asynchronous API), one stream synchronisation at the end.
-        # 8 calls in flight are enough to keep the PCIe link busy; a deeper ring only enlarges the set of pinned
-        # result buffers the host has to absorb (2 MB each)
-        e2e_lanes = max(min(args.streams, args.e2e_lanes), 1)
-        e2e_ring = build_ring(dev, rank, e2e_lanes, "map")
+        # the same work as ONE call per 32 batches (n_images = 512, group = 16: 32 arg-min groups per launch): every
+        # launch fills the chip, so the serial per-launch durations are chip-level figures (per-kernel roofline)
+        grouped = None
+        if kind == "fusion" and not args.no_grouped:
+            grouped = grouped_call_table(dev, rank, ab, args)
+
+        # end-to-end through the public host API: pinned host maps -> pinned host log-depth.  One call =
+        # FusionPlan.submit_pinned(): a graph of [H2D copy of the packed inputs, pair build + the path's kernels,
+        # D2H copy of the log-depth maps], calls issued round-robin on `e2e_lanes` streams (asynchronous API),
+        # one stream synchronisation at the end.  A step = the same number of calls as above.
+        e2e_lanes = max(min(S, args.e2e_lanes), 1)
+        e2e_ring = build_ring(dev, rank, e2e_lanes, "map", call_images, want_bins=False)
         for p in e2e_ring:
             hb = p._host_buffers()
             hb["x_d1"].copy_(p.host_inputs[0])
             for s, t in zip(p.scales, p.host_inputs[1]):
                 hb["src"][s].copy_(t)
             p.capture_e2e()
-        e2e_step = lambda p: p.submit_pinned()   # noqa: E731
-        e2e_streams = streams[:len(e2e_ring)]
-        timed_steps(e2e_ring, e2e_streams, max(W, 3), e2e_step)
+        e2e_streams = [torch.cuda.Stream() for _ in range(e2e_lanes)]
+
+        def e2e_steps(k):
+            cur = torch.cuda.current_stream()
+            fork = torch.cuda.Event()
+            fork.record(cur)
+            for st in e2e_streams:
+                st.wait_event(fork)
+            for i in range(k * n_plans):
+                with torch.cuda.stream(e2e_streams[i % e2e_lanes]):
+                    e2e_ring[i % e2e_lanes].submit_pinned()
+            for st in e2e_streams:
+                ev = torch.cuda.Event()
+                ev.record(st)
+                cur.wait_event(ev)
+
+        timed_region(lambda: e2e_steps(max(W, 3)))
         dist_barrier()
-        e_dev_ms, e_wall_ms = timed_steps(e2e_ring, e2e_streams, K, e2e_step)
+        e_dev_ms, e_wall_ms = timed_region(lambda: e2e_steps(K))
         dist_barrier()
         e_ms = dist_max(max(e_dev_ms, e_wall_ms), dev)
-        # the same calls batched: one graph launch per pass over the e2e ring (copies included)
-        e2e_graph = capture_ring(e2e_ring, len(e2e_streams), e2e=True)
-        nb = len(e2e_ring)
-        timed(nb, lambda k: e2e_graph.replay())
-        reps = max(K // nb, 1)
-        eb_dev_ms, eb_wall_ms = timed(K, lambda k: [e2e_graph.replay() for _ in range(reps)])
-        eb_ms = dist_max(max(eb_dev_ms, eb_wall_ms), dev) / (reps * nb) * K
         pcie = pcie_d2h_peak(dev) if rank == 0 else {}
         stage = {}
         if rank == 0 and not args.no_stage_table:
             stage = {"batch_16": stage_kernel_table(dev, 16), "batch_256": stage_kernel_table(dev, 256)}
     clocks = clk.summary()
 
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured)"
-    else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    traffic, traffic_spf = None, None
+    peak, peak_src = hbm_peak()
+    traffic = {}
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
-        tj = json.load(open(tpath))
-        traffic, traffic_spf = tj.get("als_sparse_kernel_dram_bytes_per_launch"), tj.get("als_sparsify_raw_kernel_dram_bytes_per_launch")
-    # dominant kernel by time: the compact-page ALS iterations
-    achieved = ab["als_sparse_kernel"] * BATCH / t_sps / 1e9
-    kernel_s = {"als_sparsify_raw": t_spf, "als_sparse": t_sps, "als_dense": t_dns, "als_select": t_sel, "fuse_tail": t_tail}
-    kernel_b = {"als_sparsify_raw": ab["sparsify_kernel"], "als_sparse": ab["als_sparse_kernel"], "als_dense": ab["als_dense_kernel"],
+        traffic = json.load(open(tpath))
+    kernel_b = {"als_sparsify": ab["sparsify_kernel"], "als_sparse": ab["als_sparse_kernel"], "als_dense": ab["als_dense_kernel"],
                 "als_select": ab["als_select_kernel"], "fuse_tail": ab["tail_kernel"]}
+    # dominant kernel by time: the compact-page ALS iterations
+    dom = max((k for k in kernel_s if k in kernel_b), key=lambda k: kernel_s[k])
+    total_images = world * K * images_per_step
+    path_gbs = ab["path"] * images_per_step * K / (dev_ms * 1e-3) / 1e9
+    roof = {"bound": "hbm", "unit": "GB/s", "peak": peak, "peak_source": peak_src, "kernel": ring[0].kernel_names().get(dom, dom)}
+    if grouped and dom in grouped["kernel_us"]:
+        # chip-level figure: the kernel timed alone while it processes 32 batches per launch
+        t_dom = grouped["kernel_us"][dom] * 1e-6
+        nb = grouped["batches_per_call"]
+        roof.update({"achieved": kernel_b[dom] * BATCH * nb / t_dom / 1e9, "algorithmic_bytes_per_launch": kernel_b[dom] * BATCH * nb,
+                     "launch_seconds": t_dom, "launch": f"{nb} batches of {BATCH} per launch (n_images {BATCH * nb}, group {BATCH}), timed alone",
+                     "traffic": traffic.get(f"{dom}_grouped_dram_bytes_per_launch")})
+    else:
+        t_dom = kernel_s[dom]
+        roof.update({"achieved": kernel_b[dom] * call_images / t_dom / 1e9, "algorithmic_bytes_per_launch": kernel_b[dom] * call_images,
+                     "launch_seconds": t_dom, "launch": f"one call ({call_images} images) per launch, timed alone",
+                     "traffic": traffic.get(f"{dom}_dram_bytes_per_launch")})
+    roof["frac"] = roof["achieved"] / peak
+    roof["single_call_launch"] = {"achieved": kernel_b[dom] * call_images / kernel_s[dom] / 1e9,
+                                  "frac": kernel_b[dom] * call_images / kernel_s[dom] / 1e9 / peak, "launch_seconds": kernel_s[dom]}
+    roof["path_at_value"] = {"achieved": path_gbs, "frac": path_gbs / peak,
+                             "note": "whole path (quantize + ALS + decompose + reconstruct contract bytes, SURVEY 8d) over the measured step time"}
+    sp = "als_sparsify"
+    if sp in kernel_s:
+        t_sp = (grouped["kernel_us"][sp] * 1e-6 / grouped["batches_per_call"]) if grouped and sp in grouped["kernel_us"] else kernel_s[sp] / tiles
+        roof["streaming_kernel"] = {"kernel": ring[0].kernel_names().get(sp, sp), "achieved": kernel_b[sp] * BATCH / t_sp / 1e9,
+                                    "frac": kernel_b[sp] * BATCH / t_sp / 1e9 / peak, "seconds_per_batch": t_sp,
+                                    "traffic": traffic.get("als_sparsify_grouped_dram_bytes_per_launch")}
 
     out = {
-        "metric": METRIC, "value": world * K * BATCH / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "metric": METRIC, "value": total_images / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32+f64", "data": "synthetic",
-        "config": {
-            "workload": f"BASELINE configs[1]: standalone fusion path, batch 16, scales {'/'.join(map(str, SCALES))}; inputs = ordinary 8x8 "
-                        f"map + raw pair matrices (1 f32 64x64 + {sum((s // 16) ** 2 for s in SCALES if s > 8)} f64 256x64 per image) resident "
-                        "in HBM; quantize + ALS + decompose + weighted reconstruction -> bins, relative maps, y_hat, 128x128 f64 log-depth",
-            "batch": BATCH, "scales": list(SCALES), "images_per_step_per_gpu": BATCH,
-            "dtype_detail": "f32: 8x8 pair ratios + Lloyd compare, ALS, y_hat; f64: page pair ratios + Lloyd compare, decomposition, logs, recombination",
-            "l2_policy": f"inputs larger than L2: ring of {n_plans} resident batches = {ring_in_bytes / 1e6:.0f} MB of inputs (L2 126 MB)",
-            "batches_in_flight": args.streams,
-            "cuda_graph": f"{args.streams} lanes (streams), one graph launch per {n_plans // args.streams} steps of a lane, {LAUNCHES_PER_STEP} kernels per step",
-            "launches_per_step": LAUNCHES_PER_STEP,
-            "single_stream_ms_per_step": lat_ms,
-            "algorithmic_bytes_per_image": ab,
-            "kernel_ms": {**{k: v * 1e3 for k, v in kernel_s.items()}, "als_iterate_phase": t_iter * 1e3},
-            "kernel_gbs": {k: kernel_b[k] * BATCH / v / 1e9 for k, v in kernel_s.items()},
-            "kernel_note": "serial launch durations on one stream (CUDA-graph timed) and algorithmic GB/s by the SURVEY 8d contract bytes; "
-                           "als_iterate_phase = sparsify + compact-page ALS + dense ALS back to back",
-            "path_gbs_at_value": ab["path"] * BATCH * K / (dev_ms * 1e-3) / 1e9,
-            "stage_kernels": stage,
-            "stage_kernels_note": "stand-alone drop-in ops, CUDA-graph timed, algorithmic GB/s; at batch 16 the inputs are L2-resident "
-                                  "and the kernels are launch-latency bound, at batch 256 they stream from HBM",
-        },
+        "dtype": "f32+f64", "data": "synthetic", "config": shared_config(kind),
+        "step": {"calls_per_step_per_gpu": n_plans, "images_per_step_per_gpu": images_per_step, "lanes": S,
+                 "launches_per_call": launches_per_call, "us_per_call": dev_ms * 1e3 / (K * n_plans),
+                 "single_stream_us_per_call": lat_s * 1e6,
+                 "l2_policy": f"inputs larger than L2: ring of {n_plans} resident calls = {ring_in_bytes / 1e6:.0f} MB (L2 126 MB)"},
+        "kernel_us": {k: round(v * 1e6, 2) for k, v in kernel_s.items()},
+        "kernel_gbs": {k: round(kernel_b[k] * call_images / v / 1e9, 1) for k, v in kernel_s.items() if k in kernel_b},
         "clocks": clocks,
-        "e2e": {"value": world * K * BATCH / (e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": e2e_ring[0].h2d_bytes(),
-                "d2h_bytes_per_step": e2e_ring[0].d2h_bytes(),
-                "calls_in_flight": len(e2e_ring),
-                "api": "FusionPlan.submit_pinned (source='map'): one CUDA-graph launch per call = H2D copy of the pinned decoder maps, "
-                       "pair build + Lloyd + ALS + decompose + reconstruction, D2H copy of the log-depth maps",
-                "d2h_gbs_at_value": world * K * e2e_ring[0].d2h_bytes() / (e_ms * 1e-3) / 1e9 / world,
-                "pcie_measured": pcie,
-                "batched_value": world * K * BATCH / (eb_ms * 1e-3),
-                "batched_note": "same calls with one graph launch per pass over the ring (host launch rate removed)"},
-        "gpu_launches": K * LAUNCHES_PER_STEP,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                     "kernel": "als_sparse_kernel (100 ALS iterations per page on the compact form, one warp per page; issue/latency "
-                               "bound by construction - its inputs are 16 KB per page - see DESIGN.md 4.1)",
-                     "algorithmic_bytes_per_launch": ab["als_sparse_kernel"] * BATCH, "launch_seconds": t_sps, "peak_source": peak_src,
-                     "path_at_value": {"achieved": ab["path"] * BATCH * K / (dev_ms * 1e-3) / 1e9,
-                                       "frac": ab["path"] * BATCH * K / (dev_ms * 1e-3) / 1e9 / peak,
-                                       "note": "whole path (quantize + ALS + decompose + reconstruct contract bytes) over the measured step "
-                                               "time: the figure north_star's 60 % target is stated on"},
-                     "streaming_kernel": {"kernel": "als_sparsify_raw_kernel (reads every raw pair matrix once: structure check + Lloyd)",
-                                          "achieved": ab["sparsify_kernel"] * BATCH / t_spf / 1e9,
-                                          "frac": ab["sparsify_kernel"] * BATCH / t_spf / 1e9 / peak,
-                                          "algorithmic_bytes_per_launch": ab["sparsify_kernel"] * BATCH, "launch_seconds": t_spf,
-                                          "traffic": traffic_spf}},
+        "e2e": {"value": total_images / (e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": e2e_ring[0].h2d_bytes() * n_plans,
+                "d2h_bytes_per_step": e2e_ring[0].d2h_bytes() * n_plans, "calls_per_step": n_plans, "calls_in_flight": e2e_lanes,
+                "api": "FusionPlan.submit_pinned(source='map')",
+                "d2h_gbs_per_gpu": K * n_plans * e2e_ring[0].d2h_bytes() / (e_ms * 1e-3) / 1e9, "pcie_measured": pcie},
+        "gpu_launches": K * n_plans * launches_per_call,
+        "roofline": roof,
     }
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        lit_rate, vec_rate, dt = cpu_baseline_port(args.cpu_images)
+    if grouped:
+        out["grouped_call"] = {k: grouped[k] for k in ("value", "us_per_batch", "batches_per_call", "kernel_us")}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and kind == "fusion":
+        lit_rate, vec_rate, dt = cpu_baseline_port(args.cpu_calls)
         out["cpu_baseline"] = {"value": lit_rate, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                               "sample": f"{args.cpu_images} images (one call) of the batch-16 workload through oracle/literal.py, "
-                                         f"the loop-for-loop restatement of the reference ({dt:.1f} s)",
+                               "sample": f"{args.cpu_calls} calls of {BATCH} images through oracle/literal.py, the loop-for-loop "
+                                         f"restatement of the reference ({dt:.1f} s)",
                                "vectorised_port_value": vec_rate, "host_cpus": os.cpu_count()}
     if rank == 0:
+        write_detail(f"bench_detail_{kind}.json", {"algorithmic_bytes_per_image": ab, "stage_kernels": stage, "grouped_call": grouped,
+                                                    "kernel_seconds": kernel_s, "line": out})
         print(json.dumps(out), flush=True)
-    if world > 1:
-        import torch.distributed as dist
-        dist.barrier()
-        dist.destroy_process_group()
+    finish_dist(world)
+
+
+def grouped_call_table(dev, rank, ab, args):
+    """One CALL for 32 reference batches: FusionPlan(n_images = 512, group = 16) - 32 arg-min groups per launch,
+    bit-identical to 32 separate calls (tests/test_gpu_parity.py::test_plan_overlap_and_multi_group...).  Ring of
+    4 such plans (128 batches, > L2).  Returns throughput on two alternating streams and the per-launch kernel
+    durations (serial, one stream)."""
+    import md_rdm_b200.ops  # noqa: F401
+    from md_rdm_b200.fusion import FusionPlan
+    R = torch.ops.rdm
+    nb, n_ring = args.group_batches, max(args.ring // args.group_batches, 2)
+    plans = []
+    for b in range(n_ring):
+        x_d1, rel, weights = synthetic_batch(BATCH * nb, SCALES, seed=batch_seed(rank, 5000 + b))
+        plan = FusionPlan(BATCH * nb, SCALES, "raw", group=BATCH, device=dev, want_bins=True)
+        rel_d = [r.to(dev) for r in rel]
+        srcs = [R.pair_v1(r) if r.shape[2] == 8 else R.pair_id(r)[0] for r in rel_d]
+        plan.load_inputs(x_d1.to(dev), srcs, torch.cat([w.reshape(-1) for w in weights]).to(dev))
+        plan.capture()
+        plans.append(plan)
+        del srcs, rel_d
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream() for _ in range(2)]
+
+    def passes(k):
+        cur = torch.cuda.current_stream()
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        for st in streams:
+            st.wait_event(fork)
+        for i in range(k * n_ring):
+            with torch.cuda.stream(streams[i % 2]):
+                plans[i % n_ring].replay()
+        for st in streams:
+            ev = torch.cuda.Event()
+            ev.record(st)
+            cur.wait_event(ev)
+
+    timed_region(lambda: passes(3))
+    k = max(args.steps, 10)
+    dms, wms = timed_region(lambda: passes(k))
+    ms = max(dms, wms)
+    reps = 4 * n_ring
+    kernel_us = {name: time_serial([(lambda p=p, m=mask: p.run_als_phase(m)) for p in plans], reps) * 1e6
+                 for name, mask in plans[0].phase_masks().items()}
+    kernel_us["fuse_tail"] = time_serial([(lambda p=p: p.run_tail()) for p in plans], reps) * 1e6
+    out = {"value": k * n_ring * nb * BATCH / (ms * 1e-3), "us_per_batch": ms * 1e3 / (k * n_ring * nb), "batches_per_call": nb,
+           "kernel_us": {k_: round(v, 2) for k_, v in kernel_us.items()},
+           "kernel_us_per_batch": {k_: round(v / nb, 3) for k_, v in kernel_us.items()}}
+    del plans
+    torch.cuda.empty_cache()
+    return out
+
+
+# ----------------------------------------------------------------------------- ours: training step (config 3)
+def run_train(args):
+    rank, local_rank, world = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    init_dist(dev, world)
+    from md_rdm_b200 import _cabi
+    _cabi.load()
+    from md_rdm_b200.training import TrainingStep
+    K, W = args.steps, args.warmup
+    n_ring = 8
+    steps = []
+    for b in range(n_ring):
+        x_d1, rel, weights = synthetic_batch(BATCH, SCALES, seed=batch_seed(rank, 9000 + b))
+        y_raw, logits = synthetic_gt(BATCH, batch_seed(rank, 9000 + b) + 1)
+        ts = TrainingStep(BATCH, SCALES, device=dev)
+        ts.load(rel, y_raw, logits, torch.cat([w.reshape(-1) for w in weights]))
+        steps.append(ts)
+    parity = None
+    if rank == 0 and not args.no_parity_gate:
+        parity = train_parity_gate(steps[0], dev)
+    cur = torch.cuda.current_stream()
+
+    def run(k):
+        for i in range(k):
+            steps[i % n_ring].step()
+
+    with ClockSampler(local_rank) as clk:
+        timed_region(lambda: run(max(W, 3)))
+        t_end = time.perf_counter() + 0.3
+        while time.perf_counter() < t_end:
+            timed_region(lambda: run(8))
+        dist_barrier()
+        dev_ms, wall_ms = timed_region(lambda: run(K))
+        dist_barrier()
+        ms = dist_max(max(dev_ms, wall_ms), dev)
+        # e2e: host tensors (pinned) in, loss value read back on the host every step
+        for ts in steps:
+            ts.pin_host()
+        def run_e2e(k):
+            for i in range(k):
+                steps[i % n_ring].step_from_host()
+        timed_region(lambda: run_e2e(3))
+        dist_barrier()
+        e_dev, e_wall = timed_region(lambda: run_e2e(K))
+        dist_barrier()
+        e_ms = dist_max(max(e_dev, e_wall), dev)
+    del cur
+    clocks = clk.summary()
+    peak, peak_src = hbm_peak()
+    ab = algorithmic_bytes(SCALES)
+    step_bytes = (ab["pair"] + ab["path"] + ab["gt_decompose"]) * BATCH
+    out = {
+        "metric": "training_step_maps_per_sec", "value": world * K * BATCH / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
+        "config": shared_config("train"),
+        "step": {"images_per_step_per_gpu": BATCH, "launches_per_step": steps[0].launches_per_step(),
+                 "what": "DORN head -> x_d1, pair build + Lloyd + ALS (from the decoder maps), fused tail with autograd, GT resize 226->128 + mask "
+                         "+ gm-normalise + decompose n=7, ordinal GT, MSE + component loss + Ordinal_Loss, backward to Weights and the DORN logits"},
+        "clocks": clocks,
+        "e2e": {"value": world * K * BATCH / (e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": steps[0].h2d_bytes(), "d2h_bytes_per_step": steps[0].d2h_bytes(),
+                "api": "TrainingStep.step_from_host: pinned decoder maps + GT + logits in, loss scalar and Weights gradient out"},
+        "gpu_launches": K * steps[0].launches_per_step(),
+        "roofline": {"bound": "hbm", "unit": "GB/s", "peak": peak, "peak_source": peak_src, "achieved": step_bytes * K / (ms * 1e-3) / 1e9,
+                     "frac": step_bytes * K / (ms * 1e-3) / 1e9 / peak, "traffic": None,
+                     "kernel": "whole step (pair + path + GT decompose contract bytes over the step time); the step is launch-latency bound"},
+        "parity_gate": parity,
+    }
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    finish_dist(world)
+
+
+def train_parity_gate(ts, dev):
+    """Loss and Weights gradient of one step against the CPU oracle (torch autograd on oracle/fusion_ref.py)."""
+    from oracle import fusion_ref as fr
+    books = fr.load_codebooks()
+    h = ts.host_copy()
+    decode, ord_ref = fr.dorn_regression(h["logits"])
+    sizes = [k for k in fr.slot_sizes(SCALES) if k > 0]
+    w_ref, off = [], 0
+    for k in sizes:
+        w_ref.append(h["weights"][off:off + k].clone().view(k, 1).requires_grad_(True))
+        off += k
+    fwd = fr.fusion_forward(decode, h["rel"], w_ref, books)
+    loss_ref, mse_ref, fine_ref, final_ref = fr.training_loss(h["y_raw"], fwd["y_hat"])
+    y128 = fr.mask_target(fr.resize(h["y_raw"], 128))
+    ord_loss_ref = fr.ordinal_loss(ord_ref, fr.depth2label_sid(fr.resize(y128, 8)))
+    total_ref = loss_ref + ord_loss_ref
+    total_ref.backward()
+    res = ts.step()
+    torch.cuda.synchronize()
+    g_ref = torch.cat([w.grad.reshape(-1) for w in w_ref])
+    g = ts.weights.grad.detach().cpu()
+    loss_err = abs(float(res["loss"]) - float(total_ref)) / abs(float(total_ref))
+    grad_err = float((g - g_ref).abs().max() / g_ref.abs().max())
+    ok = loss_err <= 1e-5 and grad_err <= 1e-4
+    if not ok:
+        raise SystemExit(f"bench.py --config train: parity gate failed (loss rel err {loss_err:.2e}, grad rel err {grad_err:.2e})")
+    return {"loss_rel_err": loss_err, "weights_grad_rel_err": grad_err, "ok": ok}
 
 
 # ----------------------------------------------------------------------------- reference arm
@@ -549,21 +734,43 @@ def run_reference(args):
     torch.set_num_threads(os.cpu_count() or 1)
     books = fr.load_codebooks()
     K, W = args.steps, args.warmup
-    per_step = 1   # images per step: a bounded sample of the batch-16 workload
+    kind = args.config
+    tiles = 4 if kind == "kitti" else 1
+    per_step = BATCH * tiles   # one call = one arg-min group, as in our arm
     batches = [fr.synthetic_batch(per_step, SCALES, seed=batch_seed(0, i)) for i in range(4)]
+    if kind == "train":
+        y_raw, logits = synthetic_gt(BATCH, batch_seed(0, 9000) + 1)
+
+    def literal_step(b):
+        if kind != "train":
+            return lit.fusion_forward_literal(*b, books)
+        x_d1, rel, weights = b
+        w = [t.clone().requires_grad_(True) for t in weights]
+        decode, ord_ = fr.dorn_regression(logits)
+        filled = [lit.relative_decoder_tail_literal(x, books) for x in rel]
+        rows = [fr.decompose(fr.gm_normalize(decode), 3)] + [fr.decompose(f, int(math.log2(f.shape[2])), relative_map=True) for f in filled]
+        y_hat = fr.make_pred(w, fr.fine_detail_matrices(rows))
+        loss, _, _, _ = fr.training_loss(y_raw, y_hat)
+        y128 = fr.mask_target(fr.resize(y_raw, 128))
+        (loss + fr.ordinal_loss(ord_, fr.depth2label_sid(fr.resize(y128, 8)))).backward()
+        return loss
+
+    def vector_step(b):
+        return fr.fusion_forward(*b, books)
+
     # The literal port (the reference's own loop structure) costs ~0.3-1 s per image.  If K steps of it would
-    # not finish within a few minutes, the vectorised restatement of the same arithmetic is timed instead
-    # and the line says so: the bound on the run time takes precedence.
+    # not finish within the budget, the vectorised restatement of the same arithmetic is timed instead and the
+    # line says so: the bound on the run time takes precedence.
     t0 = time.perf_counter()
-    lit.fusion_forward_literal(*batches[0], books)
+    literal_step(batches[0])
     t_lit = time.perf_counter() - t0
-    use_literal = (K + W) * t_lit <= args.ref_budget_s
+    use_literal = (K + W - 1) * t_lit <= args.ref_budget_s or kind == "train"
     if use_literal:
-        step = lambda b: lit.fusion_forward_literal(*b, books)   # noqa: E731
-        what = "oracle/literal.py (loop-for-loop port of the reference)"
+        step, what = literal_step, "oracle/literal.py (loop-for-loop port of the reference)"
+        W = max(W - 1, 0)   # the probe call above was the first warm-up step
     else:
-        step = lambda b: fr.fusion_forward(*b, books)            # noqa: E731
-        what = (f"oracle/fusion_ref.py (vectorised port: {K + W} steps of the literal port at {t_lit:.2f} s each "
+        step = vector_step
+        what = (f"oracle/fusion_ref.py (vectorised port: {K + W} steps of the literal port at {t_lit:.1f} s each "
                 f"would exceed the {args.ref_budget_s:.0f} s budget)")
     for i in range(W):
         step(batches[i % 4])
@@ -572,14 +779,12 @@ def run_reference(args):
         step(batches[i % 4])
     dt = time.perf_counter() - t0
     val = K * per_step / dt
-    sample = f"{per_step} image per step of the batch-16 scales-8/16/32 workload, {what}"
+    sample = f"one call of {per_step} images per step ({K} steps), {what}"
     out = {
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
-        "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32+f64", "data": "synthetic",
-        "config": {"workload": "BASELINE configs[1] on the host CPU: decoder maps -> pair build + Lloyd + ALS + decompose + weighted "
-                               "reconstruction, reference algorithm", "batch": per_step, "scales": list(SCALES),
-                   "literal_port_s_per_image": t_lit},
+        "impl": "reference", "metric": METRIC if kind != "train" else "training_step_maps_per_sec", "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": K, "warmup": args.warmup, "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32+f64", "data": "synthetic", "config": shared_config(kind),
+        "step": {"calls_per_step_per_gpu": 1, "images_per_step_per_gpu": per_step, "literal_port_s_per_call": t_lit},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -593,26 +798,32 @@ def main():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--streams", type=int, default=32, help="batches in flight (CUDA stream branches)")
+    ap.add_argument("--config", default="fusion", choices=["fusion", "train", "kitti"])
+    ap.add_argument("--streams", type=int, default=32, help="lanes = calls in flight (CUDA streams)")
     ap.add_argument("--e2e-lanes", type=int, default=8, help="host calls in flight in the e2e measurement")
-    ap.add_argument("--ring", type=int, default=128, help="resident input batches (ring > L2)")
-    ap.add_argument("--cpu-images", type=int, default=48)
+    ap.add_argument("--ring", type=int, default=128, help="resident input batches (ring > L2) = calls per step")
+    ap.add_argument("--group-batches", type=int, default=32, help="batches per call of the grouped-call table")
+    ap.add_argument("--cpu-calls", type=int, default=3, help="calls of 16 images timed for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stage-table", action="store_true")
+    ap.add_argument("--no-grouped", action="store_true")
+    ap.add_argument("--no-parity-gate", action="store_true")
     ap.add_argument("--scales", default="8,16,32", help="relative decoder scales (default: BASELINE configs[1]); "
                     "8,16,32,64 is the configuration network/RDM_Net.py:96-97 names")
-    ap.add_argument("--ref-budget-s", type=float, default=200.0, help="--impl reference: wall-clock budget for the literal port")
+    ap.add_argument("--ref-budget-s", type=float, default=300.0, help="--impl reference: wall-clock budget for the literal port")
     args = ap.parse_args()
     global SCALES
     SCALES = tuple(int(v) for v in args.scales.split(","))
+    args.steps = 20 if args.steps is None else args.steps
     if args.impl == "reference":
-        args.steps = 20 if args.steps is None else args.steps
         args.warmup = 3 if args.warmup is None else max(args.warmup, 1)
         run_reference(args)
     else:
-        args.steps = 2000 if args.steps is None else args.steps
-        args.warmup = 20 if args.warmup is None else max(args.warmup, 3)
-        run_ours(args)
+        args.warmup = 5 if args.warmup is None else max(args.warmup, 3)
+        if args.config == "train":
+            run_train(args)
+        else:
+            run_fusion(args, args.config)
 
 
 if __name__ == "__main__":

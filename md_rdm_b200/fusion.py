@@ -1,6 +1,7 @@
-"""Batched fast entry point of the fusion path: all relative decoder scales of one batch in
-THREE launches (ALS iterate, ALS select/normalise/re-tile, fused decompose+combine+recombine),
-with every buffer preallocated, optional CUDA-graph replay and a pinned-host end-to-end call.
+"""Batched fast entry point of the fusion path: all relative decoder scales of one batch in a fixed
+number of launches (`FusionPlan.launches_per_run`: compact page form, ALS on the compact pages, dense ALS
+of the 8x8 maps, arg-min/normalise/re-tile, fused decompose+combine+recombine), with every buffer
+preallocated, optional CUDA-graph replay and a pinned-host end-to-end call.
 
 This sits beside the drop-in names (md_rdm_b200.computations / rdm_net) and computes exactly
 what RN:103-133 + network/module.py:132 compute for decoder 1 plus relative decoders at
@@ -14,6 +15,9 @@ source = "raw": inputs are materialised raw pair matrices (f32 64x64 for scale 8
 """
 from __future__ import annotations
 
+import contextlib
+import weakref
+from collections import OrderedDict
 from ctypes import c_void_p
 from typing import Dict, List, Optional, Sequence
 
@@ -125,7 +129,22 @@ class FusionPlan:
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self._graph_e2e: Optional[torch.cuda.CUDAGraph] = None
         self._pinned = None
-        self.launches_per_run = 3   # als_kernel<0>, als_kernel<1>, fuse_tail_kernel
+        has_pages, has_8 = any(s > 8 for s in self.scales), 8 in self.scales
+        # sparsify + compact-page ALS (page scales), dense ALS (8x8 maps and the page fallback), select, fused tail
+        self.launches_per_run = (2 if has_pages else 0) + (2 if self.scales else 0) + 1
+
+    @staticmethod
+    def phase_masks() -> Dict[str, int]:
+        """The ALS launches by `rdm_als_fused_phases` mask bit (bench.py times them one by one)."""
+        return {"als_sparsify": 4, "als_sparse": 8, "als_dense": 16, "als_select": 2}
+
+    @staticmethod
+    def kernel_names() -> Dict[str, str]:
+        return {"als_sparsify": "als_sparsify_raw_kernel / als_sparsify_map_kernel (structure check + Lloyd: reads every raw pair matrix once)",
+                "als_sparse": "als_sparse_kernel (100 ALS iterations per page on the compact form, one warp per page)",
+                "als_dense": "als_kernel<0> (dense ALS: the 8x8 maps and any page matrix without pair structure)",
+                "als_select": "als_kernel<1> (batch-wide arg-min, normalise, re-tile)",
+                "fuse_tail": "fuse_tail_kernel (decompose + combine + recombine)"}
 
     def _views(self, buf: torch.Tensor):
         """Typed views (x_d1 and one source per scale) of a packed input byte buffer."""
@@ -143,7 +162,25 @@ class FusionPlan:
         (batch 16, scales 8/16/32): one step alone 103 -> 77 us, but with 16 batches in flight 7 % FEWER maps/s
         (the join costs more than the idle SMs it fills), so it is off unless the plan was built with
         `overlap=True` (latency-bound callers)."""
-        overlap = self.overlap if overlap is None else overlap
+        with self._guard():
+            self._run_als(self.overlap if overlap is None else overlap)
+            self._run_tail()
+        return self.depth
+
+    def _guard(self):
+        """Make the plan's device current for the launches (a plan built for cuda:1 may be run while cuda:0 is
+        current); free when it already is."""
+        if torch.cuda.current_device() == (self.device.index if self.device.index is not None else torch.cuda.current_device()):
+            return contextlib.nullcontext()
+        return torch.cuda.device(self.device)
+
+    def run_als(self, overlap: Optional[bool] = None) -> Dict[int, torch.Tensor]:
+        """Only the ALS launches (pair build / Lloyd / ALS / arg-min / re-tile): fills and returns `self.rel`."""
+        with self._guard():
+            self._run_als(self.overlap if overlap is None else overlap)
+        return self.rel
+
+    def _run_als(self, overlap: bool) -> None:
         cur = torch.cuda.current_stream(self.device)
         st = c_void_p(cur.cuda_stream)
         lib = self.lib
@@ -161,22 +198,23 @@ class FusionPlan:
                 check(lib.rdm_als_fused_phases(descs, n, self.N, self.group, 2, st), "rdm_als_fused_phases")
             else:
                 check(lib.rdm_als_fused(descs, n, self.N, self.group, st), "rdm_als_fused")
-        check(lib.rdm_fuse_tail(c_void_p(self.x_d1.data_ptr()), self._rel_ptrs, self._sides, len(self.scales),
-                                c_void_p(self.weights.data_ptr()), self.N, c_void_p(self.yhat.data_ptr()),
-                                c_void_p(self.depth.data_ptr()), self._a_ptrs, st), "rdm_fuse_tail")
-        return self.depth
 
     def run_als_phase(self, phase_mask: int) -> None:
         """Only the ALS launches selected by phase_mask (1 = iterate, 2 = select): used by bench.py to
         time the dominant kernel alone."""
-        st = c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-        check(self.lib.rdm_als_fused_phases(self._descs, len(self.scales), self.N, self.group, phase_mask, st), "rdm_als_fused_phases")
+        with self._guard():
+            st = c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            check(self.lib.rdm_als_fused_phases(self._descs, len(self.scales), self.N, self.group, phase_mask, st), "rdm_als_fused_phases")
 
-    def run_tail(self) -> None:
+    def _run_tail(self) -> None:
         st = c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         check(self.lib.rdm_fuse_tail(c_void_p(self.x_d1.data_ptr()), self._rel_ptrs, self._sides, len(self.scales),
                                      c_void_p(self.weights.data_ptr()), self.N, c_void_p(self.yhat.data_ptr()),
                                      c_void_p(self.depth.data_ptr()), self._a_ptrs, st), "rdm_fuse_tail")
+
+    def run_tail(self) -> None:
+        with self._guard():
+            self._run_tail()
 
     def capture(self) -> None:
         """Record run() into a CUDA graph (the library does no host sync and no allocation)."""
@@ -228,9 +266,10 @@ class FusionPlan:
 
     def _enqueue_e2e(self) -> None:
         hb = self._host_buffers()
-        self._in_dev.copy_(hb["packed"], non_blocking=True)      # one H2D copy for all inputs
-        self.run()
-        hb["depth"].copy_(self.depth, non_blocking=True)          # D2H of the fused log-depth maps
+        with self._guard():
+            self._in_dev.copy_(hb["packed"], non_blocking=True)      # one H2D copy for all inputs
+            self.run()
+            hb["depth"].copy_(self.depth, non_blocking=True)          # D2H of the fused log-depth maps
 
     def capture_e2e(self) -> None:
         """CUDA graph of the whole host call: H2D copy node, the kernels of run(), D2H copy node."""
@@ -314,22 +353,50 @@ def capture_ring(plans: Sequence[FusionPlan], n_streams: int, e2e: bool = False)
     return g
 
 
-_plans: Dict[tuple, FusionPlan] = {}
+_PLAN_CACHE_MAX = 8
+_plans: "OrderedDict[tuple, tuple]" = OrderedDict()   # key -> (plan, weakref to the caller's Quantization or None)
+
+
+def clear_plans() -> None:
+    """Drop the cached plans of `fuse_maps` (frees their device workspaces)."""
+    _plans.clear()
 
 
 def fuse_maps(x_d1: torch.Tensor, rel_maps: Sequence[torch.Tensor], weights: Sequence[torch.Tensor] | torch.Tensor,
               quant: Optional[Quantization] = None):
     """Functional form: decoder outputs in, (depth (B,1,128,128) f64, y_hat list, filled relative maps) out.
     x_d1 (B,1,8,8) int64 DORN counts, rel_maps[i] (B,1,s_i,s_i) f32; weights: the `Weights.weight_list`
-    (list of (K,1)) or a flat tensor.  One arg-min group = the whole call, like one reference forward."""
+    (list of (K,1)) or a flat tensor.  One arg-min group = the whole call, like one reference forward
+    (RN:103-133 + network/module.py:132).
+
+    Gradients: when autograd is recording and any weight requires grad, the tail goes through
+    `ops.fuse_tail_autograd`, so `depth` and `y_hat` carry gradients to the `Weights` parameters (the only
+    gradients the training loss needs); the relative maps get none (Lloyd severs them).  Otherwise the
+    whole call is the inference plan.  Calls are single-stream: a cached plan owns static input / output buffers
+    (results are cloned before returning), so two threads or streams must not share one (B, scales, device, quant)."""
     B = x_d1.shape[0]
     scales = tuple(int(r.shape[2]) for r in rel_maps)
-    key = (B, scales, str(x_d1.device), id(quant))
-    plan = _plans.get(key)
-    if plan is None:
-        plan = _plans[key] = FusionPlan(B, scales, "map", device=x_d1.device, quant=quant, want_bins=False)
-    if not torch.is_tensor(weights):
-        weights = torch.cat([w.reshape(-1) for w in weights if w.numel()])
-    plan.load_inputs(x_d1, rel_maps, weights.float())
+    key = (B, scales, str(x_d1.device), id(quant) if quant is not None else None)
+    hit = _plans.get(key)
+    if hit is not None and quant is not None and hit[1]() is not quant:
+        hit = None                                   # id() reused by another object after collection: stale codebooks
+    if hit is None:
+        plan = FusionPlan(B, scales, "map", device=x_d1.device, quant=quant, want_bins=False)
+        _plans[key] = (plan, weakref.ref(quant) if quant is not None else None)
+        while len(_plans) > _PLAN_CACHE_MAX:
+            _plans.popitem(last=False)
+    else:
+        plan = hit[0]
+        _plans.move_to_end(key)
+    w_list = [weights] if torch.is_tensor(weights) else [w for w in weights if w.numel()]
+    needs_grad = torch.is_grad_enabled() and any(w.requires_grad for w in w_list)
+    flat = torch.cat([w.reshape(-1) for w in w_list]).float()
+    if needs_grad:
+        from .ops import fuse_tail_autograd, split_yhat as _split
+        plan.load_inputs(x_d1, rel_maps, None)
+        rel = [t.clone() for t in plan.run_als().values()]
+        depth, yhat = fuse_tail_autograd(x_d1.contiguous(), rel, flat)
+        return depth, _split(yhat, plan.kmax), rel
+    plan.load_inputs(x_d1, rel_maps, flat.detach())
     plan.run()
     return plan.depth.clone(), [y.clone() for y in plan.yhat_list()], [plan.rel[s].clone() for s in scales]

@@ -1,0 +1,121 @@
+"""The reference's training step on the fast path (BASELINE config 3).
+
+Mirrors `RelativeDephModule.training_step` + `compute_final_depth` + `compute_ordinal_target` + `normalize`
+(network/module.py:64-97, 119-149, "MOD") for the configuration RN:96-97 names (decoder 1 + relative decoders):
+the CNN is out of scope, so the step starts from what the decoders emit - the DORN logits of decoder 1 and the
+relative decoder maps - and ends with the gradients of `Weights` (and of the DORN logits, through Ordinal_Loss).
+
+    DORN head (RN:313-345)                       rdm::dorn_regression        -> x_d1 (int64 counts), ord (f64)
+    pair build + Lloyd + ALS (RN:358-396)        FusionPlan.run_als          -> filled relative maps
+    decompose + combine + recombine (RN:117-133, MOD:132)   ops.fuse_tail_autograd -> y_hat, final depth (autograd to Weights)
+    GT: resize 226->128 (MOD:68), mask (MOD:74-78), normalise + decompose n=7 (MOD:123), ordinal d0 (MOD:126)
+                                                 rdm::gt_prepare (one launch) or the stand-alone ops
+    losses: MSE(final, y) (MOD:89) + detached per-scale component loss (CP:499-510) + Ordinal_Loss (loss.py:17-59)
+
+Gradients: only `Weights` and the DORN logits receive any; Lloyd severs everything upstream of ALS.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Sequence
+
+import torch
+
+from . import computations as cp
+from . import ops  # noqa: F401
+from .fusion import FusionPlan
+from .loss import depth2label_sid
+from .ops import fuse_tail_autograd, split_yhat
+
+R = torch.ops.rdm
+
+
+class TrainingStep:
+    def __init__(self, batch: int, scales: Sequence[int] = (8, 16, 32), device="cuda", gt_side: int = 226, K: int = 90,
+                 fused_gt: bool = True):
+        self.device = torch.device(device)
+        self.B, self.scales = int(batch), tuple(int(s) for s in scales)
+        self.plan = FusionPlan(self.B, self.scales, "map", device=self.device, want_bins=False)
+        dev, f32, f64 = self.device, torch.float32, torch.float64
+        self.weights = torch.ones((self.plan.n_weights,), dtype=f32, device=dev, requires_grad=True)
+        self.logits = torch.zeros((self.B, 2 * K, 8, 8), dtype=f32, device=dev, requires_grad=True)
+        self.y_raw = torch.ones((self.B, 1, gt_side, gt_side), dtype=f64, device=dev)
+        self.fused_gt = bool(fused_gt) and hasattr(R, "gt_prepare")
+        self._host: Optional[Dict[str, torch.Tensor]] = None
+        self._loss_host: Optional[torch.Tensor] = None
+        self._grad_host: Optional[torch.Tensor] = None
+
+    # ------------------------------------------------------------------ inputs
+    def load(self, rel: Sequence[torch.Tensor], y_raw: torch.Tensor, logits: torch.Tensor, weights: torch.Tensor) -> None:
+        with torch.no_grad():
+            for s, t in zip(self.scales, rel):
+                self.plan.src[s].copy_(t.reshape(self.plan.src[s].shape), non_blocking=True)
+            self.y_raw.copy_(y_raw, non_blocking=True)
+            self.logits.copy_(logits, non_blocking=True)
+            self.weights.copy_(weights.reshape(-1), non_blocking=True)
+        self._host_src = dict(rel=[t.clone() for t in rel], y_raw=y_raw.clone(), logits=logits.clone(), weights=weights.reshape(-1).clone())
+
+    def host_copy(self) -> Dict[str, torch.Tensor]:
+        return self._host_src
+
+    # ------------------------------------------------------------------ ground truth (MOD:68, 74-78, 119-127)
+    def targets(self):
+        """(y masked 128x128 f64, component targets [d0, f1..f7] f64, ordinal target (B,1,8,8) int32)."""
+        if self.fused_gt:
+            y, pyr, ord_t = R.gt_prepare(self.y_raw)
+            return y, ops.unpack_pyramid(pyr, self.B, 128, False), ord_t
+        y = cp.resize(self.y_raw, 128)                                         # MOD:68
+        y = (y * (y > 0)) + ((y <= 0) + 1e-4)                                  # MOD:74-78
+        comps = cp.decompose_depth_map([], R.gm_normalize(y), 7)[::-1]        # MOD:123, MOD:145-149
+        ord_t = depth2label_sid(cp.resize(y, 8))                               # MOD:126 / MOD:134-143 (same tensor)
+        comps[0] = cp.decompose_depth_map([], R.gm_normalize(ord_t.long()), 3)[::-1][0]
+        return y, comps, ord_t
+
+    # ------------------------------------------------------------------ one step
+    def step(self) -> Dict[str, torch.Tensor]:
+        self.weights.grad = None
+        self.logits.grad = None
+        x_d1, ord_ = R.dorn_regression(self.logits)                            # RN:313-345
+        rel = self.plan.run_als()                                              # RN:358-396 for every relative decoder
+        final, yhat = fuse_tail_autograd(x_d1, [rel[s] for s in self.scales], self.weights)   # RN:117-133 + MOD:132
+        y, comps, ord_t = self.targets()
+        # CP:499-510: per-scale MSE, summed through torch.as_tensor => detached (no host sync here)
+        with torch.no_grad():
+            fine = torch.stack([torch.nn.functional.mse_loss(a.double(), b) for a, b in zip(split_yhat(yhat, self.plan.kmax), comps)]).sum()
+        ord_loss = R.ordinal_loss(ord_, ord_t)                                 # loss.py:17-59
+        mse = torch.nn.functional.mse_loss(final, y)                           # MOD:89
+        loss = mse + fine + ord_loss                                           # MOD:90-92
+        loss.backward()
+        return {"loss": loss.detach(), "mse": mse.detach(), "fine": fine, "ord": ord_loss.detach(), "final": final.detach()}
+
+    def launches_per_step(self) -> int:
+        """Kernels of librdm_b200 per step (torch's own elementwise kernels for the losses come on top)."""
+        gt = 1 if self.fused_gt else 7
+        return 2 + (self.plan.launches_per_run - 1) + 1 + gt + 2 + 2 + len(range(self.plan.kmax + 1))
+
+    # ------------------------------------------------------------------ host end to end
+    def pin_host(self) -> None:
+        h = self._host_src
+        self._host = dict(rel=[t.pin_memory() for t in h["rel"]], y_raw=h["y_raw"].pin_memory(), logits=h["logits"].pin_memory())
+        self._loss_host = torch.zeros((), dtype=torch.float64).pin_memory()
+        self._grad_host = torch.zeros((self.plan.n_weights,), dtype=torch.float32).pin_memory()
+
+    def h2d_bytes(self) -> int:
+        h = self._host_src
+        return sum(t.numel() * t.element_size() for t in h["rel"]) + h["y_raw"].numel() * 8 + h["logits"].numel() * 4
+
+    def d2h_bytes(self) -> int:
+        return 8 + 4 * self.plan.n_weights
+
+    def step_from_host(self) -> float:
+        """Pinned host inputs -> device, one step, loss and Weights gradient back on the host (synchronous)."""
+        h = self._host
+        with torch.no_grad():
+            for s, t in zip(self.scales, h["rel"]):
+                self.plan.src[s].copy_(t, non_blocking=True)
+            self.y_raw.copy_(h["y_raw"], non_blocking=True)
+            self.logits.copy_(h["logits"], non_blocking=True)
+        out = self.step()
+        self._loss_host.copy_(out["loss"], non_blocking=True)
+        self._grad_host.copy_(self.weights.grad, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return float(self._loss_host)
