@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define RDM_ABI_VERSION 1
+#define RDM_ABI_VERSION 2
 
 typedef void* rdm_stream_t; /* cudaStream_t */
 
@@ -95,6 +95,23 @@ enum {
                           never written (rows=64: src=(N,64); rows=256: src=(N,side,side)) */
 };
 
+/* rdm_als_scale_t.flags */
+enum {
+  RDM_ALS_DENSE_ONLY = 1,     /* page matrices take the dense kernel even when they have the pair-build structure
+                                 (A/B measurements, tests of the dense path) */
+  RDM_ALS_TRUE_TRANSPOSE = 2, /* "paper-correct" knobs of SURVEY 8f rank 4, OFF by default (see below) */
+  RDM_ALS_TRUE_GM = 4,
+  RDM_ALS_CORRECT_TILING = 8,
+  RDM_ALS_FLAGS_ALL = 15
+};
+/* rdm_als_fused_phases phase_mask bits: the launches of rdm_als_fused, selectable one by one (profiling) */
+enum {
+  RDM_ALS_PHASE_SPARSIFY = 1, /* compact page form: structure check + Lloyd of the page scales (the HBM-streaming kernel) */
+  RDM_ALS_PHASE_PAGES = 2,    /* ALS on the compact pages, one CTA per (group, page), arg-min + normalise + re-tile inside */
+  RDM_ALS_PHASE_DENSE = 4,    /* dense ALS: the 8x8 maps (one cluster per group) and page items without pair structure */
+  RDM_ALS_PHASE_ALL = 7
+};
+
 /* One relative decoder scale.  Matrices are (N, pages, rows, 64), rows = 64 (8x8 map, square
  * case CP:38-85, limit 30) or 256 (16x16 page, CP:95-155, limit 100). */
 typedef struct rdm_als_scale {
@@ -104,7 +121,7 @@ typedef struct rdm_als_scale {
   int32_t pages;            /* P = 1 (side 8, 16) or (side/16)^2 */
   int32_t side;             /* map side s */
   int32_t limit;            /* ALS iterations (rows 64: <= 63, rows 256: <= 127) */
-  int32_t reserved;
+  int32_t flags;            /* RDM_ALS_* bits below; 0 = the reference's behaviour on the fast path */
   const double* thresholds; /* device f64[40]; required for RAW_* and MAP_F32 */
   const double* levels;     /* device f64[41]; required for RAW_* and MAP_F32 */
   uint8_t* bins_out;        /* optional (N,P,rows,64) u8 Lloyd bins */
@@ -112,30 +129,24 @@ typedef struct rdm_als_scale {
   float* pages_out;         /* optional (N,P,rows) f32: per-page ALS maps before re-tiling */
   float* map_out;           /* optional (N,side,side) f32: CP:218-238 `reconstruct` re-tiling
                                (bug-compatible: only pages 0..side/16-1 reach the map) */
-  float* ws;                /* REQUIRED workspace, N * rdm_als_ws_floats(rows, pages, limit) f32:
-                               16-byte aligned; per (image, page) the SSE record, then every
-                               iterate p_1..p_limit [limit][rows] (the arg-min is batch-wide, so
-                               the iterate to emit is only known after all images have finished),
-                               then for 256-row units the 16 KB compact page form and its flags */
+  float* ws;                /* REQUIRED workspace, N * rdm_als_ws_floats(rows, pages, limit) f32, 16-byte
+                               aligned: per (image, page) the 16 KB compact page form and its structure flags
+                               (256-row units) or the unit's SSE record (64-row units).  No iterate is kept:
+                               the batch-wide arg-min is taken inside the iterate kernels. */
   float* record_out;        /* optional (N/group,P,limit+1) f32 rmse record (CP:53-61) */
   int32_t* kstar_out;       /* optional (N/group,P) i32 selected iteration (CP:74, CP:143) */
 } rdm_als_scale_t;
 
-/* Lloyd + rank-1 ALS + geometric normalisation + page re-tiling for `n_scales` scales in a
- * fixed number of launches.  Replaces Ordinal_Layer.forward (non-DORN branch, RN:358-396)
+/* Lloyd + rank-1 ALS + batch-wide arg-min + geometric normalisation + page re-tiling for `n_scales`
+ * scales in three launches (two without page scales).  Replaces Ordinal_Layer.forward (non-DORN branch, RN:358-396)
  * minus the pair build (unless src_kind == RDM_SRC_MAP_F32), i.e. LloydQuantization,
  * cp.quadratic_als, cp.alternating_least_squares, cp.als_step, cp.quick_gm, cp.reconstruct.
  * `scales` is a HOST array.  n_images must be a multiple of group. */
 int rdm_als_fused(const rdm_als_scale_t* scales, int32_t n_scales, int64_t n_images,
                   int32_t group, rdm_stream_t stream);
-/* The same, launching only the selected phases: bit 0 = iterate (Lloyd + ALS iterations, SSE
- * record and every iterate into ws), bit 1 = select (batch-wide arg-min, normalise, re-tile;
- * needs ws from a previous iterate phase).  The iterate phase is three launches that can also be
- * selected one by one (profiling): bit 2 = compact page form (structure check + Lloyd, the
- * HBM-streaming kernel), bit 3 = ALS on the compact pages (one warp per page), bit 4 = dense ALS
- * (8x8 maps and any page matrix without the pair-build structure); bit 0 = bits 2|3|4.  Bits 3 and
- * 4 read the per-page structure flags bit 2 leaves in ws, so they must follow a bit-2 launch on
- * the same inputs (same stream, or ordered by an event); they are independent of each other. */
+/* The same, launching only the phases selected by RDM_ALS_PHASE_* bits.  PAGES and DENSE read the per-page
+ * structure flags SPARSIFY leaves in ws, so they must follow a SPARSIFY launch on the same inputs (same stream, or
+ * ordered by an event); they are independent of each other. */
 int rdm_als_fused_phases(const rdm_als_scale_t* scales, int32_t n_scales, int64_t n_images,
                          int32_t group, int32_t phase_mask, rdm_stream_t stream);
 /* Host-side copy of the geometry tables the compact-page kernels use (RN:266-273 + CP:269-295 window

@@ -13,10 +13,13 @@ from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # RDM_B200_LIB selects an experimental build of the same ABI (tools/als_variants.py); default = the product
 LIB_PATH = os.environ.get("RDM_B200_LIB") or os.path.join(_HERE, "librdm_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # rdm_als_scale_t.src_kind
 SRC_RAW_F64, SRC_RAW_F32, SRC_VAL_F32, SRC_VAL_F64, SRC_MAP_F32 = range(5)
+# rdm_als_scale_t.flags and rdm_als_fused_phases masks (include/rdm_b200.h)
+ALS_DENSE_ONLY, ALS_TRUE_TRANSPOSE, ALS_TRUE_GM, ALS_CORRECT_TILING = 1, 2, 4, 8
+PHASE_SPARSIFY, PHASE_PAGES, PHASE_DENSE, PHASE_ALL = 1, 2, 4, 7
 # rdm_quick_gm / rdm_gm_normalize dtype
 DT_F32, DT_F64, DT_I64 = range(3)
 
@@ -25,7 +28,7 @@ class AlsScale(Structure):
     """rdm_als_scale_t"""
     _fields_ = [
         ("src", c_void_p), ("src_kind", c_int32), ("rows", c_int32), ("pages", c_int32), ("side", c_int32),
-        ("limit", c_int32), ("reserved", c_int32),
+        ("limit", c_int32), ("flags", c_int32),
         ("thresholds", c_void_p), ("levels", c_void_p), ("bins_out", c_void_p), ("values_out", c_void_p),
         ("pages_out", c_void_p), ("map_out", c_void_p), ("ws", c_void_p), ("record_out", c_void_p),
         ("kstar_out", c_void_p),

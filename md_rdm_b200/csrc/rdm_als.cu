@@ -56,9 +56,9 @@ struct AlsScaleDev {
   float* record_out;
   int32_t* kstar_out;
   int32_t kind, rows, pages, side, limit;
-  int32_t cta_begin;   // first blockIdx.x of this scale in the select launch (one CTA per 256-row unit / four 64-row units)
-  int32_t cta_begin0;  // ... and in the dense iterate launch, where a compact-eligible page scale gets only
-  int32_t cta_count0;  //     cta_count0 CTAs that walk its units with that stride (most units need nothing: rdm_als_sparse.cu)
+  int32_t cta_begin;   // first blockIdx.x of this scale
+  int32_t cta_count;   // working CTAs of this scale (64-row: groups x cluster; pages: CTAs that walk the (group, page) items with this stride)
+  int32_t dense_only;  // page scale: every item is iterated here (RDM_ALS_DENSE_ONLY, or a source kind the compact kernel does not take)
 };
 
 struct AlsParams {
@@ -66,7 +66,6 @@ struct AlsParams {
   int64_t n_images;
   int32_t n_scales;
   int32_t group;
-  int32_t sparse;   // page units with the pair-build structure are handled by rdm_als_sparse.cu
 };
 
 struct AlsSmem {
@@ -79,7 +78,9 @@ struct AlsSmem {
   float thr_f[kThrPad];
   float lvl_f[kLvl + 3];
   float inv_f[4][64];                 // 1/d (pair build fused, 64-row units)
-  float rm[256];                      // group rmse record (phase 1)
+  float rm[256];                      // group rmse record (64-row: one row of 64 per unit team)
+  float recu[128];                    // SSE record of the unit just iterated (page fallback)
+  double recg[128];                   // group SSE record accumulated over the units (page fallback)
   int cell_s[kThr];
   int sorted;
   LloydLut lut;                       // bin lookup table in the dtype this CTA compares in
@@ -124,11 +125,6 @@ __device__ __forceinline__ ulonglong2 lds_v2u64(uint32_t a) {
   asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "r"(a) : "memory");
   return v;
 }
-
-#ifndef RDM_EXP
-#define RDM_EXP 0   // timing experiments only (wrong results): 1 no record, 2 no reciprocals, 4 no barriers, 8 no iterate history, 16 no reduce-scatter
-#endif
-constexpr int kExp = RDM_EXP;
 
 // ---- packed f32x2 arithmetic (sm_100a FFMA2)
 using u64 = unsigned long long;
@@ -234,11 +230,6 @@ __device__ __forceinline__ void tile_dot(const float2 (&R)[4][8], uint32_t op, i
     }
     n0 = ffma2(x[k].x, x[k].x, n0);
     n1 = ffma2(x[k].y, x[k].y, n1);
-  }
-  if (kExp & 16) {
-    own = (hsum2(a[0][0], a[0][1]) + hsum2(a[1][0], a[1][1])) + (hsum2(a[2][0], a[2][1]) + hsum2(a[3][0], a[3][1]));
-    nrm = hsum2(n0, n1);
-    return;
   }
   own = reduce_scatter4(hsum2(a[0][0], a[0][1]), hsum2(a[1][0], a[1][1]), hsum2(a[2][0], a[2][1]), hsum2(a[3][0], a[3][1]), cb);
   nrm = group_sum4(hsum2(n0, n1));
@@ -466,12 +457,14 @@ __device__ __forceinline__ void load_unit(float2 (&R)[4][8], const AlsScaleDev& 
 // unit reduces all iterations once, after the loop (two rows per slot: the scratch fits in the dead
 // staging tile).
 constexpr float kDirectFrac = 0.015f;
-// n_iter alternating iterations.  Writes the SSE of iterations 0..n_iter to rec[] and the iterates
-// p_1..p_n_iter to hist[(k-1) * rows + row].  E: (n_iter+1) x (NT/2+1) floats of shared scratch.
-template <int G>
-__device__ __forceinline__ void als_iterate(const float2 (&R)[4][8], AlsSmem& sm, float* __restrict__ E, int unit, int lt, int n_iter,
-                                            float* __restrict__ rec, float* __restrict__ hist) {
-  constexpr bool RECORD = true;
+// n_iter alternating iterations; returns the iterate p_{n_iter} of the row this thread owns (1 for n_iter = 0).
+// RECORD: also writes the SSE of iterations 0..n_iter to rec[] (shared or global); E: (n_iter+1) x (NT/2+1)
+// floats of shared scratch.  Without RECORD the same iterates are computed (bit-identical: the record never
+// feeds back into p or q) and nothing else: this is how the selected iterate p_k* is re-materialised once the
+// group-wide arg-min is known, instead of keeping every iterate.
+template <int G, bool RECORD>
+__device__ __forceinline__ float als_iterate(const float2 (&R)[4][8], AlsSmem& sm, float* __restrict__ E, int unit, int lt, int n_iter,
+                                             float* __restrict__ rec) {
   constexpr int NW = 2 * G;
   constexpr int NT = 64 * G;
   constexpr int EH = NT / 2;                     // two rows (lanes l, l^4) share one slot
@@ -524,14 +517,11 @@ __device__ __forceinline__ void als_iterate(const float2 (&R)[4][8], AlsSmem& sm
     if (!(m.lane & 4)) sts_f32(Es, e0p);
   }
   float p = 1.0f;
-#ifdef RDM_TIMING
-  const long long tl0 = clock64();
-#endif
   for (int k = 1; k <= n_iter; ++k) {
     p = s * invA;                                // (R q) @ inverse(A)
+    if (!RECORD && k == n_iter) break;           // replay: p_k* is all that is wanted
     sts_f32(ps + 4 * m.row_own, p);
-    if (!(kExp & 8)) hist[(k - 1) * NT + m.row_own] = p;   // fire-and-forget: phase 1 picks p_k*
-    if (!(kExp & 4)) unit_barrier(bar_id, NT);   // A: p visible
+    unit_barrier(bar_id, NT);                    // A: p visible
     float ef = 0.f;
     if (RECORD) {   // algebraic residual of this row (f32 pair arithmetic: error-free product and sum); straight-line
                     // code next to the operand loads so that it fills their latency
@@ -547,7 +537,7 @@ __device__ __forceinline__ void als_iterate(const float2 (&R)[4][8], AlsSmem& sm
     if constexpr (G == 4) {
       if (m.lw < 4 && m.lane == 0) sts_f32(ppart + 4 * m.rp, pseg);
     }
-    if (!(kExp & 4)) unit_barrier(bar_id, NT);   // B: q partials (and |p|^2 segments) visible
+    unit_barrier(bar_id, NT);                    // B: q partials (and |p|^2 segments) visible
     float npp = pseg;
     if constexpr (G == 4) {
       const float4 a = lds_v4f32(ppart);
@@ -569,16 +559,16 @@ __device__ __forceinline__ void als_iterate(const float2 (&R)[4][8], AlsSmem& sm
         u0 = lds_f32(qpart + 4 * (64 * unit + m.lane));
         u1 = lds_f32(qpart + 4 * (64 * unit + m.lane + 32));
       }
-      const float invB = (kExp & 2) ? (npp + kLambda) * 1e-4f : rcp_newton(npp + kLambda);
+      const float invB = rcp_newton(npp + kLambda);
       qw ^= qw_flip;
       qop = qw + 64 * m.cb;
       sts_f32(qw + 4 * m.lane, u0 * invB);
       sts_f32(qw + 4 * m.lane + 128, u1 * invB);
       __syncwarp();
       tile_dot(R, qop, m.cb, s, Q);
-      invA = (kExp & 2) ? (Q + kLambda) * 1e-2f : rcp_newton(Q + kLambda);
+      invA = rcp_newton(Q + kLambda);
     }
-    if (RECORD && !(kExp & 1)) {
+    if (RECORD) {
       if (direct) {   // reads only this warp's own data (its rows of p in ps, its old q copy): no barrier needed
         float pj[4];
 #pragma unroll
@@ -589,9 +579,6 @@ __device__ __forceinline__ void als_iterate(const float2 (&R)[4][8], AlsSmem& sm
       if (!(m.lane & 4)) sts_f32(Es + 4 * k * ES, ef);
     }
   }
-#ifdef RDM_TIMING
-  if (RECORD && lt == 0 && unit == 0 && blockIdx.x % 37 == 0) printf("  block %d loop %lld cycles for %d iterations\n", blockIdx.x, clock64() - tl0, n_iter);
-#endif
   if (RECORD) {
     unit_barrier(bar_id, NT);
     for (int k = lt; k <= n_iter; k += NT) {
@@ -607,148 +594,136 @@ __device__ __forceinline__ void als_iterate(const float2 (&R)[4][8], AlsSmem& sm
       rec[k] = (float)((t0 + t1) + (t2 + t3));
     }
   }
+  return p;
 }
 
 // ---------------------------------------------------------------------------------------------
-template <int G, int PHASE>
-__device__ __forceinline__ void als_unit(const AlsParams& P, const AlsScaleDev& sc, AlsSmem& sm, float* tile, float* E,
-                                         int64_t unit_idx, int unit, int lt) {
+// First minimum of a unit team's rmse record rm[0..limit] (CP:74, CP:143) as a parallel min over (value bits,
+// index) keys: rmse values are >= 0, so their bit patterns order like the values and ties resolve to the
+// smaller index (limit <= 127: threads 0..127 hold one key each, teams of 64 threads take two).
+template <int G>
+__device__ __forceinline__ int first_argmin(const float* rm, int limit, AlsSmem& sm, int unit, int lt) {
+  constexpr int NT = 64 * G;
+  const TileMap<G> m(lt);
+  const int bar_id = (G == 4) ? 0 : 1 + unit;
+  unsigned long long key = ~0ull;
+  for (int k = lt; k <= limit; k += NT) {
+    const unsigned long long kk = ((unsigned long long)__float_as_uint(rm[k]) << 32) | (unsigned)k;
+    key = kk < key ? kk : key;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+    key = other < key ? other : key;
+  }
+  unsigned long long* kscr = reinterpret_cast<unsigned long long*>(sm.qpart) + unit * 8;   // 8 keys per unit
+  if (m.lane == 0) kscr[m.lw] = key;
+  unit_barrier(bar_id, NT);
+#pragma unroll
+  for (int w = 0; w < 2 * G; ++w) {
+    const unsigned long long other = kscr[w];
+    key = other < key ? other : key;
+  }
+  unit_barrier(bar_id, NT);   // kscr (= qpart) is reused by the replay
+  return (int)(key & 0xffffffffu);
+}
+
+// quick_gm(p, H) with H = rows: prod_i p_i^(1/H^2)  (CP:76, CP:146, CP:244-255), then p / gm into pages_out and the
+// re-tiled map (CP:218-238).  The exponent is 2^-12 or 2^-16, so p^(1/H^2) = exp(x) with |x| = |ln p| / H^2 < 3e-3:
+// 1 + x + x^2/2 + x^3/6 is exact to f32 rounding (x^4/24 < 4e-12), and p = 1 gives exactly 1.
+template <int G>
+__device__ __forceinline__ void emit_unit(const AlsScaleDev& sc, AlsSmem& sm, int64_t unit_idx, int unit, int lt, float p) {
   constexpr int NT = 64 * G;
   constexpr int ROWS = 64 * G;
   const TileMap<G> m(lt);
   const int row = m.row_own;
   const int bar_id = (G == 4) ? 0 : 1 + unit;
-  const int64_t ws_stride = als_ws_stride(ROWS, sc.limit);
-  const int64_t ws_rec = als_ws_rec(ROWS, sc.limit);
-  float* ws = sc.ws + unit_idx * ws_stride;
-
-  if constexpr (PHASE == 0) {
-    float2 R[4][8];
-#ifdef RDM_TIMING
-    const long long t0 = clock64();
-#endif
-    load_unit<G>(R, sc, sm, tile, unit_idx, unit, lt, true);
-#ifdef RDM_TIMING
-    const long long t1 = clock64();
-#endif
-    als_iterate<G>(R, sm, E, unit, lt, sc.limit, ws, ws + ws_rec);
-#ifdef RDM_TIMING
-    const long long t2 = clock64();
-    if (lt == 0 && (unit_idx % 37) == 0)
-      printf("unit %lld rows %d: load %lld cycles, iterate(+record) %lld cycles\n", (long long)unit_idx, ROWS, t1 - t0, t2 - t1);
-#endif
-    return;
-  } else {
-    // ---- batch-wide rmse record and first arg-min (CP:172-173, CP:74, CP:143)
-    const int64_t img = unit_idx / sc.pages;
-    const int pg = (int)(unit_idx - img * sc.pages);
-    const int64_t g0 = (img / P.group) * P.group;   // first image of the reference batch
-    float* rm = sm.rm + unit * 64;
-    const double inv_cnt = 1.0 / ((double)P.group * (double)(ROWS * kCols));
-    const int64_t gstride = (int64_t)sc.pages * ws_stride;
-    for (int k = lt; k <= sc.limit; k += NT) {
-      const float* col = sc.ws + (g0 * sc.pages + pg) * ws_stride + k;
-      double t = 0.0;
-      int b = 0;
-      for (; b + 8 <= P.group; b += 8) {   // 8 independent loads in flight, summed in image order
-        float v[8];
+  const int64_t img = unit_idx / sc.pages;
+  const int pg = (int)(unit_idx - img * sc.pages);
+  float pw;
+  {
+    const float x = logf(p) * (1.0f / ((float)ROWS * (float)ROWS));
+    pw = 1.0f + fmaf(fmaf(x, 1.0f / 6.0f, 0.5f) * x, x, x);
+    if (!(p > 0.0f) || !(fabsf(x) < 3e-3f)) pw = (float)pow((double)p, 1.0 / ((double)ROWS * (double)ROWS));   // zeros, negatives, NaN, huge ratios
+  }
+  const float prod = warp_prod(pw);
+  unit_barrier(bar_id, NT);
+  float* scratch = sm.p_s + unit * 64;
+  if (m.lane == 0) scratch[m.lw] = prod;
+  unit_barrier(bar_id, NT);
+  float gm = scratch[0];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = col[(b + j) * gstride];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) t += (double)v[j];
-      }
-      for (; b < P.group; ++b) t += (double)col[b * gstride];
-      rm[k] = (float)sqrt(t * inv_cnt);
-    }
-    // first arg-min (CP:74, CP:143) as a parallel min over (value bits, index) keys: rmse values are
-    // >= 0, so their bit patterns order like the values and ties resolve to the smaller index
-    // (limit <= 127: threads 0..127 hold one key each, NT >= 64 threads take two)
-    unsigned long long key = ~0ull;
-    for (int k = lt; k <= sc.limit; k += NT) {
-      const unsigned long long kk = ((unsigned long long)__float_as_uint(rm[k]) << 32) | (unsigned)k;
-      key = kk < key ? kk : key;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
-      key = other < key ? other : key;
-    }
-    unsigned long long* kscr = reinterpret_cast<unsigned long long*>(sm.qpart) + unit * 8;   // 8 keys per unit
-    if (m.lane == 0) kscr[m.lw] = key;
-    unit_barrier(bar_id, NT);
-#pragma unroll
-    for (int w = 0; w < 2 * G; ++w) {
-      const unsigned long long other = kscr[w];
-      key = other < key ? other : key;
-    }
-    const int kstar = (int)(key & 0xffffffffu);
-    if (img == g0) {
-      const int64_t gp = (img / P.group) * sc.pages + pg;
-      if (sc.record_out)
-        for (int k = lt; k <= sc.limit; k += NT) sc.record_out[gp * (sc.limit + 1) + k] = rm[k];
-      if (sc.kstar_out && lt == 0) sc.kstar_out[gp] = kstar;
-    }
-    const float p = (kstar == 0) ? 1.0f : ws[ws_rec + (int64_t)(kstar - 1) * ROWS + row];
-    // ---- quick_gm(p, H) with H = rows: prod_i p_i^(1/H^2)  (CP:76, CP:146, CP:244-255).  The exponent is
-    // 2^-12 or 2^-16, so p^(1/H^2) = exp(x) with |x| = |ln p| / H^2 < 3e-3: 1 + x + x^2/2 + x^3/6 is exact to
-    // f32 rounding (x^4/24 < 4e-12), and p = 1 gives exactly 1.
-    float pw;
-    {
-      const float x = logf(p) * (1.0f / ((float)ROWS * (float)ROWS));
-      pw = 1.0f + fmaf(fmaf(x, 1.0f / 6.0f, 0.5f) * x, x, x);
-      if (!(p > 0.0f) || !(fabsf(x) < 3e-3f)) pw = (float)pow((double)p, 1.0 / ((double)ROWS * (double)ROWS));   // zeros, negatives, NaN, huge ratios
-    }
-    float prod = warp_prod(pw);
-    unit_barrier(bar_id, NT);   // rm[] no longer needed; reuse p_s as scratch
-    float* scratch = sm.p_s + unit * 64;
-    if (m.lane == 0) scratch[m.lw] = prod;
-    unit_barrier(bar_id, NT);
-    float gm = scratch[0];
-#pragma unroll
-    for (int w = 1; w < 2 * G; ++w) gm *= scratch[w];
-    const float out = p / gm;
-    if (sc.pages_out) sc.pages_out[unit_idx * ROWS + row] = out;
-    if (sc.map_out) {
-      if constexpr (G == 1) {
-        sc.map_out[img * 64 + row] = out;
-      } else {
-        const int side = sc.side, ratio = side >> 4;
-        float* mp = sc.map_out + img * (int64_t)side * side;
-        // CP:218-238 as written: block-row j of every block-column holds page j (< ratio)
-        if (pg < ratio)
-          for (int bc = 0; bc < ratio; ++bc) mp[(16 * pg + (row >> 4)) * side + 16 * bc + (row & 15)] = out;
-      }
+  for (int w = 1; w < 2 * G; ++w) gm *= scratch[w];
+  unit_barrier(bar_id, NT);   // scratch (= p_s) is reused by the next unit
+  const float out = p / gm;
+  if (sc.pages_out) sc.pages_out[unit_idx * ROWS + row] = out;
+  if (sc.map_out) {
+    if constexpr (G == 1) {
+      sc.map_out[img * 64 + row] = out;
+    } else {
+      const int side = sc.side, ratio = side >> 4;
+      float* mp = sc.map_out + img * (int64_t)side * side;
+      // CP:218-238 as written: block-row j of every block-column holds page j (< ratio)
+      if (pg < ratio)
+        for (int bc = 0; bc < ratio; ++bc) mp[(16 * pg + (row >> 4)) * side + 16 * bc + (row & 15)] = out;
     }
   }
 }
 
-template <int PHASE>
+__device__ __forceinline__ unsigned cluster_ctarank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ unsigned cluster_nctarank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {   // every thread of every CTA of the cluster
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// The dense kernel: one launch, thread-block clusters of `cluster` CTAs.
+//  * 64-row units (the 8x8 maps, CP:38-85): the `group` images of a reference batch belong to ONE cluster, four
+//    units per CTA and round.  Pass 1 iterates with the record and leaves each unit's SSE record in the
+//    workspace; one cluster barrier later every team sums the group's records (CP:172-173), takes the first
+//    minimum (CP:74) and replays its own k* iterations on the matrix it still holds in registers.
+//  * 256-row units (pages): only the (group, page) items the compact kernel left alone - a matrix without the
+//    pair-build structure, or a scale flagged RDM_ALS_DENSE_ONLY.  One CTA walks the units of an item one after
+//    the other: pass 1 accumulates the group record, pass 2 reloads and replays k* iterations.
 __global__ void __launch_bounds__(kAlsThreads, 2) als_kernel(const __grid_constant__ AlsParams P) {
   extern __shared__ __align__(16) float tile[];
   __shared__ AlsSmem sm;
   int si = 0;
 #pragma unroll 1
   for (int k = 1; k < P.n_scales; ++k)
-    if ((int)blockIdx.x >= (PHASE == 0 ? P.s[k].cta_begin0 : P.s[k].cta_begin)) si = k;
+    if ((int)blockIdx.x >= P.s[k].cta_begin) si = k;
   const AlsScaleDev& sc = P.s[si];
   const int tid = threadIdx.x;
-  const int64_t n_units = P.n_images * sc.pages;
-  const int local_cta = (int)blockIdx.x - (PHASE == 0 ? sc.cta_begin0 : sc.cta_begin);
-  const int unit_stride = PHASE == 0 ? sc.cta_count0 : 1 << 30;   // phase 1: one unit per CTA
-  // Page units whose matrix has the pair-build structure were iterated by als_sparse_kernel
-  // (rdm_als_sparse.cu); the sparsify kernels leave four band flags per unit for these kinds.
-  const bool flagged = PHASE == 0 && P.sparse && sc.rows == 256 &&
-                       (sc.kind == RDM_SRC_RAW_F64 || sc.kind == RDM_SRC_VAL_F64 || sc.kind == RDM_SRC_MAP_F32);
-  auto is_compact = [&](int64_t unit_idx) {
-    const float4 fl = *reinterpret_cast<const float4*>(sc.ws + unit_idx * als_ws_stride(256, sc.limit) + als_ws_compact(sc.limit) + kCompactFloats);
-    return fl.x == 1.0f && fl.y == 1.0f && fl.z == 1.0f && fl.w == 1.0f;
+  const int local_cta = (int)blockIdx.x - sc.cta_begin;
+  const int group = P.group;
+  const bool pages = sc.rows == 256;
+  const int64_t n_items = (P.n_images / group) * sc.pages;
+  const int64_t stride256 = als_ws_stride(256, sc.limit);
+  // does the compact kernel own this (group, page) item?  (all of its units carry the four band flags)
+  auto item_is_compact = [&](int64_t item) {
+    if (sc.dense_only) return false;
+    const int64_t g = item / sc.pages, pg = item - g * sc.pages;
+    bool all = true;
+    for (int b = 0; b < group; ++b) {
+      const float4 fl = *reinterpret_cast<const float4*>(sc.ws + ((g * group + b) * sc.pages + pg) * stride256 + kCompactFloats);
+      all = all && fl.x == 1.0f && fl.y == 1.0f && fl.z == 1.0f && fl.w == 1.0f;
+    }
+    return all;
   };
-  if (flagged) {   // nothing to do for this CTA?  leave before the codebook prologue (CTA-uniform)
+  if (pages) {   // nothing to do for this CTA?  leave before the codebook prologue (CTA-uniform)
+    if (local_cta >= sc.cta_count) return;           // padding CTA of the last cluster
     bool any = false;
-    for (int64_t u = local_cta; u < n_units; u += unit_stride) any |= !is_compact(u);
+    for (int64_t it = local_cta; it < n_items; it += sc.cta_count) any |= !item_is_compact(it);
     if (!any) return;
   }
-  if (PHASE == 0 && sc.thr) {   // phase 1 never quantises
+  if (sc.thr) {
     if (tid == 0) sm.sorted = 1;
     __syncthreads();
     if (tid < kThrPad) {
@@ -771,19 +746,95 @@ __global__ void __launch_bounds__(kAlsThreads, 2) als_kernel(const __grid_consta
     sm.lut.ncell = 0;
   }
   __syncthreads();
-  if (sc.rows == 256) {
-    // 256-row unit: the record scratch E aliases the staging tile (dead once the rows are in registers)
-    for (int64_t unit_idx = local_cta; unit_idx < n_units; unit_idx += unit_stride) {
-      if (flagged && is_compact(unit_idx)) continue;
-      als_unit<4, PHASE>(P, sc, sm, tile, tile, unit_idx, 0, tid);
-      __syncthreads();   // E (= tile) is read until the end of a unit
+  const int limit = sc.limit;
+
+  if (pages) {
+    // ---- page items without pair structure: sequential units, the record scratch E aliases the staging tile
+    const double inv_cnt = 1.0 / ((double)group * (double)(256 * kCols));
+    for (int64_t item = local_cta; item < n_items; item += sc.cta_count) {
+      if (item_is_compact(item)) continue;
+      const int64_t g = item / sc.pages, pg = item - g * sc.pages;
+      for (int k = tid; k <= limit; k += kAlsThreads) sm.recg[k] = 0.0;
+      __syncthreads();
+      float2 R[4][8];
+      for (int b = 0; b < group; ++b) {
+        const int64_t unit_idx = (g * group + b) * sc.pages + pg;
+        load_unit<4>(R, sc, sm, tile, unit_idx, 0, tid, true);
+        als_iterate<4, true>(R, sm, tile, 0, tid, limit, sm.recu);
+        __syncthreads();
+        for (int k = tid; k <= limit; k += kAlsThreads) sm.recg[k] += (double)sm.recu[k];   // images in order, as CP:172-173 sums them
+        __syncthreads();
+      }
+      for (int k = tid; k <= limit; k += kAlsThreads) {
+        sm.rm[k] = (float)sqrt(sm.recg[k] * inv_cnt);
+        if (sc.record_out) sc.record_out[item * (limit + 1) + k] = sm.rm[k];
+      }
+      __syncthreads();
+      const int kstar = first_argmin<4>(sm.rm, limit, sm, 0, tid);
+      if (sc.kstar_out && tid == 0) sc.kstar_out[item] = kstar;
+      for (int b = 0; b < group; ++b) {
+        const int64_t unit_idx = (g * group + b) * sc.pages + pg;
+        load_unit<4>(R, sc, sm, tile, unit_idx, 0, tid, false);
+        const float p = als_iterate<4, false>(R, sm, tile, 0, tid, kstar, nullptr);
+        emit_unit<4>(sc, sm, unit_idx, 0, tid, p);
+        __syncthreads();
+      }
     }
-  } else {
-    const int unit = tid >> 6;
-    const int64_t unit_idx = (int64_t)local_cta * 4 + unit;
-    // 64-row units: four independent units per CTA, so E lives behind the four staging tiles
-    if (unit_idx < n_units)
-      als_unit<1, PHASE>(P, sc, sm, tile + unit * (64 * 64), tile + kTileFloats + unit * ((sc.limit + 1) * 33), unit_idx, unit, tid & 63);
+    return;
+  }
+
+  // ---- 64-row units: cluster = one reference batch
+  const unsigned crank = cluster_ctarank(), csize = cluster_nctarank();
+  const int64_t g = local_cta / (int)csize;
+  const int unit = tid >> 6, lt = tid & 63;
+  const int per_round = 4 * (int)csize;
+  const int rounds = (group + per_round - 1) / per_round;
+  const int64_t stride64 = als_ws_stride(64, limit);
+  float* tile_u = tile + unit * (64 * 64);
+  float* E_u = tile + kTileFloats + unit * ((limit + 1) * 33);
+  float2 R[4][8];
+  for (int r = 0; r < rounds; ++r) {
+    const int b = r * per_round + (int)crank * 4 + unit;
+    if (b < group) {
+      const int64_t unit_idx = g * group + b;
+      load_unit<1>(R, sc, sm, tile_u, unit_idx, unit, lt, true);
+      als_iterate<1, true>(R, sm, E_u, unit, lt, limit, sc.ws + unit_idx * stride64);
+    }
+  }
+  __threadfence();
+  cluster_sync_all();
+  // every team sums the group's records in image order (f64), takes the rmse and its first minimum
+  float* rm = sm.rm + unit * 64;
+  const double inv_cnt = 1.0 / ((double)group * (double)(64 * kCols));
+  for (int k = lt; k <= limit; k += 64) {
+    const float* col = sc.ws + g * group * stride64 + k;
+    double t = 0.0;
+    int b = 0;
+    for (; b + 8 <= group; b += 8) {   // 8 independent loads in flight, summed in image order
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = __ldcg(col + (b + j) * stride64);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) t += (double)v[j];
+    }
+    for (; b < group; ++b) t += (double)__ldcg(col + b * stride64);
+    rm[k] = (float)sqrt(t * inv_cnt);
+  }
+  unit_barrier(1 + unit, 64);
+  const int kstar = first_argmin<1>(rm, limit, sm, unit, lt);
+  if (crank == 0 && unit == 0) {
+    if (sc.record_out)
+      for (int k = lt; k <= limit; k += 64) sc.record_out[g * (limit + 1) + k] = rm[k];
+    if (sc.kstar_out && lt == 0) sc.kstar_out[g] = kstar;
+  }
+  for (int r = 0; r < rounds; ++r) {
+    const int b = r * per_round + (int)crank * 4 + unit;
+    if (b < group) {
+      const int64_t unit_idx = g * group + b;
+      if (rounds > 1) load_unit<1>(R, sc, sm, tile_u, unit_idx, unit, lt, false);   // single round: the tile is still in registers
+      const float p = als_iterate<1, false>(R, sm, E_u, unit, lt, kstar, nullptr);
+      emit_unit<1>(sc, sm, unit_idx, unit, lt, p);
+    }
   }
 }
 
@@ -823,14 +874,13 @@ extern "C" int64_t rdm_als_ws_floats(int32_t rows, int32_t pages, int32_t limit)
 
 extern "C" int rdm_als_fused(const rdm_als_scale_t* scales, int32_t n_scales, int64_t n_images, int32_t group,
                              rdm_stream_t stream) {
-  return rdm_als_fused_phases(scales, n_scales, n_images, group, 3, stream);
+  return rdm_als_fused_phases(scales, n_scales, n_images, group, RDM_ALS_PHASE_ALL, stream);
 }
 
 extern "C" int rdm_als_fused_phases(const rdm_als_scale_t* scales, int32_t n_scales, int64_t n_images, int32_t group,
                                     int32_t phase_mask, rdm_stream_t stream) {
   RDM_REQUIRE(scales, "rdm_als_fused: null scales");
-  RDM_REQUIRE(phase_mask >= 1 && phase_mask <= 31, "rdm_als_fused_phases: phase_mask must be in 1..31");
-  if (phase_mask & 1) phase_mask |= 4 | 8 | 16;
+  RDM_REQUIRE(phase_mask >= 1 && phase_mask <= RDM_ALS_PHASE_ALL, "rdm_als_fused_phases: phase_mask must be in 1..%d", RDM_ALS_PHASE_ALL);
   RDM_REQUIRE(n_scales >= 1 && n_scales <= kMaxScales, "rdm_als_fused: n_scales must be 1..%d (got %d)", kMaxScales, n_scales);
   RDM_REQUIRE(n_images >= 0, "rdm_als_fused: negative n_images");
   RDM_REQUIRE(group >= 1, "rdm_als_fused: group must be >= 1");
@@ -840,10 +890,13 @@ extern "C" int rdm_als_fused_phases(const rdm_als_scale_t* scales, int32_t n_sca
   P.n_scales = n_scales;
   P.group = group;
   P.n_images = n_images;
-  // RDM_ALS_DENSE=1 (A/B measurements, tests of the dense kernel): every unit takes the dense kernel
-  static const bool dense_only = [] { const char* v = getenv("RDM_ALS_DENSE"); return v && v[0] == '1'; }();
-  P.sparse = dense_only ? 0 : 1;
-  int64_t ctas = 0, ctas0 = 0;
+  const int64_t n_groups = n_images / group;
+  // cluster size of the dense launch: the 64-row units of one reference batch share a cluster, four per CTA
+  int cluster = 1;
+  for (int k = 0; k < n_scales; ++k)
+    if (scales[k].rows == 64)
+      while (cluster < 8 && 4 * cluster < group) cluster *= 2;
+  int64_t ctas = 0;
   for (int k = 0; k < n_scales; ++k) {
     const rdm_als_scale_t& h = scales[k];
     RDM_REQUIRE(h.src && h.ws, "rdm_als_fused: scale %d: src and ws are required", k);
@@ -852,6 +905,7 @@ extern "C" int rdm_als_fused_phases(const rdm_als_scale_t* scales, int32_t n_sca
     RDM_REQUIRE(h.src_kind >= RDM_SRC_RAW_F64 && h.src_kind <= RDM_SRC_MAP_F32, "rdm_als_fused: scale %d: bad src_kind %d", k, h.src_kind);
     RDM_REQUIRE(h.limit >= 0 && h.limit <= (h.rows == 64 ? 63 : 127), "rdm_als_fused: scale %d: limit %d out of range", k, h.limit);
     RDM_REQUIRE(h.pages >= 1, "rdm_als_fused: scale %d: pages must be >= 1", k);
+    RDM_REQUIRE((h.flags & ~RDM_ALS_FLAGS_ALL) == 0, "rdm_als_fused: scale %d: unknown flag bits 0x%x", k, h.flags);
     const bool needs_side = h.src_kind == RDM_SRC_MAP_F32 || h.map_out;
     if (needs_side) {
       if (h.rows == 64)
@@ -866,6 +920,8 @@ extern "C" int rdm_als_fused_phases(const rdm_als_scale_t* scales, int32_t n_sca
     RDM_REQUIRE(h.src_kind == RDM_SRC_MAP_F32 || aligned16(h.src), "rdm_als_fused: scale %d: src must be 16-byte aligned", k);
     RDM_REQUIRE((!h.values_out || aligned16(h.values_out)) && (!h.bins_out || (reinterpret_cast<uintptr_t>(h.bins_out) & 3u) == 0),
                 "rdm_als_fused: scale %d: values_out must be 16-byte and bins_out 4-byte aligned", k);
+    RDM_REQUIRE((!h.pages_out || aligned16(h.pages_out)) && (!h.map_out || aligned16(h.map_out)),
+                "rdm_als_fused: scale %d: pages_out and map_out must be 16-byte aligned", k);
     AlsScaleDev& d = P.s[k];
     d.src = h.src;
     d.thr = quant ? h.thresholds : nullptr;
@@ -883,21 +939,25 @@ extern "C" int rdm_als_fused_phases(const rdm_als_scale_t* scales, int32_t n_sca
     d.side = h.side;
     d.limit = h.limit;
     d.cta_begin = (int32_t)ctas;
-    d.cta_begin0 = (int32_t)ctas0;
-    const int64_t units = n_images * h.pages;
-    const int64_t n1 = (h.rows == 256) ? units : (units + 3) / 4;
-    ctas += n1;
-    // dense iterate launch: a compact-eligible page scale keeps few CTAs (each walks up to 8 units and
-    // normally finds nothing to do); every such CTA reserves 100 KB of shared memory and 32 K registers
-    const bool eligible = P.sparse && h.rows == 256 &&
-                          (h.src_kind == RDM_SRC_RAW_F64 || h.src_kind == RDM_SRC_VAL_F64 || h.src_kind == RDM_SRC_MAP_F32);
-    int64_t n0 = n1;
-    if (eligible) n0 = std::min<int64_t>(units, std::max<int64_t>(8, (units + 7) / 8));
-    d.cta_count0 = (h.rows == 256) ? (int32_t)n0 : 1;
-    ctas0 += n0;
+    // page scales the compact kernel can take (rdm_als_sparse.cu) keep a few strided fallback CTAs here, each of
+    // which normally finds nothing to do; every other page scale gets one CTA per (group, page) item
+    const bool compact_eligible = h.rows == 256 && !(h.flags & RDM_ALS_DENSE_ONLY) &&
+                                  (h.src_kind == RDM_SRC_RAW_F64 || h.src_kind == RDM_SRC_VAL_F64 || h.src_kind == RDM_SRC_MAP_F32);
+    d.dense_only = (h.rows == 256 && !compact_eligible) ? 1 : 0;
+    int64_t n;
+    if (h.rows == 64) {
+      n = n_groups * cluster;
+      d.cta_count = (int32_t)n;
+    } else {
+      const int64_t items = n_groups * h.pages;
+      n = compact_eligible ? std::min<int64_t>(items, std::max<int64_t>(8, (items + 7) / 8)) : items;
+      d.cta_count = (int32_t)n;
+      n = (n + cluster - 1) / cluster * cluster;   // whole clusters
+    }
+    ctas += n;
     RDM_REQUIRE(ctas < (1ll << 30), "rdm_als_fused: too many work units");
   }
-  // dynamic shared memory: staging tile, plus the record scratch E of phase 0
+  // dynamic shared memory: staging tile, plus the record scratch E
   size_t dyn1 = kTileFloats * sizeof(float), dyn = dyn1;
   for (int k = 0; k < n_scales; ++k) {
     const size_t need = (scales[k].rows == 256) ? (size_t)(scales[k].limit + 1) * 129 * sizeof(float)
@@ -905,23 +965,35 @@ extern "C" int rdm_als_fused_phases(const rdm_als_scale_t* scales, int32_t n_sca
     if (need > dyn) dyn = need;
   }
   static size_t smem_set0[64];
-  cudaError_t e = ensure_dyn_smem(als_kernel<0>, dyn, smem_set0);
+  cudaError_t e = ensure_dyn_smem(als_kernel, dyn, smem_set0);
   if (e != cudaSuccess) {
     set_error("rdm_als_fused: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     return (int)e;
   }
-  if (P.sparse && (phase_mask & (4 | 8))) {
-    int rc = als_sparse_launch(scales, n_scales, n_images, (phase_mask & 4) != 0, (phase_mask & 8) != 0, (cudaStream_t)stream);
+  if (phase_mask & (RDM_ALS_PHASE_SPARSIFY | RDM_ALS_PHASE_PAGES)) {
+    int rc = als_sparse_launch(scales, n_scales, n_images, group, (phase_mask & RDM_ALS_PHASE_SPARSIFY) != 0,
+                               (phase_mask & RDM_ALS_PHASE_PAGES) != 0, (cudaStream_t)stream);
     if (rc) return rc;
   }
-  if (phase_mask & 16) {
-    als_kernel<0><<<(unsigned)ctas0, kAlsThreads, dyn, (cudaStream_t)stream>>>(P);
-    int rc = launch_status("als_kernel<iterate>");
-    if (rc) return rc;
-  }
-  if (phase_mask & 2) {
-    als_kernel<1><<<(unsigned)ctas, kAlsThreads, 0, (cudaStream_t)stream>>>(P);
-    return launch_status("als_kernel<select>");
+  if (phase_mask & RDM_ALS_PHASE_DENSE) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)ctas);
+    cfg.blockDim = dim3(kAlsThreads);
+    cfg.dynamicSmemBytes = dyn;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, als_kernel, P);
+    if (e != cudaSuccess) {
+      set_error("rdm_als_fused: als_kernel launch: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    return launch_status("als_kernel");
   }
   return 0;
 }

@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(256) als_sparsify_raw_kernel(const __grid_cons
   const unsigned it0 = kSparsifyTables.item[h][lane], it1 = kSparsifyTables.item[h][32 + lane], it2 = kSparsifyTables.item[h][64 + lane];
   const unsigned centry = *reinterpret_cast<const unsigned*>(&kSparsifyTables.compact[8 * h + (lane >> 2)][4 * (lane & 3)]);
   if (quant) load_book(sc, thr_d, lvl_f, &sorted, tid, 256);
-  float* compact = sc.ws + unit * als_ws_stride(256, sc.limit) + als_ws_compact(sc.limit);
+  float* compact = sc.ws + unit * als_ws_stride(256, sc.limit);
   const int srt = quant ? sorted : 1;
   const int lane_f = (r0 >= 1) ? 0 : 28;             // column 0 / 56 is outside every window of this pixel row
   const int a = (lane >> 2) - r0;
@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(256) als_sparsify_map_kernel(const __grid_cons
   const int r0 = min(row >> 5, 5), c0 = min((row & 15) >> 1, 5), span0 = min(((row & 15) >> 2) * 2, 4);
   const int bf = lloyd_bin<double>(d, thr_d, srt);   // 55 of 64 columns hold d itself
   const float f = lvl_f[bf];
-  float* compact = sc.ws + unit * als_ws_stride(256, sc.limit) + als_ws_compact(sc.limit);
+  float* compact = sc.ws + unit * als_ws_stride(256, sc.limit);
   float o[16];
   o[0] = f;
   o[13] = o[14] = o[15] = 0.f;
@@ -331,47 +331,81 @@ __device__ __forceinline__ float span_dot(const float (&D)[12], const float (&v)
     if ((e & 3) >= FROM) acc = fmaf(D[e], v[e], acc);
   return acc;
 }
-#ifdef RDM_SPARSE_FFMA2
-// Variant for A/B measurements: the 12-entry dot as six packed fma.rn.f32x2 (even / odd partial sums) + one add.
-// The register pairs (D[2e], D[2e+1]) and (v[2e], v[2e+1]) are contiguous, so the compiler needs no moves.
-template <int T>
-__device__ __forceinline__ float row_dot(const float (&D)[12], const float (&v)[12]) {
-  unsigned long long acc = 0ull;   // (0.f, 0.f)
-#pragma unroll
-  for (int e = 0; e < 12; e += 2) {
-    unsigned long long d, x;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(D[e]), "f"(D[e + 1]));
-    asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(v[e]), "f"(v[e + 1]));
-    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(d), "l"(x));
-  }
-  float lo, hi;
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc));
-  return lo + hi;
-}
-#else
 template <int T>   // row slot T = 4 dr + cc
 __device__ __forceinline__ float row_dot(const float (&D)[12], const float (&v)[12]) {
   return span_dot<((T & 3) >= 2) ? 1 : 0>(D, v);
 }
-#endif
 
-// One warp per unit.  Dynamic shared memory: (limit + 1) x 32 floats (per-lane residuals of every iteration).
-// Measured and rejected: capping the kernel at 128 registers (16 warps per SM) and pre-summing the residuals
-// over lane pairs to halve the scratch - both lengthen the iteration (47 -> 52..54 us per launch).
-__global__ void __launch_bounds__(32) als_sparse_kernel(const __grid_constant__ SparseParams P) {
-  __shared__ __align__(16) float qs[64];
-  __shared__ __align__(16) float ps[256];
-  extern __shared__ __align__(16) float E[];
-  const int lane = threadIdx.x;
-  const int gunit = blockIdx.x;
-  const SparseScaleDev& sc = find_scale(P, gunit);
-  const int64_t unit = gunit - sc.unit_begin;
-  const int limit = sc.limit;
-  float* wsu = sc.ws + unit * als_ws_stride(256, limit);
-  const float* compact = wsu + als_ws_compact(limit);
-  const float4 fl = *reinterpret_cast<const float4*>(compact + kCompactFloats);   // checked after the loads below are in flight
-  float* rec = wsu;
-  float* hist = wsu + als_ws_rec(256, limit);
+// ---- the grouped page kernel --------------------------------------------------------------------
+// One CTA per (reference batch = "group", page); warp w iterates the page of image w of the group, so the 16
+// images whose rmse the reference averages (CP:172-173) meet in ONE CTA and the arg-min (CP:143) is taken while
+// the iterations run: nothing but the selected iterate ever leaves the SM.
+//
+//  * Iteration k of a warp leaves its 32 per-lane residuals in E[k % 3][warp][lane] and ARRIVES (bar.arrive, no
+//    wait) on named barrier 1 + k % 3.
+//  * Warp (k % W) is the reducer of iteration k: at the top of its step k+1 it waits for the arrivals
+//    (bar.sync on the same barrier), sums the group's residuals (f64), takes the rmse, compares it with the
+//    running minimum (strict <: the FIRST minimum wins, as list.index(min(list)) does) and publishes
+//    flag[k % 3] = 2 k + new_minimum.
+//  * Every warp reads the verdict on iteration k at the end of its step k + kLag, and on a new minimum copies
+//    p_k from its 3-deep ring of iterates into its `best` row.  The flag wait also bounds the skew between the
+//    warps, which is what makes the 3-deep rings and the 3 barriers safe to reuse (see the ordering argument
+//    in DESIGN.md 4.1).
+// Groups of more than 16 images take kRounds rounds of 16 warps: pass 1 accumulates the group record over the
+// rounds (no iterate is kept), pass 2 re-runs the k* selected iterations of every unit (bit-identical
+// arithmetic) and emits them.  On noise-like maps k* <= 1, so pass 2 is a few per cent of pass 1.
+constexpr int kLag = 2;
+constexpr int kRing = kLag + 1;
+static_assert(kLag == 2 && kRing == 3, "the ring slot arithmetic of pages_iterate assumes a lag of 2");
+constexpr int kGroupWarps = 16;
+constexpr int kWarpFloats = kRing * 256 + 64 + 256;   // p ring, q, best
+constexpr int kMaxLimit = 127;
+
+struct PagesScaleDev {
+  float* ws;
+  float* pages_out;
+  float* map_out;
+  float* record_out;
+  int32_t* kstar_out;
+  int32_t pages, side, limit;
+  int32_t cta_begin;   // first (group, page) item of this scale
+};
+struct PagesParams {
+  PagesScaleDev s[kMaxSparseScales];
+  int64_t n_images;
+  int32_t n_scales, group;
+};
+
+struct PagesShared {            // fixed part of the dynamic shared memory (the per-warp rows follow)
+  float E[kRing][kGroupWarps][32];
+  double recg[kMaxLimit + 1];   // group record accumulated over the rounds (multi-round groups)
+  unsigned flag[kRing];
+  float best_rmse;
+  int kstar;
+  int all_compact;
+};
+
+__device__ __forceinline__ void named_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void named_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ unsigned ld_volatile_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory");
+  return v;
+}
+
+// The matrix of one page in registers: a lane owns the 2 x 4 pixel block (rows 2rh..2rh+1, columns 4kq..4kq+3)
+// = 8 matrix rows, and with them the two entries q[8rh+kq], q[8rh+4+kq].
+struct PageRegs {
+  float f[8], D[8][12];
+};
+
+// MODE 0: record + online arg-min (single-round groups); MODE 1: record only, accumulated into sh.recg
+// (multi-round groups, pass 1); MODE 2: no record, n_iter iterations, the last iterate is returned in p_out
+// (multi-round groups, pass 2).
+template <int MODE>
+__device__ __forceinline__ void pages_iterate(const PageRegs& M, PagesShared& sh, float* __restrict__ ps, float* __restrict__ qs,
+                                              float* __restrict__ best, int lane, int warp, int W, int n_iter, double inv_cnt,
+                                              float* __restrict__ record_out, float (&p_out)[8]) {
   const int rh = lane >> 2, kq = lane & 3;
   const int r0 = min(rh, 5), span0 = min(2 * kq, 4);
   const int sp = 8 * r0 + span0;            // first span column
@@ -380,45 +414,113 @@ __global__ void __launch_bounds__(32) als_sparse_kernel(const __grid_constant__ 
   // in the opposite order, so that the 128-bit stores of p (8 lanes = rh, rh+1 per wavefront) hit 32 distinct
   // banks.  Nothing else depends on the order: both pixel rows share the window.
   const int off_s[2] = {row_base + 16 * (rh & 1), row_base + 16 * ((rh & 1) ^ 1)};
+  const int nbar = (W + 1) * 32;
+  constexpr bool RECORD = MODE != 2;
+  const float (&f)[8] = M.f;
+  const float (&D)[8][12] = M.D;
 
-  float f[8], D[8][12];
+  float A = 0.f;
+  if (RECORD) {
+    // A = sum over this lane's rows of A_rho, and the record of iteration 0 (p = q = 1, CP:123):
+    // sum_j fl(1 - R)^2 with 52 columns outside the span
+    double e0 = 0.0, asum = 0.0;
 #pragma unroll
-  for (int dr = 0; dr < 2; ++dr)
+    for (int t = 0; t < 8; ++t) {
+      const float u = __fsub_rn(1.0f, f[t]);
+      double acc = 52.0 * ((double)u * (double)u);
 #pragma unroll
-    for (int cc = 0; cc < 4; ++cc) {
-      const int t = 4 * dr + cc;
-      const float4* c4 = reinterpret_cast<const float4*>(compact + (off_s[dr] + cc) * kCompactRowFloats);
-      const float4 a = c4[0], b = c4[1], c = c4[2], d = c4[3];
-      f[t] = a.x;
-      D[t][0] = a.y; D[t][1] = a.z; D[t][2] = a.w;
-      D[t][3] = b.x; D[t][4] = b.y; D[t][5] = b.z; D[t][6] = b.w;
-      D[t][7] = c.x; D[t][8] = c.y; D[t][9] = c.z; D[t][10] = c.w;
-      D[t][11] = d.x;
+      for (int e = 0; e < 12; ++e) {
+        asum = fma((double)D[t][e], 2.0 * (double)f[t] + (double)D[t][e], asum);
+        const float w = __fsub_rn(1.0f, __fadd_rn(f[t], D[t][e]));
+        acc = fma((double)w, (double)w, acc);
+      }
+      e0 += acc;
     }
-  if (!(fl.x == 1.0f && fl.y == 1.0f && fl.z == 1.0f && fl.w == 1.0f)) return;   // not a pair matrix: the dense kernel takes it
-  // A = sum over this lane's rows of A_rho, and the record of iteration 0 (p = q = 1, CP:123):
-  // sum_j fl(1 - R)^2 with 52 columns outside the span
-  double e0 = 0.0, asum = 0.0;
-#pragma unroll
-  for (int t = 0; t < 8; ++t) {
-    const float u = __fsub_rn(1.0f, f[t]);
-    double acc = 52.0 * ((double)u * (double)u);
-#pragma unroll
-    for (int e = 0; e < 12; ++e) {
-      asum = fma((double)D[t][e], 2.0 * (double)f[t] + (double)D[t][e], asum);
-      const float w = __fsub_rn(1.0f, __fadd_rn(f[t], D[t][e]));
-      acc = fma((double)w, (double)w, acc);
-    }
-    e0 += acc;
+    A = (float)asum;
+    sh.E[0][warp][lane] = (float)e0;
+    named_arrive(1, nbar);
   }
-  const float A = (float)asum;
-  E[lane] = (float)e0;
+
+  // the reducer's work for iteration j (one warp, all lanes): group rmse, first-minimum test, verdict
+  auto reduce_iteration = [&](int j) {
+    const int slot = j % kRing;   // once per W iterations per warp
+    named_sync(1 + slot, nbar);
+    const int u = lane & 15, h = lane >> 4;
+    double t = 0.0;
+    if (u < W) {
+      const float4* e4 = reinterpret_cast<const float4*>(&sh.E[slot][u][16 * h]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 x = e4[i];
+        t += (double)x.x;
+        t += (double)x.y;
+        t += (double)x.z;
+        t += (double)x.w;
+      }
+    }
+    t += __shfl_xor_sync(kFull, t, 16);
+    // unit record rounded to f32, then the group sum in f64 (the reference sums f32 values; exact in f64)
+    double g = (h == 0 && u < W) ? (double)(float)t : 0.0;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) g += __shfl_xor_sync(kFull, g, o);
+    g = __shfl_sync(kFull, g, 0);
+    unsigned verdict = (unsigned)j << 1;
+    if (MODE == 0) {
+      const float rm = (float)sqrt(g * inv_cnt);           // CP:172-173 over the whole reference batch
+      bool better = false;
+      if (lane == 0) {
+        better = rm < sh.best_rmse;                        // strict: the first minimum wins (CP:143)
+        if (better) {
+          sh.best_rmse = rm;
+          sh.kstar = j;
+        }
+        if (record_out) record_out[j] = rm;
+      }
+      verdict |= better ? 1u : 0u;
+    } else if (lane == 0) {
+      sh.recg[j] += g;
+    }
+    __syncwarp();
+    if (lane == 0) {
+      __threadfence_block();
+      *reinterpret_cast<volatile unsigned*>(&sh.flag[slot]) = verdict;
+    }
+  };
+  auto await_verdict = [&](int j, int slot) -> bool {
+    const unsigned* fp = &sh.flag[slot];
+    unsigned v;
+    do {
+      v = ld_volatile_u32(fp);
+    } while ((v >> 1) != (unsigned)j);
+    return (v & 1u) != 0u;
+  };
+  auto keep_if_best = [&](int j, int slot) {   // end of step j + kLag; slot = j % kRing
+    if (await_verdict(j, slot) && MODE == 0) {
+      if (j == 0) {
+#pragma unroll
+        for (int dr = 0; dr < 2; ++dr) *reinterpret_cast<float4*>(best + off_s[dr]) = make_float4(1.f, 1.f, 1.f, 1.f);
+      } else {
+        const float* src = ps + slot * 256;
+#pragma unroll
+        for (int dr = 0; dr < 2; ++dr) *reinterpret_cast<float4*>(best + off_s[dr]) = *reinterpret_cast<const float4*>(src + off_s[dr]);
+      }
+    }
+  };
 
   float qa = 1.0f, qb = 1.0f, m = 1.0f;   // this lane's two entries of q (slot rows >> 2); centre of the q statistics
   qs[lane] = 1.0f;
   qs[lane + 32] = 1.0f;
+#pragma unroll
+  for (int t = 0; t < 8; ++t) p_out[t] = 1.0f;
   __syncwarp();
-  for (int k = 1; k <= limit; ++k) {
+  int next_red = warp;   // next iteration this warp is the reducer of (j % W == warp)
+  int sk = 0;            // k % kRing
+  for (int k = 1; k <= n_iter; ++k) {
+    sk = sk == kRing - 1 ? 0 : sk + 1;
+    if (RECORD && k - 1 == next_red) {
+      reduce_iteration(k - 1);
+      next_red += W;
+    }
     // ---- statistics of q_{k-1} about m: S1 = sum (q - m), V = sum (q - m)^2
     const float da = qa - m, db = qb - m;
     float S1 = da + db, V = fmaf(da, da, db * db);
@@ -439,10 +541,12 @@ __global__ void __launch_bounds__(32) als_sparse_kernel(const __grid_constant__ 
       constexpr int t = decltype(tc)::value;
       const float sD = row_dot<t>(D[t], v);
       p[t] = fmaf(f[t], Q, sD) * invA;
-      const float g = fmaf(-p[t], m, f[t]);
-      gg = fmaf(g, g, gg);
-      pg = fmaf(p[t], g, pg);
-      psd = fmaf(p[t], sD, psd);
+      if (RECORD) {
+        const float g = fmaf(-p[t], m, f[t]);
+        gg = fmaf(g, g, gg);
+        pg = fmaf(p[t], g, pg);
+        psd = fmaf(p[t], sD, psd);
+      }
       pp = fmaf(p[t], p[t], pp);
       psum += p[t];
     };
@@ -450,15 +554,22 @@ __global__ void __launch_bounds__(32) als_sparse_kernel(const __grid_constant__ 
     p_row(std::integral_constant<int, 2>{}); p_row(std::integral_constant<int, 3>{});
     p_row(std::integral_constant<int, 4>{}); p_row(std::integral_constant<int, 5>{});
     p_row(std::integral_constant<int, 6>{}); p_row(std::integral_constant<int, 7>{});
-    E[k * 32 + lane] = fmaf(-2.0f, fmaf(S1, pg, psd), fmaf(64.0f, gg, fmaf(V, pp, A)));
+    float* pk = ps + sk * 256;
 #pragma unroll
-    for (int dr = 0; dr < 2; ++dr) {
-      const float4 pv = make_float4(p[4 * dr], p[4 * dr + 1], p[4 * dr + 2], p[4 * dr + 3]);
-      *reinterpret_cast<float4*>(ps + off_s[dr]) = pv;
-      *reinterpret_cast<float4*>(hist + (int64_t)(k - 1) * 256 + off_s[dr]) = pv;   // phase 1 picks p_k*
+    for (int dr = 0; dr < 2; ++dr)
+      *reinterpret_cast<float4*>(pk + off_s[dr]) = make_float4(p[4 * dr], p[4 * dr + 1], p[4 * dr + 2], p[4 * dr + 3]);
+    if (RECORD) {
+      sh.E[sk][warp][lane] = fmaf(-2.0f, fmaf(S1, pg, psd), fmaf(64.0f, gg, fmaf(V, pp, A)));
+      named_arrive(1 + sk, nbar);
     }
     __syncwarp();
-    if (k == limit) break;   // the reference's last q-update is never used
+    if (k == n_iter) {   // the reference's last q-update is never used
+      if (!RECORD) {
+#pragma unroll
+        for (int t = 0; t < 8; ++t) p_out[t] = p[t];
+      }
+      break;
+    }
     // ---- q-update: |p|^2, the four segment sums P_r' (segment r' = rows 64r'..64r'+63 = lanes 8r'..8r'+7)
 #pragma unroll
     for (int o = 1; o <= 4; o <<= 1) {
@@ -472,7 +583,7 @@ __global__ void __launch_bounds__(32) als_sparse_kernel(const __grid_constant__ 
     auto q_seg = [&](auto cc_c) {   // row (dr, cc) has rho % 4 = cc: it meets p[64 cc + j]
       constexpr int cc = decltype(cc_c)::value;
       const float Pseg = __shfl_sync(kFull, psum, 8 * cc);
-      load_span(ps + 64 * cc + sp, v);
+      load_span(pk + 64 * cc + sp, v);
       ua[cc] = fmaf(f[cc], Pseg, row_dot<cc>(D[cc], v));
       ub[cc] = fmaf(f[4 + cc], Pseg, row_dot<4 + cc>(D[4 + cc], v));
     };
@@ -483,28 +594,190 @@ __global__ void __launch_bounds__(32) als_sparse_kernel(const __grid_constant__ 
     qb = ((ub[0] + ub[1]) + (ub[2] + ub[3])) * invB;
     qs[off_s[0] >> 2] = qa;   // q index of row rho is rho >> 2
     qs[off_s[1] >> 2] = qb;
+    if (RECORD && k >= kLag) keep_if_best(k - kLag, sk == kRing - 1 ? 0 : sk + 1);   // (k - 2) % 3 == (k + 1) % 3
     __syncwarp();
   }
-  __syncwarp();
-  for (int k = lane; k <= limit; k += 32) {
-    double t = 0.0;
-#pragma unroll 8
-    for (int l = 0; l < 32; ++l) t += (double)E[k * 32 + ((l + lane) & 31)];
-    rec[k] = (float)t;
+  if (RECORD) {
+    // drain: the last iteration's reducer, and the verdicts not yet read (iterations n_iter-kLag+1 .. n_iter; the
+    // loop read those up to n_iter-1-kLag)
+    if (n_iter == next_red) reduce_iteration(n_iter);
+    for (int j = max(n_iter - kLag, 0); j <= n_iter; ++j) keep_if_best(j, j % kRing);
+  }
+}
+
+// Normalise p by quick_gm(p, H) with H = rows = 256: prod_i p_i^(1/H^2) (CP:146, CP:244-255: the exponent is
+// 2^-16, so p^(1/H^2) = exp(x) with |x| = |ln p| / H^2 < 3e-3: 1 + x + x^2/2 + x^3/6 is exact to f32 rounding and
+// p = 1 gives exactly 1) and scatter the page into pages_out / the re-tiled map (CP:218-238 as written: block-row
+// j of every block-column holds page j < ratio).
+__device__ __forceinline__ void pages_emit(const PagesScaleDev& sc, int64_t unit_idx, const float (&pv)[8], int lane) {
+  const int rh = lane >> 2, kq = lane & 3;
+  const int row_base = 32 * rh + 4 * kq;
+  const int off_s[2] = {row_base + 16 * (rh & 1), row_base + 16 * ((rh & 1) ^ 1)};
+  float prod = 1.0f;
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    const float p = pv[t];
+    const float x = logf(p) * (1.0f / 65536.0f);
+    float pw = 1.0f + fmaf(fmaf(x, 1.0f / 6.0f, 0.5f) * x, x, x);
+    if (!(p > 0.0f) || !(fabsf(x) < 3e-3f)) pw = (float)pow((double)p, 1.0 / 65536.0);   // zeros, negatives, NaN, huge ratios
+    prod *= pw;
+  }
+  const float gm = warp_prod(prod);
+  const int64_t img = unit_idx / sc.pages;
+  const int pg = (int)(unit_idx - img * sc.pages);
+#pragma unroll
+  for (int ds = 0; ds < 2; ++ds) {
+    const float4 o = make_float4(pv[4 * ds] / gm, pv[4 * ds + 1] / gm, pv[4 * ds + 2] / gm, pv[4 * ds + 3] / gm);
+    const int row = off_s[ds];   // pixel (row >> 4, row & 15 .. +3)
+    if (sc.pages_out) *reinterpret_cast<float4*>(sc.pages_out + unit_idx * 256 + row) = o;
+    if (sc.map_out) {
+      const int side = sc.side, ratio = side >> 4;
+      float* mp = sc.map_out + img * (int64_t)side * side;
+      if (pg < ratio)
+        for (int bc = 0; bc < ratio; ++bc) *reinterpret_cast<float4*>(mp + (16 * pg + (row >> 4)) * side + 16 * bc + (row & 15)) = o;
+    }
+  }
+}
+
+__device__ __forceinline__ void load_page(PageRegs& M, const float* __restrict__ compact, int lane) {
+  const int rh = lane >> 2, kq = lane & 3;
+  const int row_base = 32 * rh + 4 * kq;
+  const int off_s[2] = {row_base + 16 * (rh & 1), row_base + 16 * ((rh & 1) ^ 1)};
+#pragma unroll
+  for (int dr = 0; dr < 2; ++dr)
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+      const int t = 4 * dr + cc;
+      const float4* c4 = reinterpret_cast<const float4*>(compact + (off_s[dr] + cc) * kCompactRowFloats);
+      const float4 a = c4[0], b = c4[1], c = c4[2], d = c4[3];
+      M.f[t] = a.x;
+      M.D[t][0] = a.y; M.D[t][1] = a.z; M.D[t][2] = a.w;
+      M.D[t][3] = b.x; M.D[t][4] = b.y; M.D[t][5] = b.z; M.D[t][6] = b.w;
+      M.D[t][7] = c.x; M.D[t][8] = c.y; M.D[t][9] = c.z; M.D[t][10] = c.w;
+      M.D[t][11] = d.x;
+    }
+}
+
+__device__ __forceinline__ bool unit_is_compact(const float* compact) {
+  const float4 fl = *reinterpret_cast<const float4*>(compact + kCompactFloats);
+  return fl.x == 1.0f && fl.y == 1.0f && fl.z == 1.0f && fl.w == 1.0f;
+}
+
+// grid = (group, page) items of every page scale; block = 32 x min(group, 16).
+__global__ void __launch_bounds__(32 * kGroupWarps, 1) als_pages_kernel(const __grid_constant__ PagesParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  PagesShared& sh = *reinterpret_cast<PagesShared*>(smem_raw);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* wrow = reinterpret_cast<float*>(smem_raw + ((sizeof(PagesShared) + 15) & ~size_t(15))) + warp * kWarpFloats;
+  float* ps = wrow;
+  float* qs = wrow + kRing * 256;
+  float* best = qs + 64;
+  int si = 0;
+#pragma unroll 1
+  for (int k = 1; k < P.n_scales; ++k)
+    if ((int)blockIdx.x >= P.s[k].cta_begin) si = k;
+  const PagesScaleDev& sc = P.s[si];
+  const int item = (int)blockIdx.x - sc.cta_begin;
+  const int g = item / sc.pages, pg = item - g * sc.pages;
+  const int group = P.group, limit = sc.limit;
+  const int W0 = blockDim.x >> 5;                        // warps per round
+  const int rounds = (group + W0 - 1) / W0;
+  const int64_t stride = als_ws_stride(256, limit);
+  const double inv_cnt = 1.0 / ((double)group * (double)(256 * 64));
+  float* record_out = sc.record_out ? sc.record_out + ((int64_t)g * sc.pages + pg) * (limit + 1) : nullptr;
+  auto unit_of = [&](int r) { return ((int64_t)g * group + r * W0 + warp) * sc.pages + pg; };
+
+  // every unit of the item must have the pair-build structure; otherwise the dense kernel takes the whole item
+  if (threadIdx.x == 0) sh.all_compact = 1;
+  if (threadIdx.x < kRing) sh.flag[threadIdx.x] = 0xffffffffu;
+  if (threadIdx.x == 0) {
+    sh.best_rmse = __int_as_float(0x7f800000);
+    sh.kstar = 0;
+  }
+  for (int k = threadIdx.x; k <= limit; k += blockDim.x) sh.recg[k] = 0.0;
+  __syncthreads();
+  for (int r = 0; r < rounds; ++r)
+    if (r * W0 + warp < group && lane == 0 && !unit_is_compact(sc.ws + unit_of(r) * stride)) sh.all_compact = 0;
+  __syncthreads();
+  if (!sh.all_compact) return;
+
+  PageRegs M;
+  float pv[8];
+  if (rounds == 1) {
+    load_page(M, sc.ws + unit_of(0) * stride, lane);
+#pragma unroll
+    for (int dr = 0; dr < 2; ++dr)
+      *reinterpret_cast<float4*>(best + 32 * (lane >> 2) + 4 * (lane & 3) + 16 * dr) = make_float4(1.f, 1.f, 1.f, 1.f);
+    __syncwarp();
+    pages_iterate<0>(M, sh, ps, qs, best, lane, warp, W0, limit, inv_cnt, record_out, pv);
+    {
+      const int rh = lane >> 2, kq = lane & 3;
+      const int row_base = 32 * rh + 4 * kq;
+      const int off_s[2] = {row_base + 16 * (rh & 1), row_base + 16 * ((rh & 1) ^ 1)};
+#pragma unroll
+      for (int ds = 0; ds < 2; ++ds) {
+        const float4 b = *reinterpret_cast<const float4*>(best + off_s[ds]);
+        pv[4 * ds] = b.x; pv[4 * ds + 1] = b.y; pv[4 * ds + 2] = b.z; pv[4 * ds + 3] = b.w;
+      }
+    }
+    pages_emit(sc, unit_of(0), pv, lane);
+    __syncthreads();
+    if (threadIdx.x == 0 && sc.kstar_out) sc.kstar_out[(int64_t)g * sc.pages + pg] = sh.kstar;
+    return;
+  }
+  // ---- multi-round groups: pass 1 = group record, pass 2 = replay of the selected iterations
+  for (int r = 0; r < rounds; ++r) {
+    const int Wr = min(W0, group - r * W0);
+    if (warp < Wr) {
+      load_page(M, sc.ws + unit_of(r) * stride, lane);
+      pages_iterate<1>(M, sh, ps, qs, best, lane, warp, Wr, limit, inv_cnt, nullptr, pv);
+    }
+    __syncthreads();
+    if (threadIdx.x < kRing) sh.flag[threadIdx.x] = 0xffffffffu;
+    __syncthreads();
+  }
+  if (warp == 0) {   // first minimum of the group record (CP:143), as a min over (value bits, index) keys
+    unsigned long long key = ~0ull;
+    for (int k = lane; k <= limit; k += 32) {
+      const float rm = (float)sqrt(sh.recg[k] * inv_cnt);
+      if (record_out) record_out[k] = rm;
+      const unsigned long long kk = ((unsigned long long)__float_as_uint(rm) << 32) | (unsigned)k;
+      key = kk < key ? kk : key;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(kFull, key, o);
+      key = other < key ? other : key;
+    }
+    if (lane == 0) {
+      sh.kstar = (int)(key & 0xffffffffu);
+      if (sc.kstar_out) sc.kstar_out[(int64_t)g * sc.pages + pg] = sh.kstar;
+    }
+  }
+  __syncthreads();
+  const int kstar = sh.kstar;
+  for (int r = 0; r < rounds; ++r) {
+    if (r * W0 + warp >= group) break;
+    load_page(M, sc.ws + unit_of(r) * stride, lane);
+    pages_iterate<2>(M, sh, ps, qs, best, lane, warp, 1, kstar, inv_cnt, nullptr, pv);
+    pages_emit(sc, unit_of(r), pv, lane);
   }
 }
 
 }  // namespace
 
 // Launch the compact path for every eligible scale (256-row units given as f64 matrices or as maps).
-int als_sparse_launch(const rdm_als_scale_t* scales, int32_t n_scales, int64_t n_images, bool sparsify, bool iterate, cudaStream_t stream) {
-  SparseParams raw{}, map{}, all{};
+int als_sparse_launch(const rdm_als_scale_t* scales, int32_t n_scales, int64_t n_images, int32_t group, bool sparsify, bool iterate,
+                      cudaStream_t stream) {
+  SparseParams raw{}, map{};
+  PagesParams all{};
   raw.n_images = map.n_images = all.n_images = n_images;
-  int64_t n_raw = 0, n_map = 0, n_all = 0;
-  int max_limit = 0;
+  all.group = group;
+  int64_t n_raw = 0, n_map = 0, n_items = 0;
+  const int64_t n_groups = n_images / group;
   for (int k = 0; k < n_scales; ++k) {
     const rdm_als_scale_t& h = scales[k];
-    if (h.rows != 256) continue;
+    if (h.rows != 256 || (h.flags & RDM_ALS_DENSE_ONLY)) continue;
     const bool is_map = h.src_kind == RDM_SRC_MAP_F32;
     if (!(is_map || h.src_kind == RDM_SRC_RAW_F64 || h.src_kind == RDM_SRC_VAL_F64)) continue;
     const bool quant = h.src_kind != RDM_SRC_VAL_F64;
@@ -525,13 +798,20 @@ int als_sparse_launch(const rdm_als_scale_t* scales, int32_t n_scales, int64_t n
     d.unit_begin = (int32_t)n_part;
     part.s[part.n_scales++] = d;
     n_part += units;
-    d.unit_begin = (int32_t)n_all;
-    all.s[all.n_scales++] = d;
-    n_all += units;
-    if (h.limit > max_limit) max_limit = h.limit;
+    PagesScaleDev& a = all.s[all.n_scales++];
+    a.ws = h.ws;
+    a.pages_out = h.pages_out;
+    a.map_out = h.map_out;
+    a.record_out = h.record_out;
+    a.kstar_out = h.kstar_out;
+    a.pages = h.pages;
+    a.side = h.side;
+    a.limit = h.limit;
+    a.cta_begin = (int32_t)n_items;
+    n_items += n_groups * h.pages;
   }
-  if (n_all == 0) return 0;
-  RDM_REQUIRE(n_all < (1ll << 28), "rdm_als_fused: too many work units");
+  if (n_items == 0) return 0;
+  RDM_REQUIRE(n_raw + n_map < (1ll << 28), "rdm_als_fused: too many work units");
   if (n_raw && sparsify) {
     als_sparsify_raw_kernel<<<(unsigned)(4 * n_raw), 256, 0, stream>>>(raw);
     int rc = launch_status("als_sparsify_raw_kernel");
@@ -543,8 +823,16 @@ int als_sparse_launch(const rdm_als_scale_t* scales, int32_t n_scales, int64_t n
     if (rc) return rc;
   }
   if (!iterate) return 0;
-  als_sparse_kernel<<<(unsigned)n_all, 32, (size_t)(max_limit + 1) * 32 * sizeof(float), stream>>>(all);
-  return launch_status("als_sparse_kernel");
+  const int warps = group < kGroupWarps ? group : kGroupWarps;
+  const size_t dyn = ((sizeof(PagesShared) + 15) & ~size_t(15)) + (size_t)warps * kWarpFloats * sizeof(float);
+  static size_t smem_set[64];
+  cudaError_t e = ensure_dyn_smem(als_pages_kernel, dyn, smem_set);
+  if (e != cudaSuccess) {
+    set_error("rdm_als_fused: cudaFuncSetAttribute(als_pages_kernel): %s", cudaGetErrorString(e));
+    return (int)e;
+  }
+  als_pages_kernel<<<(unsigned)n_items, 32 * warps, dyn, stream>>>(all);
+  return launch_status("als_pages_kernel");
 }
 
 }  // namespace rdm

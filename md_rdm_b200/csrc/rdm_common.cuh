@@ -17,7 +17,7 @@ namespace rdm {
 // ---- error plumbing (no exceptions cross the ABI) --------------------------------------
 void set_error(const char* fmt, ...);
 int launch_status(const char* what);   // cudaGetLastError -> return code + message
-int als_sparse_launch(const rdm_als_scale_t* scales, int32_t n_scales, int64_t n_images, bool sparsify, bool iterate, cudaStream_t stream);   // rdm_als_sparse.cu
+int als_sparse_launch(const rdm_als_scale_t* scales, int32_t n_scales, int64_t n_images, int32_t group, bool sparsify, bool iterate, cudaStream_t stream);   // rdm_als_sparse.cu
 
 #define RDM_REQUIRE(cond, ...)            \
   do {                                    \
@@ -51,17 +51,15 @@ constexpr int kLvl = 41;              // Lloyd levels
 constexpr int kThrPad = 64;           // padded table for the branch-free search (NaN fill)
 
 // ---- ALS workspace layout (rdm_als_scale_t.ws), per unit = one (image, page) ------------------
-//   [0, rec)                 SSE record of iterations 0..limit
-//   [rec, rec + limit*rows)  iterates p_1..p_limit
-//   256-row units only:      [.., +256*16) compact page form (rdm_als_sparse.cu), then 4 band flags
-// For 256-row units `rec` is padded to a multiple of 4 floats so that every section is 16-byte aligned.
+//   256-row units: the 16 KB compact page form (rdm_als_sparse.cu: 256 rows x [f, D[12], 3 pad]), then 4 band
+//                  flags (1.0f = the band has the pair-build structure) and 4 pad floats;
+//   64-row units:  the SSE record of iterations 0..limit (exchanged between the CTAs of a group's cluster).
+// No iterate history: the arg-min is taken inside the iterate kernels (rdm_als_sparse.cu, rdm_als.cu).
 constexpr int kCompactRowFloats = 16;   // f, D[12], 3 pad
 constexpr int kCompactFloats = 256 * kCompactRowFloats;
-__host__ __device__ __forceinline__ int64_t als_ws_rec(int rows, int limit) { return rows == 256 ? ((limit + 1 + 3) & ~3) : limit + 1; }
 __host__ __device__ __forceinline__ int64_t als_ws_stride(int rows, int limit) {
-  return als_ws_rec(rows, limit) + (int64_t)limit * rows + (rows == 256 ? kCompactFloats + 4 : 0);
+  return rows == 256 ? kCompactFloats + 8 : ((limit + 1 + 3) & ~3);
 }
-__host__ __device__ __forceinline__ int64_t als_ws_compact(int limit) { return als_ws_rec(256, limit) + (int64_t)limit * 256; }
 
 // ---- warp helpers -------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {

@@ -35,7 +35,7 @@ LIMIT_PAGE = 100
 class FusionPlan:
     def __init__(self, n_images: int, scales: Sequence[int] = (8, 16, 32), source: str = "map", group: Optional[int] = None,
                  device="cuda", quant: Optional[Quantization] = None, want_bins: bool = True, want_values: bool = False,
-                 want_A: bool = False, limit_8: int = LIMIT_8, limit_page: int = LIMIT_PAGE, overlap: bool = False):
+                 want_A: bool = False, limit_8: int = LIMIT_8, limit_page: int = LIMIT_PAGE, overlap: bool = False, flags: int = 0):
         if source not in ("map", "raw"):
             raise ValueError("source must be 'map' or 'raw'")
         self.lib = load()                      # raises if librdm_b200.so is missing: no fallback
@@ -113,7 +113,7 @@ class FusionPlan:
             if want_values:
                 self.values[s] = torch.empty((N, P, rows, 64), dtype=f32, device=dev)
             d = descs[i]
-            d.src, d.src_kind, d.rows, d.pages, d.side, d.limit = self.src[s].data_ptr(), kind, rows, P, s, limit
+            d.src, d.src_kind, d.rows, d.pages, d.side, d.limit, d.flags = self.src[s].data_ptr(), kind, rows, P, s, limit, int(flags)
             d.thresholds, d.levels = thr.data_ptr(), lvl.data_ptr()
             d.bins_out = self.bins[s].data_ptr() if want_bins else None
             d.values_out = self.values[s].data_ptr() if want_values else None
@@ -130,20 +130,20 @@ class FusionPlan:
         self._graph_e2e: Optional[torch.cuda.CUDAGraph] = None
         self._pinned = None
         has_pages, has_8 = any(s > 8 for s in self.scales), 8 in self.scales
-        # sparsify + compact-page ALS (page scales), dense ALS (8x8 maps and the page fallback), select, fused tail
-        self.launches_per_run = (2 if has_pages else 0) + (2 if self.scales else 0) + 1
+        # sparsify + compact-page ALS (page scales), dense ALS (8x8 maps and the page fallback), fused tail
+        self.launches_per_run = (2 if has_pages else 0) + (1 if self.scales else 0) + 1
 
     @staticmethod
     def phase_masks() -> Dict[str, int]:
         """The ALS launches by `rdm_als_fused_phases` mask bit (bench.py times them one by one)."""
-        return {"als_sparsify": 4, "als_sparse": 8, "als_dense": 16, "als_select": 2}
+        return {"als_sparsify": _cabi.PHASE_SPARSIFY, "als_sparse": _cabi.PHASE_PAGES, "als_dense": _cabi.PHASE_DENSE}
 
     @staticmethod
     def kernel_names() -> Dict[str, str]:
         return {"als_sparsify": "als_sparsify_raw_kernel / als_sparsify_map_kernel (structure check + Lloyd: reads every raw pair matrix once)",
-                "als_sparse": "als_sparse_kernel (100 ALS iterations per page on the compact form, one warp per page)",
-                "als_dense": "als_kernel<0> (dense ALS: the 8x8 maps and any page matrix without pair structure)",
-                "als_select": "als_kernel<1> (batch-wide arg-min, normalise, re-tile)",
+                "als_sparse": "als_pages_kernel (100 ALS iterations per page on the compact form, one CTA per (batch, page), one warp per "
+                              "image, batch-wide arg-min + normalise + re-tile inside)",
+                "als_dense": "als_kernel (dense ALS of the 8x8 maps, one cluster per batch, arg-min inside; fallback for pages without pair structure)",
                 "fuse_tail": "fuse_tail_kernel (decompose + combine + recombine)"}
 
     def _views(self, buf: torch.Tensor):
@@ -154,12 +154,11 @@ class FusionPlan:
     def run(self, overlap: Optional[bool] = None) -> torch.Tensor:
         """Enqueue the whole path on the current stream; returns the (N,1,128,128) f64 log-depth buffer.
 
-        After the compact page form is built (phase bit 4) the iterate phase is two independent launches -
-        the ALS on the compact pages (bit 8) and the dense ALS of the 8x8 maps plus the fallback for pages
-        without pair structure (bit 16, reads the flags bit 4 wrote) - so with `overlap` the dense launch goes
-        to a side stream that forks from and joins the current one (plain events: capturable into a CUDA
-        graph, where it becomes two parallel branches).  The select launch needs both.  Measured on B200
-        (batch 16, scales 8/16/32): one step alone 103 -> 77 us, but with 16 batches in flight 7 % FEWER maps/s
+        After the compact page form is built (PHASE_SPARSIFY) the ALS on the compact pages (PHASE_PAGES) and the
+        dense ALS of the 8x8 maps plus the fallback for pages without pair structure (PHASE_DENSE, reads the flags
+        the sparsify launch wrote) are independent launches - so with `overlap` the dense launch goes to a side
+        stream that forks from and joins the current one (plain events: capturable into a CUDA graph, where it
+        becomes two parallel branches).  It shortens one call alone but costs throughput with many calls in flight
         (the join costs more than the idle SMs it fills), so it is off unless the plan was built with
         `overlap=True` (latency-bound callers)."""
         with self._guard():
@@ -190,18 +189,16 @@ class FusionPlan:
                 if self._side is None:
                     self._side = torch.cuda.Stream(self.device)
                 side = self._side
-                check(lib.rdm_als_fused_phases(descs, n, self.N, self.group, 4, st), "rdm_als_fused_phases")
+                check(lib.rdm_als_fused_phases(descs, n, self.N, self.group, _cabi.PHASE_SPARSIFY, st), "rdm_als_fused_phases")
                 side.wait_stream(cur)
-                check(lib.rdm_als_fused_phases(descs, n, self.N, self.group, 16, c_void_p(side.cuda_stream)), "rdm_als_fused_phases")
-                check(lib.rdm_als_fused_phases(descs, n, self.N, self.group, 8, st), "rdm_als_fused_phases")
+                check(lib.rdm_als_fused_phases(descs, n, self.N, self.group, _cabi.PHASE_DENSE, c_void_p(side.cuda_stream)), "rdm_als_fused_phases")
+                check(lib.rdm_als_fused_phases(descs, n, self.N, self.group, _cabi.PHASE_PAGES, st), "rdm_als_fused_phases")
                 cur.wait_stream(side)
-                check(lib.rdm_als_fused_phases(descs, n, self.N, self.group, 2, st), "rdm_als_fused_phases")
             else:
                 check(lib.rdm_als_fused(descs, n, self.N, self.group, st), "rdm_als_fused")
 
     def run_als_phase(self, phase_mask: int) -> None:
-        """Only the ALS launches selected by phase_mask (1 = iterate, 2 = select): used by bench.py to
-        time the dominant kernel alone."""
+        """Only the ALS launches selected by phase_mask (`_cabi.PHASE_*`): used by bench.py to time the kernels one by one."""
         with self._guard():
             st = c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
             check(self.lib.rdm_als_fused_phases(self._descs, len(self.scales), self.N, self.group, phase_mask, st), "rdm_als_fused_phases")

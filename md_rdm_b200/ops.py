@@ -206,13 +206,14 @@ _KIND_DTYPE = {_cabi.SRC_RAW_F64: torch.float64, _cabi.SRC_RAW_F32: torch.float3
 
 @torch.library.custom_op("rdm::als_rank1", mutates_args=())
 def als_rank1(src: Tensor, kind: int, rows: int, side: int, limit: int, group: int, thresholds: Optional[Tensor],
-              levels: Optional[Tensor], want_bins: bool, want_values: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+              levels: Optional[Tensor], want_bins: bool, want_values: bool, flags: int = 0) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
     """Lloyd (optional) + rank-1 ALS + batch-wide arg-min + gm normalisation + re-tiling for ONE
     scale (RN:358-396 minus DORN; CP:38-85, CP:95-155, CP:218-238).
 
     src: kind RAW_*/VAL_*: (N,P,rows,64) (or (N,rows,64) when P == 1); kind MAP_F32: (N,1,side,side).
     Returns (map (N,1,side,side) f32, pages (N,P,rows) f32, rmse record (N/group,P,limit+1) f32,
-    kstar (N/group,P) i32, bins u8 (N,P,rows,64) or empty, values f32 (N,P,rows,64) or empty)."""
+    kstar (N/group,P) i32, bins u8 (N,P,rows,64) or empty, values f32 (N,P,rows,64) or empty).
+    flags: `_cabi.ALS_*` bits (rdm_als_scale_t.flags); 0 = the reference's behaviour."""
     _need_cuda("als_rank1", src, thresholds, levels)
     if src.dtype != _KIND_DTYPE[kind]:
         raise RuntimeError(f"rdm::als_rank1: src dtype {src.dtype} does not match kind {kind}")
@@ -232,7 +233,7 @@ def als_rank1(src: Tensor, kind: int, rows: int, side: int, limit: int, group: i
     kstar = torch.empty((G, P), dtype=torch.int32, device=dev)
     bins = torch.empty((N, P, rows, 64) if want_bins else (0,), dtype=torch.uint8, device=dev)
     values = torch.empty((N, P, rows, 64) if want_values else (0,), dtype=torch.float32, device=dev)
-    sc = AlsScale(src=s.data_ptr(), src_kind=kind, rows=rows, pages=P, side=side, limit=limit, reserved=0,
+    sc = AlsScale(src=s.data_ptr(), src_kind=kind, rows=rows, pages=P, side=side, limit=limit, flags=int(flags),
                   thresholds=thresholds.data_ptr() if thresholds is not None else None,
                   levels=levels.data_ptr() if levels is not None else None,
                   bins_out=bins.data_ptr() if want_bins else None, values_out=values.data_ptr() if want_values else None,
@@ -244,7 +245,7 @@ def als_rank1(src: Tensor, kind: int, rows: int, side: int, limit: int, group: i
 
 
 @als_rank1.register_fake
-def _(src, kind, rows, side, limit, group, thresholds, levels, want_bins, want_values):
+def _(src, kind, rows, side, limit, group, thresholds, levels, want_bins, want_values, flags=0):
     P = 1 if rows == 64 else (side // 16) ** 2
     per = side * side if kind == _cabi.SRC_MAP_F32 else P * rows * 64
     N = src.numel() // per
@@ -704,7 +705,7 @@ def _zero_setup_2(ctx, inputs, output):
 
 pair_pages.register_autograd(_zero_grad_backward(2, 2), setup_context=_zero_setup_2)
 lloyd_quantize.register_autograd(_zero_grad_backward(1, 3), setup_context=_zero_setup_1)
-als_rank1.register_autograd(_zero_grad_backward(1, 10), setup_context=_zero_setup_1)
+als_rank1.register_autograd(_zero_grad_backward(1, 11), setup_context=_zero_setup_1)
 
 
 # ============================================================================ SURVEY 8f "next": DORN head + ordinal loss

@@ -30,8 +30,9 @@ def test_abi_version_and_sizes(lib):
     assert lib.rdm_pyramid_len(128, 0) == 21845
     assert lib.rdm_pyramid_len(8, 1) == 84
     assert lib.rdm_pyramid_len(12, 0) == -1
-    assert lib.rdm_als_ws_floats(256, 4, 100) == 4 * (104 + 100 * 256 + 256 * 16 + 4)   # record (padded), iterates, compact page form, band flags
-    assert lib.rdm_als_ws_floats(64, 1, 30) == 31 + 30 * 64
+    assert lib.rdm_als_ws_floats(256, 4, 100) == 4 * (256 * 16 + 8)   # compact page form + band flags (no iterate history)
+    assert lib.rdm_als_ws_floats(256, 4, 100) <= 4 * 4300
+    assert lib.rdm_als_ws_floats(64, 1, 30) == 32                     # the unit's SSE record
     sides = (ctypes.c_int32 * 3)(8, 16, 32)
     assert lib.rdm_fuse_tail_weight_count(sides, 3) == 4 + 3 + 4 + 5
     assert ctypes.sizeof(_cabi.AlsScale) == 8 + 6 * 4 + 9 * 8
@@ -56,8 +57,12 @@ def test_argument_errors_do_not_launch(lib):
     rc = lib.rdm_als_fused(sc, 1, 4, 4, null)
     assert rc < 0 and b"ws must be 16-byte aligned" in lib.rdm_last_error()
     sc.ws = 16
-    rc = lib.rdm_als_fused_phases(sc, 1, 4, 4, 32, null)
+    rc = lib.rdm_als_fused_phases(sc, 1, 4, 4, 8, null)
     assert rc < 0 and b"phase_mask" in lib.rdm_last_error()
+    sc.flags = 64
+    rc = lib.rdm_als_fused(sc, 1, 4, 4, null)
+    assert rc < 0 and b"unknown flag bits" in lib.rdm_last_error()
+    sc.flags = 0
     # empty batches are a no-op, not an error
     assert lib.rdm_pair_v1_f32(one, 0, one, null) == 0
     assert lib.rdm_als_fused(sc, 1, 0, 4, null) == 0
