@@ -149,10 +149,11 @@ int rdm_als_fused(const rdm_als_scale_t* scales, int32_t n_scales, int64_t n_ima
  * ordered by an event); they are independent of each other. */
 int rdm_als_fused_phases(const rdm_als_scale_t* scales, int32_t n_scales, int64_t n_images,
                          int32_t group, int32_t phase_mask, rdm_stream_t stream);
-/* Host-side copy of the geometry tables the compact-page kernels use (RN:266-273 + CP:269-295 window
- * anchoring), for tests: lane_slots u64[2*6*32], item u16[2*96], compact u8[16*16] (see
- * md_rdm_b200/csrc/rdm_als_sparse.cu: SparsifyTables).  No device work. */
-int rdm_sparsify_geometry(uint64_t* lane_slots, uint16_t* item, uint8_t* compact);
+/* Host-side copy of the compact page form's geometry (RN:266-273 + CP:269-295 window anchoring), for tests:
+ * window_cols i32[256*9] = the nine window columns of every matrix row (row-major over the 3x3 window),
+ * fill_col i32[256] = a column outside every window of that pixel row, compact u8[256*16] = source of each
+ * entry of the 16-float compact row (0..8 window slot minus f, 9 = f, 15 = zero).  No device work. */
+int rdm_sparsify_geometry(int32_t* window_cols, int32_t* fill_col, uint8_t* compact);
 /* f32 workspace elements per image for one scale (rdm_als_scale_t.ws) */
 int64_t rdm_als_ws_floats(int32_t rows, int32_t pages, int32_t limit);
 

@@ -82,145 +82,200 @@ __device__ __forceinline__ void load_book(const SparseScaleDev& sc, double* thr_
 }
 
 // ---------------------------------------------------------------------------------------------
-// Geometry tables of the sparsify kernel (built at compile time).  A warp owns 8 matrix rows = pixels
-// (r, cb..cb+7) of the page, cb in {0, 8}; all share r0 = min(r/2, 5); pixel column c has c0 = min(c/2, 5) and
-// span0 = min(2 (c/4), 4).  "Slot" numbers the 10 informative values of a row: 0..8 the 3x3 window (row-major),
-// 9 the fill value.
-struct SparsifyTables {
-  // lane_slots[cb/8][r0][lane]: byte i = slot of matrix column 2*lane (low nibble) and 2*lane+1 (high nibble) in row i
-  unsigned long long lane_slots[2][6][32];
-  // item[cb/8][id], id = 10 i + slot < 80: index into the row's staging line (0..23 parent rows x columns, 24 fill)
-  // | i << 5 | slot << 8 | valid << 12
-  unsigned short item[2][96];
-  // compact[c][e]: source of entry e of the 16-float compact row of pixel column c: 0..8 window slot (value - f),
-  // 9 the fill value itself, 15 zero
-  unsigned char compact[16][16];
-};
-constexpr SparsifyTables make_sparsify_tables() {
-  SparsifyTables t{};
-  for (int h = 0; h < 2; ++h)
-    for (int r0 = 0; r0 < 6; ++r0)
-      for (int lane = 0; lane < 32; ++lane) {
-        unsigned long long w = 0;
-        for (int i = 0; i < 8; ++i) {
-          const int c = 8 * h + i, c0 = (c >> 1) < 5 ? (c >> 1) : 5;
-          const int a = (lane >> 2) - r0, cc = (2 * lane) & 7;
-          unsigned long long sl[2] = {9, 9};
-          for (int e = 0; e < 2; ++e)
-            if (a >= 0 && a < 3 && cc + e - c0 >= 0 && cc + e - c0 < 3) sl[e] = (unsigned long long)(3 * a + cc + e - c0);
-          w |= (sl[0] | (sl[1] << 4)) << (8 * i);
-        }
-        t.lane_slots[h][r0][lane] = w;
-      }
-  for (int h = 0; h < 2; ++h)
-    for (int id = 0; id < 96; ++id) {
-      if (id >= 80) { t.item[h][id] = 0; continue; }
-      const int i = id / 10, slot = id % 10;
-      const int c = 8 * h + i, c0 = (c >> 1) < 5 ? (c >> 1) : 5;
-      const int src = slot == 9 ? 24 : 8 * (slot / 3) + c0 + slot % 3;
-      t.item[h][id] = (unsigned short)(src | (i << 5) | (slot << 8) | (1 << 12));
-    }
-  for (int c = 0; c < 16; ++c) {
-    const int c0 = (c >> 1) < 5 ? (c >> 1) : 5, span0 = 2 * (c >> 2) < 4 ? 2 * (c >> 2) : 4;
-    for (int e = 0; e < 16; ++e) {
-      unsigned char code = 15;
-      if (e == 0) code = 9;
-      else if (e <= 12) {
-        const int be = span0 + ((e - 1) & 3) - c0;
-        if (be >= 0 && be < 3) code = (unsigned char)(3 * ((e - 1) >> 2) + be);
-      }
-      t.compact[c][e] = code;
-    }
+// Geometry of a page row rho = 16 r + c (RN:266-273 + CP:269-295): the 3x3 window of the 8x8 parent page is anchored
+// at (r0, c0) = (min(r/2,5), min(c/2,5)); the compact row keeps it as a 3 x 4 span starting at the even column
+// span0 = min(2 (c/4), 4).
+struct RowGeom {
+  int r0, c0, span0;
+  __host__ __device__ __forceinline__ explicit RowGeom(int rho) {
+    const int r = rho >> 4, c = rho & 15;
+    r0 = (r >> 1) < 5 ? (r >> 1) : 5;
+    c0 = (c >> 1) < 5 ? (c >> 1) : 5;
+    span0 = 2 * (c >> 2) < 4 ? 2 * (c >> 2) : 4;
   }
-  return t;
-}
-__device__ const SparsifyTables kSparsifyTables = make_sparsify_tables();
+  __host__ __device__ __forceinline__ int window_col(int a, int b) const { return 8 * (r0 + a) + c0 + b; }
+  // a matrix column outside every window of this pixel row: parent row 0 unless the window starts there, else row 7
+  __host__ __device__ __forceinline__ int fill_col() const { return r0 >= 1 ? 0 : 56; }
+};
 
-// grid = units x 4 bands of 64 rows; a warp owns 8 rows, a lane two adjacent matrix columns of each.  Only 10
-// values per row carry information, so after the bit-wise structure check the warp gathers those 80 values
-// through shared memory and quantises them in three full-warp passes instead of quantising 512 values in
-// sixteen.  The per-lane geometry comes from kSparsifyTables (three small loads per warp).
-__global__ void __launch_bounds__(256) als_sparsify_raw_kernel(const __grid_constant__ SparseParams P) {
+// ---- mbarrier / bulk-copy (TMA) primitives --------------------------------------------------------------
+__device__ __forceinline__ uint32_t sm_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n"
+      "W_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@!p bra W_%=;\n\t}"
+      ::"r"(bar), "r"(parity) : "memory");
+}
+// 1-D bulk async copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- the HBM-streaming kernel of the path ----------------------------------------------------------------
+// Work item = one band of 64 matrix rows (32 KB of f64, contiguous in HBM) = one CTA of 64 threads; six CTAs fit an
+// SM, so ~190 KB of loads are in flight per SM.  Thread 0 issues ONE 32 KB bulk async copy (cp.async.bulk = TMA,
+// 1-D) that completes on an mbarrier; the codebook is fetched while it flies.  The 64 threads then own ONE ROW
+// EACH, with no cross-lane traffic:
+//   * read the fill value and the nine window values of the row (their columns follow from the row index);
+//   * overwrite the nine window entries of the staged row with the fill value, then compare all 64 entries with
+//     the fill value bit-wise (two LOP3 per entry): any difference = the row lacks the pair-build structure;
+//   * quantise the 10 informative values (f64 compares, RN:376-378), emit the 16-float compact row, and - if
+//     asked - the row of bins / quantised values, which are fill or window values by construction (assembled in
+//     the row's own staging bytes and copied out by the warp with 128-bit stores).
+// Shared-memory banks: rows are 512 bytes apart, i.e. on the same banks (a padded layout needs one bulk copy per
+// row, and 64 small copies per band are request-rate bound: measured 2.6 TB/s).  So (i) thread t walks the 16-byte
+// chunks of its row in the order c ^ t, and keeps logical output chunk k at position k ^ t: at every step the
+// lanes of a warp touch 32 different chunks; (ii) the rows of a band are dealt to the two warps so that each
+// warp holds every residue rho mod 32 once AND at most 3 rows per half-warp share a window position (a warp
+// of 32 consecutive rows would have 12): lane l of warp w takes pixel column c = l & 15 of pixel row
+// 4 band + (l >> 4) + 2 ((c ^ (l >> 4) ^ w) & 1).
+// About 12 warp-instructions per matrix row (the round-1 kernel, in which a warp shared a row: 92).
+constexpr int kBandRows = 64;
+constexpr int kRowBytes = 512;                 // 64 f64
+constexpr int kStageBytes = kBandRows * kRowBytes;
+
+__global__ void __launch_bounds__(kBandRows) als_sparsify_raw_kernel(const __grid_constant__ SparseParams P) {
+  extern __shared__ __align__(128) unsigned char stage[];
   __shared__ double thr_d[kThrPad];
   __shared__ float lvl_f[kLvl + 3];
   __shared__ int sorted;
-  __shared__ __align__(16) double stage[8][8][26];   // per warp, per row: 3 parent rows x 8 columns, then the fill value
-  __shared__ float resv[8][8][12];                   // quantised values by slot
-  __shared__ uint8_t resb[8][8][16];                 // their bins
+  __shared__ __align__(8) unsigned long long full_bar;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gunit = blockIdx.x >> 2, band = blockIdx.x & 3;
   const SparseScaleDev& sc = find_scale(P, gunit);
   const int64_t unit = gunit - sc.unit_begin;
   const bool quant = sc.kind == RDM_SRC_RAW_F64;
-  const int64_t mat_off = unit * (int64_t)(256 * 64);
-  const int row0 = band * 64 + warp * 8;             // rows row0 .. row0+7: pixel row row0 >> 4, columns cb .. cb+7
-  const double* src = reinterpret_cast<const double*>(sc.src) + mat_off + row0 * 64 + 2 * lane;
-  double2 x[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) x[i] = ldg_stream_f64x2(src + i * 64);
-  const int r0 = min(row0 >> 5, 5), h = (row0 >> 3) & 1;
-  const unsigned long long slots = kSparsifyTables.lane_slots[h][r0][lane];
-  const unsigned it0 = kSparsifyTables.item[h][lane], it1 = kSparsifyTables.item[h][32 + lane], it2 = kSparsifyTables.item[h][64 + lane];
-  const unsigned centry = *reinterpret_cast<const unsigned*>(&kSparsifyTables.compact[8 * h + (lane >> 2)][4 * (lane & 3)]);
-  if (quant) load_book(sc, thr_d, lvl_f, &sorted, tid, 256);
-  float* compact = sc.ws + unit * als_ws_stride(256, sc.limit);
+  if (tid == 0) {
+    mbar_init(sm_addr(&full_bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(sc.src) + (unit * 256 + band * kBandRows) * (int64_t)kRowBytes;
+    mbar_expect_tx(sm_addr(&full_bar), kStageBytes);
+    bulk_g2s(sm_addr(stage), src, kStageBytes, sm_addr(&full_bar));
+  }
+  if (quant) load_book(sc, thr_d, lvl_f, &sorted, tid, kBandRows);   // ends with __syncthreads
+  else __syncthreads();                                              // the mbarrier is initialised for everyone
   const int srt = quant ? sorted : 1;
-  const int lane_f = (r0 >= 1) ? 0 : 28;             // column 0 / 56 is outside every window of this pixel row
-  const int a = (lane >> 2) - r0;
-  const bool rowin = (unsigned)a < 3u;
-  double* my_stage = &stage[warp][0][rowin ? 8 * a + ((2 * lane) & 7) : 24];
-  const unsigned slo = (unsigned)slots, shi = (unsigned)(slots >> 32);
-  bool ok = true;
+  // ---- this thread's row
+  const int c = lane & 15, hi = lane >> 4;
+  const int rho = band * kBandRows + 16 * (hi + 2 * ((c ^ hi ^ warp) & 1)) + c;   // matrix row = pixel of the page; rho % 32 == lane
+  const RowGeom gm(rho);
+  const uint32_t rot = (uint32_t)lane << 4;   // chunk rotation of this thread (bytes)
+  unsigned char* rb = stage + (rho & (kBandRows - 1)) * kRowBytes;
+  double* row = reinterpret_cast<double*>(rb);
+  mbar_wait(sm_addr(&full_bar), 0);
+  // ---- informative values: fill + 3x3 window; then the structure check on the neutralised row.  The fill value
+  // is read from one of the eight columns of a parent row outside the window (spread over the lanes)
+  const double F = row[gm.fill_col() + (lane & 7)];
+  double wv[9];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const unsigned sb = ((i < 4 ? slo : shi) >> (8 * (i & 3))) & 0xffu;   // slots of this lane's two columns in row i
-    const long long b0 = __double_as_longlong(x[i].x), b1 = __double_as_longlong(x[i].y);
-    const long long fb = __shfl_sync(kFull, b0, lane_f);
-    ok = ok && ((sb & 15u) != 9u || b0 == fb) && ((sb >> 4) != 9u || b1 == fb);
-    if (rowin) *reinterpret_cast<double2*>(my_stage + 26 * i) = x[i];
-    else if (lane == lane_f) my_stage[26 * i] = x[i].x;
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      double* e = row + gm.window_col(a, b);
+      wv[3 * a + b] = *e;
+      *e = F;
+    }
+  const unsigned Flo = (unsigned)__double2loint(F), Fhi = (unsigned)__double2hiint(F);
+  unsigned diff = 0;
+#pragma unroll 8
+  for (int k = 0; k < 32; ++k) {
+    const uint4 x = *reinterpret_cast<const uint4*>(rb + (((uint32_t)k << 4) ^ rot));
+    diff |= (x.x ^ Flo) | (x.y ^ Fhi);
+    diff |= (x.z ^ Flo) | (x.w ^ Fhi);
   }
-  __syncwarp();
-  auto quantise_item = [&](unsigned g) {
-    if (g & 0x1000u) {
-      const int i = (g >> 5) & 7, slot = (g >> 8) & 15;
-      const double v = stage[warp][i][g & 31u];
-      int q = 0;
-      float lv;
-      if (quant) {
-        q = lloyd_bin<double>(v, thr_d, srt);
-        lv = lvl_f[q];
-      } else {
-        lv = (float)v;   // `.float()` CP:106
+  const bool ok = diff == 0;
+  // ---- Lloyd (f64 compares) of the 10 values, or `.float()` of an already quantised matrix (CP:106)
+  int bf = 0, wb[9];
+  float f, wl[9];
+  if (quant) {
+    bf = lloyd_bin<double>(F, thr_d, srt);
+    f = lvl_f[bf];
+#pragma unroll
+    for (int w = 0; w < 9; ++w) {
+      wb[w] = lloyd_bin<double>(wv[w], thr_d, srt);
+      wl[w] = lvl_f[wb[w]];
+    }
+  } else {
+    f = (float)F;
+#pragma unroll
+    for (int w = 0; w < 9; ++w) {
+      wb[w] = 0;
+      wl[w] = (float)wv[w];
+    }
+  }
+  // ---- compact row: f, then the 3 x 4 span of (window value - f), zero outside the window
+  float* compact = sc.ws + unit * als_ws_stride(256, sc.limit);
+  {
+    float o[16];
+    o[0] = f;
+    o[13] = o[14] = o[15] = 0.f;
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int b = gm.span0 + g - gm.c0;   // window column of span column g
+        float v = 0.f;
+#pragma unroll
+        for (int bb = 0; bb < 3; ++bb)
+          if (b == bb) v = wl[3 * a + bb] - f;
+        o[1 + 4 * a + g] = v;
       }
-      resv[warp][i][slot] = lv;
-      resb[warp][i][slot] = (uint8_t)q;
-    }
-  };
-  quantise_item(it0);
-  quantise_item(it1);
-  quantise_item(it2);
-  __syncwarp();
-  {   // compact form: 8 rows x 16 floats, one float4 per lane
-    const int i = lane >> 2;
-    const float f = resv[warp][i][9];
-    float o[4];
 #pragma unroll
-    for (int e4 = 0; e4 < 4; ++e4) {
-      const unsigned code = (centry >> (8 * e4)) & 15u;
-      const float wv = resv[warp][i][code == 15u ? 9 : code];
-      o[e4] = code == 9u ? f : (code == 15u ? 0.f : wv - f);
-    }
-    *reinterpret_cast<float4*>(compact + (row0 + i) * kCompactRowFloats + 4 * (lane & 3)) = make_float4(o[0], o[1], o[2], o[3]);
+    for (int k = 0; k < 4; ++k)
+      *reinterpret_cast<float4*>(compact + rho * kCompactRowFloats + 4 * k) = make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
   }
+  // ---- optional full-size outputs, assembled in the row's own staging bytes: logical chunks 0..3 = the 64 bins,
+  // 4..19 = the 64 quantised values; logical chunk k lives at physical chunk k ^ lane
   if (sc.bins || sc.values) {
+    if (sc.bins) {
+      const unsigned rep = 0x01010101u * (unsigned)bf;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const unsigned sb = ((i < 4 ? slo : shi) >> (8 * (i & 3))) & 0xffu;
-      const int s0 = sb & 15u, s1 = sb >> 4;
-      const int64_t off = mat_off + (row0 + i) * 64 + 2 * lane;
-      if (sc.bins) *reinterpret_cast<uint16_t*>(sc.bins + off) = (uint16_t)(resb[warp][i][s0] | (resb[warp][i][s1] << 8));
-      if (sc.values) *reinterpret_cast<float2*>(sc.values + off) = make_float2(resv[warp][i][s0], resv[warp][i][s1]);
+      for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(rb + (((uint32_t)k << 4) ^ rot)) = make_uint4(rep, rep, rep, rep);
+    }
+    if (sc.values) {
+#pragma unroll
+      for (int k = 4; k < 20; ++k) *reinterpret_cast<float4*>(rb + (((uint32_t)k << 4) ^ rot)) = make_float4(f, f, f, f);
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b) {
+        const uint32_t col = (uint32_t)gm.window_col(a, b);
+        if (sc.bins) rb[((col & ~15u) ^ rot) | (col & 15u)] = (unsigned char)wb[3 * a + b];
+        if (sc.values) *reinterpret_cast<float*>(rb + ((((64u + 4u * col) & ~15u) ^ rot) | ((4u * col) & 15u))) = wl[3 * a + b];
+      }
+    __syncwarp();
+    // copy-out by the warp: the row of lane l' sits at its own rotation l'
+    const int64_t mrow0 = unit * 256 + band * kBandRows;   // first matrix row of the band
+    auto row_of = [&](uint32_t l2) {                        // band-local row held by lane l2 of this warp
+      const uint32_t c2 = l2 & 15, h2 = l2 >> 4;
+      return 16 * (h2 + 2 * ((c2 ^ h2 ^ (uint32_t)warp) & 1)) + c2;
+    };
+    if (sc.bins) {   // 64 B per row: a 128-bit store instruction covers 8 rows
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const uint32_t l2 = 8 * it + (lane >> 2), ch = lane & 3, r2 = row_of(l2);
+        const uint4 x = *reinterpret_cast<const uint4*>(stage + r2 * kRowBytes + ((ch ^ l2) << 4));
+        *reinterpret_cast<uint4*>(sc.bins + (mrow0 + r2) * 64 + 16 * ch) = x;
+      }
+    }
+    if (sc.values) {   // 256 B per row: an instruction covers 2 rows
+#pragma unroll 4
+      for (int it = 0; it < 16; ++it) {
+        const uint32_t l2 = 2 * it + (lane >> 4), ch = lane & 15, r2 = row_of(l2);
+        const float4 x = *reinterpret_cast<const float4*>(stage + r2 * kRowBytes + (((4 + ch) ^ l2) << 4));
+        *reinterpret_cast<float4*>(sc.values + (mrow0 + r2) * 64 + 4 * ch) = x;
+      }
     }
   }
   const int all_ok = __syncthreads_and(ok ? 1 : 0);
@@ -341,22 +396,27 @@ __device__ __forceinline__ float row_dot(const float (&D)[12], const float (&v)[
 // images whose rmse the reference averages (CP:172-173) meet in ONE CTA and the arg-min (CP:143) is taken while
 // the iterations run: nothing but the selected iterate ever leaves the SM.
 //
-//  * Iteration k of a warp leaves its 32 per-lane residuals in E[k % 3][warp][lane] and ARRIVES (bar.arrive, no
-//    wait) on named barrier 1 + k % 3.
-//  * Warp (k % W) is the reducer of iteration k: at the top of its step k+1 it waits for the arrivals
-//    (bar.sync on the same barrier), sums the group's residuals (f64), takes the rmse, compares it with the
-//    running minimum (strict <: the FIRST minimum wins, as list.index(min(list)) does) and publishes
-//    flag[k % 3] = 2 k + new_minimum.
-//  * Every warp reads the verdict on iteration k at the end of its step k + kLag, and on a new minimum copies
-//    p_k from its 3-deep ring of iterates into its `best` row.  The flag wait also bounds the skew between the
-//    warps, which is what makes the 3-deep rings and the 3 barriers safe to reuse (see the ordering argument
-//    in DESIGN.md 4.1).
-// Groups of more than 16 images take kRounds rounds of 16 warps: pass 1 accumulates the group record over the
+//  * Step k of a warp (iteration k) leaves its 32 per-lane residuals in E[k & 3][warp][lane] and ARRIVES (bar.arrive,
+//    no wait) on named barrier 1 + (k & 3).
+//  * Warp (j % W) is the reducer of iteration j: at the top of its step j + 2 - when every warp has normally long
+//    arrived - it completes the barrier (bar.sync), sums the group's residuals (f64), takes the rmse, compares it
+//    with the running minimum (strict <: the FIRST minimum wins, as list.index(min(list)) does) and publishes
+//    flag[j & 3] = 2 j + new_minimum.
+//    Verdicts are issued in iteration order: the reducer of j waits for the verdict on j - 1 (another warp's,
+//    possibly a step behind) before it touches the running minimum.
+//  * Every warp reads the verdict on iteration j at the end of its step j + kLag (= j + 3), and on a new minimum
+//    copies p_j from its 4-deep ring of iterates into its `best` row.
+// Why the 4-deep rings and 4 barriers can be reused: a warp enters step k only after it has read the verdict on
+// iteration k - 4 (end of step k - 1), and that verdict is published after the reducer completed barrier (k-4) & 3 and
+// read E[(k-4) & 3]; so the arrival on barrier k & 3, the store to E[k & 3] and the store to the p ring slot k & 3
+// of step k never meet their previous use.  Every wait refers to a strictly earlier step, so there is no cycle.
+// Groups of more than 16 images take several rounds of 16 warps: pass 1 accumulates the group record over the
 // rounds (no iterate is kept), pass 2 re-runs the k* selected iterations of every unit (bit-identical
 // arithmetic) and emits them.  On noise-like maps k* <= 1, so pass 2 is a few per cent of pass 1.
-constexpr int kLag = 2;
-constexpr int kRing = kLag + 1;
-static_assert(kLag == 2 && kRing == 3, "the ring slot arithmetic of pages_iterate assumes a lag of 2");
+constexpr int kLag = 3;
+constexpr int kRing = 4;
+constexpr int kRedDelay = 2;   // the reducer of iteration j works at the top of its step j + kRedDelay
+static_assert(kRing == kLag + 1 && (kRing & (kRing - 1)) == 0 && kRedDelay < kLag, "ring arithmetic of pages_iterate");
 constexpr int kGroupWarps = 16;
 constexpr int kWarpFloats = kRing * 256 + 64 + 256;   // p ring, q, best
 constexpr int kMaxLimit = 127;
@@ -379,7 +439,7 @@ struct PagesParams {
 struct PagesShared {            // fixed part of the dynamic shared memory (the per-warp rows follow)
   float E[kRing][kGroupWarps][32];
   double recg[kMaxLimit + 1];   // group record accumulated over the rounds (multi-round groups)
-  unsigned flag[kRing];
+  int flag[kRing];              // verdicts: 2 j + new_minimum, -1 before the first use
   float best_rmse;
   int kstar;
   int all_compact;
@@ -387,10 +447,37 @@ struct PagesShared {            // fixed part of the dynamic shared memory (the 
 
 __device__ __forceinline__ void named_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void named_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
-__device__ __forceinline__ unsigned ld_volatile_u32(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory");
+// shared-memory accesses of the iteration loop by 32-bit shared address (generic pointers make nvcc re-derive the
+// shared window base inside the loop, see rdm_als.cu)
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float2 s_ld2(uint32_t a) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a) : "memory");
   return v;
+}
+__device__ __forceinline__ float4 s_ld4(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void s_st4(uint32_t a, float x, float y, float z, float w) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+__device__ __forceinline__ void s_st1(uint32_t a, float x) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(x) : "memory"); }
+__device__ __forceinline__ int s_ld_flag(uint32_t a) {
+  int v;
+  asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void load_span_u32(uint32_t a, float (&v)[12]) {
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const float2 lo = s_ld2(a + 32 * r), hi = s_ld2(a + 32 * r + 8);
+    v[4 * r] = lo.x;
+    v[4 * r + 1] = lo.y;
+    v[4 * r + 2] = hi.x;
+    v[4 * r + 3] = hi.y;
+  }
 }
 
 // The matrix of one page in registers: a lane owns the 2 x 4 pixel block (rows 2rh..2rh+1, columns 4kq..4kq+3)
@@ -398,6 +485,58 @@ __device__ __forceinline__ unsigned ld_volatile_u32(const unsigned* p) {
 struct PageRegs {
   float f[8], D[8][12];
 };
+
+// The reducer's work for iteration j (one warp, all lanes): complete the barrier of iteration j, group rmse,
+// first-minimum test (DECIDE) or accumulation into the multi-round record, verdict.  Out of line: it runs once per W
+// steps of a warp and would otherwise sit in the instruction stream of the iteration loop.
+template <bool DECIDE>
+__device__ __noinline__ void pages_reduce(PagesShared& sh, int j, int W, int lane, double inv_cnt, float* record_out) {
+  const int slot = j & (kRing - 1);
+  named_sync(1 + slot, (W + 1) * 32);
+  const int u = lane & 15, h = lane >> 4;
+  double t = 0.0;
+  if (u < W) {
+    const float4* e4 = reinterpret_cast<const float4*>(&sh.E[slot][u][16 * h]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 x = e4[i];
+      t += (double)x.x;
+      t += (double)x.y;
+      t += (double)x.z;
+      t += (double)x.w;
+    }
+  }
+  t += __shfl_xor_sync(kFull, t, 16);
+  // unit record rounded to f32, then the group sum in f64 (the reference sums f32 values; exact in f64)
+  double g = (h == 0 && u < W) ? (double)(float)t : 0.0;
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) g += __shfl_xor_sync(kFull, g, o);
+  if (lane == 0) {
+    int verdict = j << 1;
+    // Decisions are taken in iteration order: the reducer of iteration j - 1 is another warp and may be a step
+    // behind this one (its arrival on THIS barrier came before its own reduction), so wait for its verdict -
+    // published after its update of the running minimum - before reading the minimum.
+    if (j > 0) {
+      const uint32_t fa = s_u32(&sh.flag[(j - 1) & (kRing - 1)]);
+      while (s_ld_flag(fa) < 2 * (j - 1)) {
+      }
+    }
+    if (DECIDE) {
+      const float rm = (float)sqrt(g * inv_cnt);           // CP:172-173 over the whole reference batch
+      if (rm < sh.best_rmse) {                             // strict: the first minimum wins (CP:143)
+        sh.best_rmse = rm;
+        sh.kstar = j;
+        verdict |= 1;
+      }
+      if (record_out) record_out[j] = rm;
+    } else {
+      sh.recg[j] += g;
+    }
+    __threadfence_block();
+    *reinterpret_cast<volatile int*>(&sh.flag[slot]) = verdict;
+  }
+  __syncwarp();
+}
 
 // MODE 0: record + online arg-min (single-round groups); MODE 1: record only, accumulated into sh.recg
 // (multi-round groups, pass 1); MODE 2: no record, n_iter iterations, the last iterate is returned in p_out
@@ -418,6 +557,20 @@ __device__ __forceinline__ void pages_iterate(const PageRegs& M, PagesShared& sh
   constexpr bool RECORD = MODE != 2;
   const float (&f)[8] = M.f;
   const float (&D)[8][12] = M.D;
+  // 32-bit shared addresses of everything the loop touches
+  // (made opaque to the compiler: left alone it re-derives them from %tid inside the loop - five S2R and some forty
+  // integer instructions per iteration - rather than keep them in registers)
+  auto keep = [](uint32_t x) {
+    asm volatile("mov.b32 %0, %0;" : "+r"(x));
+    return x;
+  };
+  const uint32_t a_ps = keep(s_u32(ps)), a_qs = s_u32(qs);
+  const uint32_t a_qspan = keep(a_qs + 4 * sp);
+  const uint32_t o_s0 = keep(4 * off_s[0]), o_s1 = keep(4 * off_s[1]), o_span = 4 * sp;
+  const uint32_t a_q0 = keep(a_qs + 4 * (off_s[0] >> 2)), a_q1 = keep(a_qs + 4 * (off_s[1] >> 2));   // q index of row rho is rho >> 2
+  const uint32_t a_E = keep(s_u32(&sh.E[0][warp][lane]));
+  const uint32_t a_flag = s_u32(&sh.flag[0]);
+  const uint32_t a_best = s_u32(best);
 
   float A = 0.f;
   if (RECORD) {
@@ -437,90 +590,42 @@ __device__ __forceinline__ void pages_iterate(const PageRegs& M, PagesShared& sh
       e0 += acc;
     }
     A = (float)asum;
-    sh.E[0][warp][lane] = (float)e0;
+    s_st1(a_E, (float)e0);
     named_arrive(1, nbar);
   }
 
-  // the reducer's work for iteration j (one warp, all lanes): group rmse, first-minimum test, verdict
-  auto reduce_iteration = [&](int j) {
-    const int slot = j % kRing;   // once per W iterations per warp
-    named_sync(1 + slot, nbar);
-    const int u = lane & 15, h = lane >> 4;
-    double t = 0.0;
-    if (u < W) {
-      const float4* e4 = reinterpret_cast<const float4*>(&sh.E[slot][u][16 * h]);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float4 x = e4[i];
-        t += (double)x.x;
-        t += (double)x.y;
-        t += (double)x.z;
-        t += (double)x.w;
-      }
-    }
-    t += __shfl_xor_sync(kFull, t, 16);
-    // unit record rounded to f32, then the group sum in f64 (the reference sums f32 values; exact in f64)
-    double g = (h == 0 && u < W) ? (double)(float)t : 0.0;
-#pragma unroll
-    for (int o = 8; o > 0; o >>= 1) g += __shfl_xor_sync(kFull, g, o);
-    g = __shfl_sync(kFull, g, 0);
-    unsigned verdict = (unsigned)j << 1;
-    if (MODE == 0) {
-      const float rm = (float)sqrt(g * inv_cnt);           // CP:172-173 over the whole reference batch
-      bool better = false;
-      if (lane == 0) {
-        better = rm < sh.best_rmse;                        // strict: the first minimum wins (CP:143)
-        if (better) {
-          sh.best_rmse = rm;
-          sh.kstar = j;
-        }
-        if (record_out) record_out[j] = rm;
-      }
-      verdict |= better ? 1u : 0u;
-    } else if (lane == 0) {
-      sh.recg[j] += g;
-    }
-    __syncwarp();
-    if (lane == 0) {
-      __threadfence_block();
-      *reinterpret_cast<volatile unsigned*>(&sh.flag[slot]) = verdict;
-    }
-  };
-  auto await_verdict = [&](int j, int slot) -> bool {
-    const unsigned* fp = &sh.flag[slot];
-    unsigned v;
+  auto keep_if_best = [&](int j) {   // end of step j + kLag: wait for the verdict on iteration j
+    const uint32_t fa = a_flag + 4 * (j & (kRing - 1));
+    int v;
     do {
-      v = ld_volatile_u32(fp);
-    } while ((v >> 1) != (unsigned)j);
-    return (v & 1u) != 0u;
-  };
-  auto keep_if_best = [&](int j, int slot) {   // end of step j + kLag; slot = j % kRing
-    if (await_verdict(j, slot) && MODE == 0) {
+      v = s_ld_flag(fa);
+    } while (v < 2 * j);             // the slot's previous verdict (or -1) is smaller
+    if (MODE == 0 && (v & 1)) {
       if (j == 0) {
-#pragma unroll
-        for (int dr = 0; dr < 2; ++dr) *reinterpret_cast<float4*>(best + off_s[dr]) = make_float4(1.f, 1.f, 1.f, 1.f);
+        s_st4(a_best + o_s0, 1.f, 1.f, 1.f, 1.f);
+        s_st4(a_best + o_s1, 1.f, 1.f, 1.f, 1.f);
       } else {
-        const float* src = ps + slot * 256;
-#pragma unroll
-        for (int dr = 0; dr < 2; ++dr) *reinterpret_cast<float4*>(best + off_s[dr]) = *reinterpret_cast<const float4*>(src + off_s[dr]);
+        const uint32_t src = a_ps + ((j & (kRing - 1)) << 10);
+        const float4 x0 = s_ld4(src + o_s0), x1 = s_ld4(src + o_s1);
+        s_st4(a_best + o_s0, x0.x, x0.y, x0.z, x0.w);
+        s_st4(a_best + o_s1, x1.x, x1.y, x1.z, x1.w);
       }
     }
   };
 
   float qa = 1.0f, qb = 1.0f, m = 1.0f;   // this lane's two entries of q (slot rows >> 2); centre of the q statistics
-  qs[lane] = 1.0f;
-  qs[lane + 32] = 1.0f;
+  s_st1(a_qs + 4 * lane, 1.0f);
+  s_st1(a_qs + 4 * lane + 128, 1.0f);
 #pragma unroll
   for (int t = 0; t < 8; ++t) p_out[t] = 1.0f;
   __syncwarp();
   int next_red = warp;   // next iteration this warp is the reducer of (j % W == warp)
-  int sk = 0;            // k % kRing
   for (int k = 1; k <= n_iter; ++k) {
-    sk = sk == kRing - 1 ? 0 : sk + 1;
-    if (RECORD && k - 1 == next_red) {
-      reduce_iteration(k - 1);
+    if (RECORD && k - kRedDelay == next_red) {
+      pages_reduce<MODE == 0>(sh, next_red, W, lane, inv_cnt, record_out);
       next_red += W;
     }
+    const uint32_t slot = (uint32_t)k & (kRing - 1);
     // ---- statistics of q_{k-1} about m: S1 = sum (q - m), V = sum (q - m)^2
     const float da = qa - m, db = qb - m;
     float S1 = da + db, V = fmaf(da, da, db * db);
@@ -535,7 +640,7 @@ __device__ __forceinline__ void pages_iterate(const PageRegs& M, PagesShared& sh
     // ---- p-update, and the residual of these rows against q_{k-1} (header comment) summed over the rows:
     //      64 sum g^2 + V sum p^2 + A - 2 (S1 sum p g + sum p sD)
     float v[12];
-    load_span(qs + sp, v);
+    load_span_u32(a_qspan, v);
     float p[8], gg = 0.f, pg = 0.f, psd = 0.f, pp = 0.f, psum = 0.f;
     auto p_row = [&](auto tc) {
       constexpr int t = decltype(tc)::value;
@@ -554,13 +659,12 @@ __device__ __forceinline__ void pages_iterate(const PageRegs& M, PagesShared& sh
     p_row(std::integral_constant<int, 2>{}); p_row(std::integral_constant<int, 3>{});
     p_row(std::integral_constant<int, 4>{}); p_row(std::integral_constant<int, 5>{});
     p_row(std::integral_constant<int, 6>{}); p_row(std::integral_constant<int, 7>{});
-    float* pk = ps + sk * 256;
-#pragma unroll
-    for (int dr = 0; dr < 2; ++dr)
-      *reinterpret_cast<float4*>(pk + off_s[dr]) = make_float4(p[4 * dr], p[4 * dr + 1], p[4 * dr + 2], p[4 * dr + 3]);
+    const uint32_t pk = a_ps + (slot << 10);
+    s_st4(pk + o_s0, p[0], p[1], p[2], p[3]);
+    s_st4(pk + o_s1, p[4], p[5], p[6], p[7]);
     if (RECORD) {
-      sh.E[sk][warp][lane] = fmaf(-2.0f, fmaf(S1, pg, psd), fmaf(64.0f, gg, fmaf(V, pp, A)));
-      named_arrive(1 + sk, nbar);
+      s_st1(a_E + (slot << 11), fmaf(-2.0f, fmaf(S1, pg, psd), fmaf(64.0f, gg, fmaf(V, pp, A))));
+      named_arrive(1 + (int)slot, nbar);
     }
     __syncwarp();
     if (k == n_iter) {   // the reference's last q-update is never used
@@ -580,10 +684,11 @@ __device__ __forceinline__ void pages_iterate(const PageRegs& M, PagesShared& sh
     pp += __shfl_xor_sync(kFull, pp, 16);
     const float invB = rcp_newton(pp + kLambda);
     float ua[4], ub[4];
+    const uint32_t pspan = pk + o_span;
     auto q_seg = [&](auto cc_c) {   // row (dr, cc) has rho % 4 = cc: it meets p[64 cc + j]
       constexpr int cc = decltype(cc_c)::value;
       const float Pseg = __shfl_sync(kFull, psum, 8 * cc);
-      load_span(pk + 64 * cc + sp, v);
+      load_span_u32(pspan + 256 * cc, v);
       ua[cc] = fmaf(f[cc], Pseg, row_dot<cc>(D[cc], v));
       ub[cc] = fmaf(f[4 + cc], Pseg, row_dot<4 + cc>(D[4 + cc], v));
     };
@@ -592,16 +697,20 @@ __device__ __forceinline__ void pages_iterate(const PageRegs& M, PagesShared& sh
     m = Q * (1.0f / 64.0f);
     qa = ((ua[0] + ua[1]) + (ua[2] + ua[3])) * invB;
     qb = ((ub[0] + ub[1]) + (ub[2] + ub[3])) * invB;
-    qs[off_s[0] >> 2] = qa;   // q index of row rho is rho >> 2
-    qs[off_s[1] >> 2] = qb;
-    if (RECORD && k >= kLag) keep_if_best(k - kLag, sk == kRing - 1 ? 0 : sk + 1);   // (k - 2) % 3 == (k + 1) % 3
+    s_st1(a_q0, qa);
+    s_st1(a_q1, qb);
+    if (RECORD && k >= kLag) keep_if_best(k - kLag);
     __syncwarp();
   }
   if (RECORD) {
-    // drain: the last iteration's reducer, and the verdicts not yet read (iterations n_iter-kLag+1 .. n_iter; the
-    // loop read those up to n_iter-1-kLag)
-    if (n_iter == next_red) reduce_iteration(n_iter);
-    for (int j = max(n_iter - kLag, 0); j <= n_iter; ++j) keep_if_best(j, j % kRing);
+    // drain: the reducers of the last kRedDelay iterations, and the verdicts not yet read (the loop read those up to
+    // n_iter - 1 - kLag).  Reducers first, in iteration order: every verdict awaited below is then on its way.
+    for (int j = max(n_iter - kRedDelay + 1, 0); j <= n_iter; ++j)
+      if (j == next_red) {
+        pages_reduce<MODE == 0>(sh, j, W, lane, inv_cnt, record_out);
+        next_red += W;
+      }
+    for (int j = max(n_iter - kLag, 0); j <= n_iter; ++j) keep_if_best(j);
   }
 }
 
@@ -689,7 +798,7 @@ __global__ void __launch_bounds__(32 * kGroupWarps, 1) als_pages_kernel(const __
 
   // every unit of the item must have the pair-build structure; otherwise the dense kernel takes the whole item
   if (threadIdx.x == 0) sh.all_compact = 1;
-  if (threadIdx.x < kRing) sh.flag[threadIdx.x] = 0xffffffffu;
+  if (threadIdx.x < kRing) sh.flag[threadIdx.x] = -1;
   if (threadIdx.x == 0) {
     sh.best_rmse = __int_as_float(0x7f800000);
     sh.kstar = 0;
@@ -733,7 +842,7 @@ __global__ void __launch_bounds__(32 * kGroupWarps, 1) als_pages_kernel(const __
       pages_iterate<1>(M, sh, ps, qs, best, lane, warp, Wr, limit, inv_cnt, nullptr, pv);
     }
     __syncthreads();
-    if (threadIdx.x < kRing) sh.flag[threadIdx.x] = 0xffffffffu;
+    if (threadIdx.x < kRing) sh.flag[threadIdx.x] = -1;
     __syncthreads();
   }
   if (warp == 0) {   // first minimum of the group record (CP:143), as a min over (value bits, index) keys
@@ -813,7 +922,13 @@ int als_sparse_launch(const rdm_als_scale_t* scales, int32_t n_scales, int64_t n
   if (n_items == 0) return 0;
   RDM_REQUIRE(n_raw + n_map < (1ll << 28), "rdm_als_fused: too many work units");
   if (n_raw && sparsify) {
-    als_sparsify_raw_kernel<<<(unsigned)(4 * n_raw), 256, 0, stream>>>(raw);
+    static size_t smem_sp[64];
+    cudaError_t es = ensure_dyn_smem(als_sparsify_raw_kernel, kStageBytes, smem_sp);
+    if (es != cudaSuccess) {
+      set_error("rdm_als_fused: cudaFuncSetAttribute(als_sparsify_raw_kernel): %s", cudaGetErrorString(es));
+      return (int)es;
+    }
+    als_sparsify_raw_kernel<<<(unsigned)(4 * n_raw), kBandRows, kStageBytes, stream>>>(raw);
     int rc = launch_status("als_sparsify_raw_kernel");
     if (rc) return rc;
   }
@@ -837,17 +952,26 @@ int als_sparse_launch(const rdm_als_scale_t* scales, int32_t n_scales, int64_t n
 
 }  // namespace rdm
 
-// Host copy of the sparsify kernel's geometry tables (built by the same constexpr function), so that the CPU
-// test suite can check them against the oracle's window mask without a GPU.
-extern "C" int rdm_sparsify_geometry(uint64_t* lane_slots, uint16_t* item, uint8_t* compact) {
-  RDM_REQUIRE(lane_slots && item && compact, "rdm_sparsify_geometry: null pointer");
-  static constexpr rdm::SparsifyTables t = rdm::make_sparsify_tables();
-  for (int h = 0; h < 2; ++h)
-    for (int r0 = 0; r0 < 6; ++r0)
-      for (int l = 0; l < 32; ++l) lane_slots[(h * 6 + r0) * 32 + l] = t.lane_slots[h][r0][l];
-  for (int h = 0; h < 2; ++h)
-    for (int i = 0; i < 96; ++i) item[h * 96 + i] = t.item[h][i];
-  for (int c = 0; c < 16; ++c)
-    for (int e = 0; e < 16; ++e) compact[c * 16 + e] = t.compact[c][e];
+// Host copy of the compact page form's geometry (computed by the same RowGeom the kernels use), so that the CPU test
+// suite can check it against the oracle's window mask without a GPU: per matrix row the nine window columns
+// (row-major over the 3x3 window), the fill reference column, and the source of each entry of the 16-float compact
+// row (0..8 = window slot minus f, 9 = the fill level f itself, 15 = zero).
+extern "C" int rdm_sparsify_geometry(int32_t* window_cols, int32_t* fill_col, uint8_t* compact) {
+  RDM_REQUIRE(window_cols && fill_col && compact, "rdm_sparsify_geometry: null pointer");
+  for (int rho = 0; rho < 256; ++rho) {
+    const rdm::RowGeom g(rho);
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b) window_cols[rho * 9 + 3 * a + b] = g.window_col(a, b);
+    fill_col[rho] = g.fill_col();
+    for (int e = 0; e < 16; ++e) {
+      uint8_t code = 15;
+      if (e == 0) code = 9;
+      else if (e <= 12) {
+        const int b = g.span0 + ((e - 1) & 3) - g.c0;
+        if (b >= 0 && b < 3) code = (uint8_t)(3 * ((e - 1) >> 2) + b);
+      }
+      compact[rho * 16 + e] = code;
+    }
+  }
   return 0;
 }

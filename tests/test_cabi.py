@@ -138,41 +138,24 @@ def test_sparsify_geometry_tables_match_the_window_mask(lib):
     land in the 3x4 span) against the oracle's window mask (RN:266-273 + CP:269-295), on the CPU."""
     import numpy as np
     from oracle import fusion_ref as fr
-    lane_slots = np.zeros(2 * 6 * 32, dtype=np.uint64)
-    item = np.zeros(2 * 96, dtype=np.uint16)
-    compact = np.zeros(16 * 16, dtype=np.uint8)
-    assert lib.rdm_sparsify_geometry(lane_slots.ctypes.data, item.ctypes.data, compact.ctypes.data) == 0
-    lane_slots = lane_slots.reshape(2, 6, 32)
-    item = item.reshape(2, 96)
-    compact = compact.reshape(16, 16)
+    window_cols = np.zeros(256 * 9, dtype=np.int32)
+    fill_col = np.zeros(256, dtype=np.int32)
+    compact = np.zeros(256 * 16, dtype=np.uint8)
+    assert lib.rdm_sparsify_geometry(window_cols.ctypes.data, fill_col.ctypes.data, compact.ctypes.data) == 0
+    window_cols, compact = window_cols.reshape(256, 9), compact.reshape(256, 16)
     mask = fr.window_mask(8, 16).numpy()                       # (256 rows, 64 columns)
     for row in range(256):
         r, c = row >> 4, row & 15
-        r0, c0, h, i = min(r >> 1, 5), min(c >> 1, 5), (c >> 3) & 1, c & 7
-        span0 = min(2 * (c >> 2), 4)
-        # per-lane slots: column j = 2*lane + e is window slot 3a+b or 9 (fill)
-        seen = {}
-        for lane in range(32):
-            byte = (int(lane_slots[h, r0, lane]) >> (8 * i)) & 0xFF
-            for e, slot in enumerate((byte & 15, byte >> 4)):
-                j = 2 * lane + e
-                assert (slot != 9) == bool(mask[row, j]), (row, j)
-                if slot != 9:
-                    assert j == 8 * (r0 + slot // 3) + c0 + slot % 3
-                    seen[slot] = j
-        assert sorted(seen) == list(range(9))
-        # gather items: the staging line holds parent rows r0..r0+2 (8 columns each), then the fill value
-        for slot in range(10):
-            g = int(item[h, 10 * i + slot])
-            assert g & 0x1000 and (g >> 5) & 7 == i and (g >> 8) & 15 == slot
-            src = g & 31
-            assert src == (24 if slot == 9 else (seen[slot] - 8 * r0))
+        r0, c0, span0 = min(r >> 1, 5), min(c >> 1, 5), min(2 * (c >> 2), 4)
+        assert sorted(window_cols[row].tolist()) == np.flatnonzero(mask[row]).tolist()
+        assert window_cols[row].tolist() == [8 * (r0 + a) + c0 + b for a in range(3) for b in range(3)]
+        # the fill reference column is outside the window of EVERY pixel of this pixel row (they share r0)
+        assert not mask[16 * r:16 * r + 16, fill_col[row]].any()
         # compact row: entry 0 = fill, entries 1..12 = span (alpha, gamma) -> window slot or zero
-        assert compact[c, 0] == 9 and all(compact[c, 13:] == 15)
+        assert compact[row, 0] == 9 and all(compact[row, 13:] == 15)
         for e in range(12):
             col = 8 * (r0 + e // 4) + span0 + e % 4
-            code = int(compact[c, 1 + e])
+            code = int(compact[row, 1 + e])
             assert (code != 15) == bool(mask[row, col]), (row, e)
             if code != 15:
-                assert seen[code] == col
-    assert all(int(v) == 0 for v in item[:, 80:].reshape(-1))
+                assert window_cols[row, code] == col

@@ -26,7 +26,7 @@ for b in range(max(64 // groups, 4)):
     plan.load_inputs(x_d1.to(dev), srcs, torch.cat([w.reshape(-1) for w in weights]).to(dev))
     ring.append(plan)
 out = {"source": source, "groups_per_launch": groups, "ring": len(ring)}
-for name, mask in (("sparsify", 4), ("als_sparse", 8), ("als_dense", 16), ("select", 2)):
+for name, mask in FusionPlan.phase_masks().items():
     out[name + "_us_per_batch16"] = round(bench.time_serial([(lambda p=p, m=mask: p.run_als_phase(m)) for p in ring], 100) * 1e6 / groups, 2)
 out["tail_us_per_batch16"] = round(bench.time_serial([(lambda p=p: p.run_tail()) for p in ring], 100) * 1e6 / groups, 2)
 out["step_us_per_batch16"] = round(bench.time_serial([(lambda p=p: p.run()) for p in ring], 100) * 1e6 / groups, 2)
