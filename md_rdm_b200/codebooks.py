@@ -11,6 +11,7 @@ loads real .mat files instead when they are available.
 from __future__ import annotations
 
 import json
+import warnings
 import os
 from typing import Dict, Tuple
 
@@ -83,10 +84,20 @@ class Quantization:
         self._dev = {k: v for k, v in self._dev.items() if k[0] != scale}
         return q, inv
 
+    def _warn_if_derived(self, scale: int) -> None:
+        """The 008 table is missing from the reference tree and is served as table(016)**2: say
+        so once per process, a deployment that holds the authors' file gets different bins at that scale."""
+        if self.derived.get(scale) and scale not in _warned:
+            _warned.add(scale)
+            warnings.warn(f"md_rdm_b200: the {scale:03d} Lloyd codebook in use is DERIVED (table of another scale to the power "
+                          f"2s/s), not the reference authors' depth_ratio_{scale:03d}_{scale:03d}_quant.mat; load the real file with "
+                          "Quantization.from_mat_dir() if you have it", stacklevel=3)
+
     # ---- reference surface (RN:420-442)
     def get_with_id(self, id):
         if 3 <= id <= 7:
             s = 1 << id
+            self._warn_if_derived(s)
             return getattr(self, _tag(s)), getattr(self, _tag(s) + "_inv")
 
     def get_size_id(self, id):
@@ -100,6 +111,7 @@ class Quantization:
         key = (scale, str(device))
         hit = self._dev.get(key)
         if hit is None:
+            self._warn_if_derived(scale)
             q = torch.from_numpy(getattr(self, _tag(scale)).reshape(-1).copy()).to(device)
             inv = torch.from_numpy(getattr(self, _tag(scale) + "_inv").reshape(-1).copy()).to(device)
             hit = (q, inv)
@@ -108,6 +120,7 @@ class Quantization:
 
 
 _default = None
+_warned = set()
 
 
 def default_quantization() -> Quantization:

@@ -747,6 +747,13 @@ def test_full_model_config1_golden(dev, books):
             rec_ref = g[f"record_{s}"][pi]                       # the reference's record
             assert np.allclose(plan.record[s][0, pi].cpu().numpy(), rec_ref, rtol=1e-5, atol=1e-8), (s, pi)
             assert rec_ref[ours_k[pi]] <= rec_ref.min() * (1 + 1e-6), (s, pi, ours_k[pi], int(g[f"kstar_{s}"][pi]))
+    # what the plateau costs in DIRECT terms (no force_k): printed (pytest -s / tools/kstar_report.py keeps the log under
+    # profiles/), and bounded: the quirky gm^(1/H) normaliser (CP:244-255) makes the emitted map scale dependent, so
+    # a different tie of the arg-min moves the log-depth by a few 1e-3 - the reference itself has that freedom
+    direct = (plan.depth.cpu() - torch.from_numpy(g["depth"])).abs().max().item()
+    print(f"\nconfig-1 golden: GPU k* per scale {ks}, reference k* {[g[f'kstar_{s}'].tolist() for s in scales]}, "
+          f"direct max |log-depth - golden| = {direct:.3e}")
+    assert direct <= 2e-2
     forced = fr.fusion_forward(x_d1, rel, weights, books, force_k=ks)
     for si, s in enumerate(scales):
         assert _rel_err(plan.rel[s].cpu(), forced["rel"][si]) < REL_MAP, s
@@ -880,3 +887,148 @@ def test_stress_pages_argmin_protocol_repeatable(dev, books):
             rr = np.array(it["record"], dtype=np.float32)
             assert np.allclose(outs[0][1][0, pi].cpu().numpy(), rr, rtol=2e-5, atol=1e-8), (group, pi)
             assert rr[ks[pi]] <= rr.min() * (1 + 3e-6), (group, pi, ks[pi], int(rr.argmin()))
+
+
+# ============================================================================ the literal call sequence of the reference
+def test_literal_call_sequence_rn_383_396(dev, books):
+    """RN:383-396 written against the drop-in NAMES exactly as the reference calls them - cp.resize,
+    cp.split_matrix, Ordinal_Layer.sparse_comparison_id, cp.alternating_least_squares, cp.reconstruct (and
+    sparse_comparison_v1 + cp.quadratic_als for the 8x8 decoder, RN:359-368; cp.multi_upsample /
+    cp.get_resized_area used directly) - against the fused Ordinal_Layer.forward and the oracle."""
+    import md_rdm_b200.computations as cp
+    from md_rdm_b200.rdm_net import Ordinal_Layer, Quantization
+    quant = Quantization()
+    g = torch.Generator().manual_seed(383)
+    for s in (8, 16, 32, 64):
+        x = torch.exp(0.3 * torch.randn(3, 1, s, s, generator=g))
+        layer = Ordinal_Layer(int(math.log2(s)) + 3, False, quant)
+        xd = x.to(dev)
+        if s == 8:                                                      # RN:359-368
+            literal = cp.quadratic_als(layer.sparse_comparison_v1(xd), True, n=3, limit=30)
+        elif s == 16:                                                   # RN:370-381
+            dn_1 = cp.resize(xd, 8)
+            literal = cp.alternating_least_squares(layer.sparse_comparison_id(xd, dn_1), 4, True, limit=100)
+        else:                                                           # RN:383-396
+            dn_1 = cp.resize(xd, s // 2)
+            pages, parents = cp.split_matrix(xd, dn_1)
+            assert len(pages) == (s // 16) ** 2 and pages[1].shape == (3, 1, 16, 16) and parents[1].shape == (3, 1, 8, 8)
+            outs = [cp.alternating_least_squares(layer.sparse_comparison_id(pg, par), 4, True, limit=100) for pg, par in zip(pages, parents)]
+            literal = cp.reconstruct(outs)
+        fused = layer(xd)
+        ref = fr.relative_decoder_tail(x, books)
+        assert literal.shape == (3, 1, s, s) and literal.dtype == torch.float32
+        assert _rel_err(literal.cpu(), ref) < REL_MAP, s
+        assert _rel_err(fused.cpu(), ref) < REL_MAP, s
+        assert _rel_err(literal.cpu(), fused.cpu()) < REL_MAP, s
+    # cp.multi_upsample (CP:362-366) and cp.get_resized_area (CP:269-295) as free functions
+    y = torch.randn(2, 1, 4, 4, generator=g)
+    up = cp.multi_upsample(y.to(dev), 3)
+    assert up.dtype == torch.float64 and torch.equal(up.cpu(), y.double().repeat_interleave(8, 2).repeat_interleave(8, 3))
+    assert cp.multi_upsample(y.to(dev), 0).dtype == torch.float32
+    par = torch.rand(2, 1, 8, 8, generator=g, dtype=torch.float64) + 0.5
+    area = cp.get_resized_area(2, 4, 3, 6, par.to(dev)).cpu()
+    want = torch.ones_like(par)
+    want[:, :, 2:5, 3:6] = par[:, :, 2:5, 3:6]
+    assert area.shape == (2, 1, 64) and torch.equal(area, want.view(2, 1, 64))
+
+
+def test_training_step_config3_batch16_fast_path(dev, books):
+    """BASELINE config 3 at its full batch (16) through md_rdm_b200.training.TrainingStep (what bench.py --config
+    train times): loss terms, final depth and the gradients of Weights and of the DORN logits against torch
+    autograd on the CPU oracle."""
+    import bench
+    from md_rdm_b200.training import TrainingStep
+    scales, B = (8, 16, 32), 16
+    _, rel, weights = fr.synthetic_batch(B, scales, seed=1603)
+    y_raw, logits = bench.synthetic_gt(B, 1604)
+    w_flat = torch.cat([w.reshape(-1) for w in weights])
+    ts = TrainingStep(B, scales, device=dev)
+    ts.load(rel, y_raw, logits, w_flat)
+    out = ts.step()
+    torch.cuda.synchronize()
+    # ---- oracle
+    lg = logits.clone().requires_grad_(True)
+    decode, ord_ = fr.dorn_regression(lg)
+    w_ref = [w.clone().requires_grad_(True) for w in weights]
+    fwd = fr.fusion_forward(decode, rel, w_ref, books)
+    loss_ref, mse_ref, fine_ref, final_ref = fr.training_loss(y_raw, fwd["y_hat"])
+    y128 = fr.mask_target(fr.resize(y_raw, 128))
+    ord_ref = fr.ordinal_loss(ord_, fr.depth2label_sid(fr.resize(y128, 8)))
+    (loss_ref + ord_ref).backward()
+    assert _depth_ok(out["final"].cpu(), final_ref.detach())
+    assert abs(out["mse"].item() - mse_ref.item()) <= 1e-6 * abs(mse_ref.item())
+    assert abs(out["fine"].item() - fine_ref.item()) <= 1e-5 * abs(fine_ref.item())
+    assert abs(out["ord"].item() - ord_ref.item()) <= 1e-5 * abs(ord_ref.item())
+    assert abs(out["loss"].item() - (loss_ref + ord_ref).item()) <= 1e-5 * abs((loss_ref + ord_ref).item())
+    g_ref = torch.cat([w.grad.reshape(-1) for w in w_ref])
+    assert _rel_err(ts.weights.grad.cpu(), g_ref) < 1e-4
+    assert torch.allclose(ts.logits.grad.cpu(), lg.grad, rtol=1e-4, atol=1e-9)
+    # a second step on the same inputs reproduces the first bit for bit (no state leaks between steps)
+    out2 = ts.step()
+    assert torch.equal(out2["loss"], out["loss"])
+
+
+def test_fuse_maps_autograd_and_cache(dev, books):
+    """fuse_maps presented as the replacement of RN:103-133 + MOD:132 must carry gradients to
+    Weights when autograd records, and its plan cache must not serve another Quantization's codebooks."""
+    from md_rdm_b200 import fusion
+    from md_rdm_b200.rdm_net import Quantization, Weights
+    scales = (8, 16)
+    x_d1, rel, weights = fr.synthetic_batch(2, scales, seed=2024)
+    wl = Weights(vector_sizes=fr.slot_sizes(scales), use_cuda=True, relative_only=False)
+    with torch.no_grad():
+        for p_, w_ in zip(wl.weight_list, weights):
+            p_.copy_(w_)
+    depth, y_hat, filled = fusion.fuse_maps(x_d1.to(dev), [r.to(dev) for r in rel], wl.weight_list)
+    assert depth.requires_grad and y_hat[0].requires_grad
+    (depth ** 2).mean().backward()
+    w_ref = [w.clone().requires_grad_(True) for w in weights]
+    o = fr.fusion_forward(x_d1, rel, w_ref, books)
+    (fr.recombination(list(o["y_hat"])) ** 2).mean().backward()
+    for p_, r_ in zip(wl.weight_list, w_ref):
+        if p_.numel():
+            assert _rel_err(p_.grad.cpu(), r_.grad) < 1e-4
+    with torch.no_grad():
+        d2, _, _ = fusion.fuse_maps(x_d1.to(dev), [r.to(dev) for r in rel], wl.weight_list)
+    assert not d2.requires_grad and _depth_ok(d2.cpu(), depth.detach().cpu())
+    # another codebook object -> another plan (keyed on the object, not on a recyclable id)
+    q2 = Quantization()
+    thr, lvl = q2.get_with_id(4)
+    q2.depth_ratio_016_016_quant = thr * 1.01
+    if hasattr(q2, "_dev"):
+        q2._dev.clear()
+    n0 = len(fusion._plans)
+    with torch.no_grad():
+        d3, _, f3 = fusion.fuse_maps(x_d1.to(dev), [r.to(dev) for r in rel], wl.weight_list, quant=q2)
+    assert len(fusion._plans) == n0 + 1
+    fusion.clear_plans()
+    assert len(fusion._plans) == 0
+
+
+def test_stress_tail_bands_and_gm_cluster(dev, books):
+    """fuse_tail_kernel exchanges fine-detail logs between the CTAs of a cluster through distributed shared memory
+    (1, 2, 4 or 8 bands per image depending on the batch), gm_cluster_kernel its partial products: 20 reruns on
+    >= 256 images must be bit-identical, and every band count must give the same values for the same image."""
+    g = torch.Generator().manual_seed(808)
+    scales = (8, 16, 32)
+    x_d1, rel, weights = fr.synthetic_batch(256, scales, seed=909)
+    w = torch.cat([t.reshape(-1) for t in weights]).to(dev)
+    xd = x_d1.to(dev)
+    filled = [torch.exp(0.2 * torch.randn(256, 1, s, s, generator=g)).to(dev) for s in scales]
+    ref_depth = None
+    for n in (256, 64, 16, 4, 1):            # the launch picks more bands per image as the batch shrinks
+        d0, y0, _ = R.fuse_tail(xd[:n], [f[:n] for f in filled], w, False)
+        for rep in range(20 if n == 256 else 5):
+            d, y, _ = R.fuse_tail(xd[:n], [f[:n] for f in filled], w, False)
+            assert _eq_nan(d, d0) and _eq_nan(y, y0), (n, rep)
+        if ref_depth is None:
+            ref_depth = d0
+        else:
+            assert _eq_nan(d0, ref_depth[:n]), n
+    y = (0.5 + 9.5 * torch.rand(256, 1, 128, 128, generator=g, dtype=torch.float64)).to(dev)
+    n0 = R.gm_normalize(y)
+    p0 = R.decompose(n0, False)
+    for rep in range(20):
+        assert torch.equal(R.gm_normalize(y), n0), rep
+        assert torch.equal(R.decompose(n0, False), p0), rep
+    assert torch.equal(R.gm_normalize(y[:3]), n0[:3])
