@@ -323,11 +323,13 @@ def stage_kernel_table(dev, batch):
     thr, lvl = q.device_tables(32, dev)
     y = (0.5 + 9.5 * torch.rand(batch, 1, 128, 128, generator=g, dtype=torch.float64)).to(dev)
     comps = [torch.randn(batch, 1, 2 ** k, 2 ** k, generator=g).to(dev) for k in range(8)]
+    y226 = synthetic_gt(batch, 5)[0].to(dev)
     cases = {
         "pair_v1": (lambda: R.pair_v1(x8), batch * (256 + 16384)),
         "pair_id_32": (lambda: R.pair_id(x32), batch * (4096 + 2048 + 4 * 131072)),
         "lloyd_quantize_f64_32": (lambda: R.lloyd_quantize(raw32, thr, lvl), raw32.numel() * 17),
         "gm_normalize+decompose_gt128": (lambda: R.decompose(R.gm_normalize(y), False), batch * (3 * 131072 + 174760)),
+        "gt_prepare_226": (lambda: R.gt_prepare(y226), batch * (226 * 226 * 8 + 131072 + 174760 + 256)),
         "recombination_128": (lambda: R.recombination(comps, 7), batch * (131072 + 4 * 21845)),
     }
     out = {}
@@ -645,9 +647,13 @@ def run_train(args):
         parity = train_parity_gate(steps[0], dev)
     cur = torch.cuda.current_stream()
 
+    if not args.no_train_graph:
+        for ts in steps:
+            ts.capture()
+
     def run(k):
         for i in range(k):
-            steps[i % n_ring].step()
+            steps[i % n_ring].step() if args.no_train_graph else steps[i % n_ring].replay()
 
     with ClockSampler(local_rank) as clk:
         timed_region(lambda: run(max(W, 3)))
@@ -679,6 +685,7 @@ def run_train(args):
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
         "config": shared_config("train"),
         "step": {"images_per_step_per_gpu": BATCH, "launches_per_step": steps[0].launches_per_step(),
+                 "cuda_graph": not args.no_train_graph,
                  "what": "DORN head -> x_d1, pair build + Lloyd + ALS (from the decoder maps), fused tail with autograd, GT resize 226->128 + mask "
                          "+ gm-normalise + decompose n=7, ordinal GT, MSE + component loss + Ordinal_Loss, backward to Weights and the DORN logits"},
         "clocks": clocks,
@@ -808,6 +815,7 @@ def main():
     ap.add_argument("--no-stage-table", action="store_true")
     ap.add_argument("--no-grouped", action="store_true")
     ap.add_argument("--no-parity-gate", action="store_true")
+    ap.add_argument("--no-train-graph", action="store_true", help="--config train: eager steps instead of CUDA-graph replays")
     ap.add_argument("--scales", default="8,16,32", help="relative decoder scales (default: BASELINE configs[1]); "
                     "8,16,32,64 is the configuration network/RDM_Net.py:96-97 names")
     ap.add_argument("--ref-budget-s", type=float, default=300.0, help="--impl reference: wall-clock budget for the literal port")

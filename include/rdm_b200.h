@@ -192,6 +192,17 @@ int rdm_decompose_bwd(const void* in, int32_t in_is_f64, int64_t n_images, int32
 int rdm_gm_bwd(const void* x, int32_t is_f64, int64_t batch, int64_t n, int32_t rc,
                const void* grad_gm, const void* grad_norm, void* grad_x, rdm_stream_t stream);
 
+/* Ground-truth preparation of the training step in ONE launch: network/module.py:68 cp.resize(y, 128)
+ * (bicubic), :74-78 mask (+1e-4 everywhere, invalid -> 1.0001), :145-149 normalize, :123 decompose n = 7, and the ordinal
+ * target of :126-127 / :134-143: utils.depth2label_sid(cp.resize(y, 8)) (utils.py:195-211) whose normalised
+ * decomposition replaces D_0.  y_raw: (N,in_h,in_w) f32|f64.  y_out: (N,128,128) f64 masked map (what the MSE uses);
+ * pyramid_out: N * rdm_pyramid_len(128, 0) f64, level-major like rdm_decompose, slot 0 = the ORDINAL D_0;
+ * ord_target_out: (N,64) i32 SID labels.  sid_K, sid_alpha and sid_log_ratio = log(beta / alpha) are passed as the
+ * f32-rounded scalars the reference's torch code holds (K = 90, alpha = 0.02, beta = 10). */
+int rdm_gt_prepare(const void* y_raw, int32_t in_is_f64, int64_t n_images, int32_t in_h, int32_t in_w,
+                   double sid_K, double sid_alpha, double sid_log_ratio, double* y_out,
+                   double* pyramid_out, int32_t* ord_target_out, rdm_stream_t stream);
+
 /* ------------------------------------------------------------------ stage 5: weighted reconstruction */
 
 /* CP:464-484 cp.make_matrix: out[b,k,:] = log(cand_k[b,:]) for K candidates of M values each.

@@ -56,6 +56,8 @@ PROTOTYPES = {
     "rdm_gm_normalize": (c_int, [c_void_p, c_int32, c_int64, c_int32, c_void_p, c_void_p]),
     "rdm_decompose": (c_int, [c_void_p, c_int32, c_int64, c_int32, c_int32, c_void_p, c_void_p]),
     "rdm_pyramid_len": (c_int64, [c_int32, c_int32]),
+    "rdm_gt_prepare": (c_int, [c_void_p, c_int32, c_int64, c_int32, c_int32, c_double, c_double, c_double, c_void_p, c_void_p, c_void_p,
+                               c_void_p]),
     "rdm_decompose_bwd": (c_int, [c_void_p, c_int32, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "rdm_gm_bwd": (c_int, [c_void_p, c_int32, c_int64, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
     "rdm_log_stack_bwd": (c_int, [POINTER(c_void_p), c_int32, c_int64, c_int64, c_void_p, POINTER(c_void_p), c_void_p]),

@@ -119,7 +119,6 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---- the HBM-streaming kernel of the path ----------------------------------------------------------------
 // Work item = one band of 64 matrix rows (32 KB of f64, contiguous in HBM) = one CTA of 64 threads; six CTAs fit an
@@ -364,17 +363,6 @@ __device__ __forceinline__ float rcp_newton(float x) {   // see rdm_als.cu
   return fmaf(fmaf(-x, r, 1.0f), r, r);
 }
 
-__device__ __forceinline__ void load_span(const float* base, float (&v)[12]) {
-#pragma unroll
-  for (int a = 0; a < 3; ++a) {
-    const float2 lo = *reinterpret_cast<const float2*>(base + 8 * a);
-    const float2 hi = *reinterpret_cast<const float2*>(base + 8 * a + 2);
-    v[4 * a] = lo.x;
-    v[4 * a + 1] = lo.y;
-    v[4 * a + 2] = hi.x;
-    v[4 * a + 3] = hi.y;
-  }
-}
 
 // sum_span D v as one FMA chain (eight independent rows interleave).  FROM = 1 skips the span's first
 // column: rows of pixel columns 4kq+2, 4kq+3 have their window in span columns 1..3 for every kq.

@@ -231,6 +231,16 @@ __device__ __forceinline__ double bicubic_half_at(F at, int y, int x, int side) 
   return acc;
 }
 
+// torch bicubic weights (A = -0.75) at fractional position t (CP:308-311 for arbitrary sizes)
+__device__ __forceinline__ void cubic_coeffs(double t, double (&w)[4]) {
+  const double A = -0.75;
+  double x;
+  x = t + 1.0; w[0] = ((A * x - 5.0 * A) * x + 8.0 * A) * x - 4.0 * A;
+  x = t;       w[1] = ((A + 2.0) * x - (A + 3.0)) * x * x + 1.0;
+  x = 1.0 - t; w[2] = ((A + 2.0) * x - (A + 3.0)) * x * x + 1.0;
+  x = 2.0 - t; w[3] = ((A * x - 5.0 * A) * x + 8.0 * A) * x - 4.0 * A;
+}
+
 // RN:266-273 + CP:269-295: is column `col` (parent pixel col/8, col%8) inside the 3x3 window of
 // page row `row` (pixel row/16, row%16)?  The window is anchored top-left at (min(r/2,5), min(c/2,5)).
 __device__ __forceinline__ bool in_window(int row, int col) {

@@ -196,14 +196,6 @@ __global__ void __launch_bounds__(256) upsample_nearest_kernel(const TIn* __rest
 // CP:308-311 cp.resize for an arbitrary target size (network/module.py:68 resizes 226 -> 128):
 // torch bicubic, align_corners=False, A = -0.75, clamped taps, f64 arithmetic, horizontal taps
 // summed first.
-__device__ __forceinline__ void cubic_coeffs(double t, double (&w)[4]) {
-  const double A = -0.75;
-  double x;
-  x = t + 1.0; w[0] = ((A * x - 5.0 * A) * x + 8.0 * A) * x - 4.0 * A;
-  x = t;       w[1] = ((A + 2.0) * x - (A + 3.0)) * x * x + 1.0;
-  x = 1.0 - t; w[2] = ((A + 2.0) * x - (A + 3.0)) * x * x + 1.0;
-  x = 2.0 - t; w[3] = ((A * x - 5.0 * A) * x + 8.0 * A) * x - 4.0 * A;
-}
 
 template <typename TIn>
 __global__ void __launch_bounds__(256) resize_bicubic_kernel(const TIn* __restrict__ in, double* __restrict__ out, int64_t n_maps,

@@ -165,90 +165,20 @@ __device__ __forceinline__ void pyramid_down(double* D, int top, Emit emit) {
   }
 }
 
-// Top level of a large map, banded over the chip: CTA (image, band) stages 10 source rows (8 own
-// + 1 halo on either side) with coalesced 128-bit loads, forms 4 rows of D_{n-1} and writes 8 rows
-// of F_n with 128-bit stores.  D_{n-1} is parked in the F_{n-1} slot of the output (same size);
-// the per-image kernel below then decomposes it in place.
-template <typename TIn>
-__global__ void __launch_bounds__(256) decompose_top_kernel(const TIn* __restrict__ in, int side, int n, int relative,
-                                                            double* __restrict__ out, int64_t n_images) {
-  extern __shared__ __align__(16) double S[];   // 10 rows x side
-  const int bands = side >> 3, half = side >> 1;
-  const int64_t img = blockIdx.x / bands;
-  const int band = blockIdx.x - (int)(img * bands);
-  const TIn* src = in + img * (int64_t)side * side;
-  const int base = relative ? 0 : 1;
-  double* fn = out + n_images * (base + off_fine(n)) + img * (int64_t)side * side;
-  double* dnext = out + n_images * (base + off_fine(n - 1)) + img * (int64_t)half * half;
-  const int r_lo = 8 * band - 1;
-  for (int i = threadIdx.x; i < 10 * side; i += blockDim.x) {
-    const int rr = i / side, c = i - rr * side;
-    const int r = min(max(r_lo + rr, 0), side - 1);
-    S[i] = (double)src[r * side + c];
-  }
-  __syncthreads();
-  double* dsm = S + 10 * side;                   // 4 rows x half of D_{n-1}
-  for (int i = threadIdx.x; i < 4 * half; i += blockDim.x) {
-    const int yy = i / half, x = i - yy * half;
-    // source rows 2y-1 .. 2y+2 with y = 4 band + yy are staged rows 2 yy .. 2 yy + 3 (clamped on load)
-    const double w[4] = {RDM_W0, RDM_W1, RDM_W1, RDM_W0};
-    double acc = 0.0;
-#pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      const double* rowp = S + (2 * yy + a) * side;
-      double inner = 0.0;
-#pragma unroll
-      for (int bb = 0; bb < 4; ++bb) {
-        const int c = min(max(2 * x - 1 + bb, 0), side - 1);
-        inner = (bb == 0) ? __dmul_rn(rowp[c], w[0]) : fma(rowp[c], w[bb], inner);
-      }
-      acc = (a == 0) ? __dmul_rn(inner, w[0]) : fma(inner, w[a], acc);
-    }
-    dsm[i] = acc;
-    dnext[(4 * band + yy) * half + x] = acc;
-  }
-  __syncthreads();
-  const bool vec_ok = (reinterpret_cast<uintptr_t>(fn) & 15u) == 0;
-  for (int i = threadIdx.x; i < 8 * half; i += blockDim.x) {   // two output pixels per thread
-    const int rr = i / half, x2 = i - rr * half;
-    const double d = dsm[(rr >> 1) * half + x2];
-    const double* sp = S + (rr + 1) * side + 2 * x2;
-    double* dst = fn + (8 * band + rr) * side + 2 * x2;
-    if (vec_ok) {
-      stg_stream_f64x2(dst, sp[0] / d, sp[1] / d);
-    } else {   // level-major offsets are N * odd doubles when D_0 is present: only 8-byte aligned for odd N
-      dst[0] = sp[0] / d;
-      dst[1] = sp[1] / d;
-    }
-  }
-}
-
 // Output is LEVEL-MAJOR: [D_0 of all images (unless relative)] [F_1 of all images] ... so every
 // component is a dense (N,1,2^k,2^k) tensor for the caller.
+// side <= 32: one CTA per image, the whole pyramid in shared memory (larger maps: decompose_cluster_kernel).
 template <typename TIn>
-__global__ void __launch_bounds__(256) decompose_kernel(const TIn* __restrict__ in, int side, int n, int relative,
-                                                        double* __restrict__ out, int64_t n_images) {
+__global__ void __launch_bounds__(256) decompose_kernel(const TIn* __restrict__ in, int side, int n, int relative, double* __restrict__ out, int64_t n_images) {
   extern __shared__ __align__(16) double D[];
   const int64_t img = blockIdx.x;
   const TIn* src = in + img * (int64_t)side * side;
   const int base = relative ? 0 : 1;
   auto fine = [&](int k) { return out + n_images * (base + off_fine(k)) + img * ((int64_t)1 << (2 * k)); };
-  int top = n;
-  if (n == 7) {   // D_7 stays in HBM/L2: it is read twice (D_6 taps, then the F_7 division)
-    double* d6 = D + off_level(6);
-    for (int idx = threadIdx.x; idx < 4096; idx += blockDim.x)
-      d6[idx] = bicubic_half_at([&](int r, int c) { return (double)src[r * 128 + c]; }, idx >> 6, idx & 63, 128);
-    __syncthreads();
-    double* f7 = fine(7);
-    for (int idx = threadIdx.x; idx < 16384; idx += blockDim.x)
-      f7[idx] = (double)src[idx] / d6[((idx >> 7) >> 1) * 64 + ((idx & 127) >> 1)];
-    top = 6;
-  } else {
-    double* dn = D + off_level(n);
-    for (int idx = threadIdx.x; idx < side * side; idx += blockDim.x) dn[idx] = (double)src[idx];
-    __syncthreads();
-  }
-  pyramid_down(D, top, [&](int k, int idx, double f) { fine(k)[idx] = f; });
+  double* dn = D + off_level(n);
+  for (int idx = threadIdx.x; idx < side * side; idx += blockDim.x) dn[idx] = (double)src[idx];
+  __syncthreads();
+  pyramid_down(D, n, [&](int k, int idx, double f) { fine(k)[idx] = f; });
   __syncthreads();
   if (!relative && threadIdx.x == 0) out[img] = D[0];
 }
@@ -803,6 +733,212 @@ __global__ void __launch_bounds__(RDM_TAIL_THREADS) fuse_tail_kernel(const __gri
 #endif
 }
 
+// ---------------------------------------------------------------------------------------------
+// Large maps (side 64 / 128): one thread-block CLUSTER of 8 CTAs per image, CTA r owns a band of side/8 rows.
+// Shared by the stand-alone decomposition (rdm_decompose, side >= 64) and the fused ground-truth preparation.
+constexpr int kBandCluster = 8;
+constexpr int kBandMaxSide = 128;
+constexpr int kBandMaxRows = kBandMaxSide / kBandCluster;      // 16
+
+struct BandSmem {
+  double Y[(kBandMaxRows + 2) * kBandMaxSide];   // staged rows of the band + one halo row either side (row stride = side)
+  double Db[(kBandMaxRows / 2) * (kBandMaxSide / 2)];   // the band's rows of D_{n-1}
+  double pyr[kPyrDoubles];                       // CTA 0: levels 0..6
+  double scratch[32];
+  double part;                                   // ground truth: sum of logs of the own rows
+  int labels[64];                                // ground truth, CTA 0: SID labels of the 8x8 map
+  float fscratch[32];
+};
+
+// From the staged rows sm.Y (global rows band*rank - 1 .. band*rank + band, border rows repeated) of a side x side map:
+// the band's rows of D_{n-1} (stride-2 bicubic, CP:308-311) -> the band's rows of F_n = D_n / up2(D_{n-1}) (CP:389) with
+// 128-bit stores; D_{n-1} goes to CTA 0's pyramid buffer through distributed shared memory, and CTA 0 finishes levels
+// n-1 .. 1 from shared memory.  Returns with `true` in CTA 0 only (its sm.pyr holds levels 0 .. n-1).
+__device__ __forceinline__ bool band_decompose(BandSmem& sm, cg::cluster_group& cluster, int rank, int side, int n, int base,
+                                               double* __restrict__ out, int64_t n_images, int64_t img) {
+  const int tid = threadIdx.x, half = side >> 1, band = side / kBandCluster;
+  double* pyr0 = cluster.map_shared_rank(&sm.pyr[0], 0);
+  for (int i = tid; i < (band / 2) * half; i += blockDim.x) {
+    const int yy = i / half, x = i - yy * half;
+    const double w[4] = {RDM_W0, RDM_W1, RDM_W1, RDM_W0};
+    double acc = 0.0;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {            // source rows 2y-1 .. 2y+2, y = (band/2) rank + yy  ->  staged rows 2 yy + a
+      const double* rowp = sm.Y + (2 * yy + a) * side;
+      double inner = 0.0;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int c = min(max(2 * x - 1 + b, 0), side - 1);
+        inner = (b == 0) ? __dmul_rn(rowp[c], w[0]) : fma(rowp[c], w[b], inner);
+      }
+      acc = (a == 0) ? __dmul_rn(inner, w[0]) : fma(inner, w[a], acc);
+    }
+    sm.Db[i] = acc;
+    pyr0[off_level(n - 1) + ((band / 2) * rank + yy) * half + x] = acc;
+  }
+  __syncthreads();
+  {
+    double* fn = out + n_images * (base + off_fine(n)) + img * (int64_t)side * side;
+    const bool vec_ok = (reinterpret_cast<uintptr_t>(fn) & 15u) == 0;
+    for (int i = tid; i < band * half; i += blockDim.x) {   // two output pixels per thread
+      const int rr = i / half, x2 = i - rr * half;
+      const double d = sm.Db[(rr >> 1) * half + x2];
+      const double* sp = sm.Y + (1 + rr) * side + 2 * x2;
+      double* dst = fn + (band * rank + rr) * side + 2 * x2;
+      if (vec_ok) {
+        stg_stream_f64x2(dst, sp[0] / d, sp[1] / d);
+      } else {   // level-major offsets are N * odd doubles when D_0 is present: only 8-byte aligned for odd N
+        dst[0] = sp[0] / d;
+        dst[1] = sp[1] / d;
+      }
+    }
+  }
+  cluster.sync();   // D_{n-1} is complete in CTA 0; nobody's shared memory is touched remotely after this
+  if (rank != 0) return false;
+  pyramid_down(sm.pyr, n - 1, [&](int k, int idx, double f) { out[n_images * (base + off_fine(k)) + img * ((int64_t)1 << (2 * k)) + idx] = f; });
+  __syncthreads();
+  return true;
+}
+
+// CP:368-392 for side 64 / 128 in one launch (no D_{n-1} parked in the output, no second kernel reading it back).
+template <typename TIn>
+__global__ void __launch_bounds__(256) decompose_cluster_kernel(const TIn* __restrict__ in, int side, int n, int relative,
+                                                                double* __restrict__ out, int64_t n_images) {
+  extern __shared__ __align__(16) unsigned char band_raw[];
+  BandSmem& sm = *reinterpret_cast<BandSmem*>(band_raw);
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int64_t img = blockIdx.x / kBandCluster;
+  const int band = side / kBandCluster;
+  const TIn* src = in + img * (int64_t)side * side;
+  const int row_lo = band * rank - 1;
+  for (int i = threadIdx.x; i < (band + 2) * side; i += blockDim.x) {
+    const int rr = i / side, c = i - rr * side;
+    sm.Y[i] = (double)src[min(max(row_lo + rr, 0), side - 1) * side + c];
+  }
+  __syncthreads();
+  if (band_decompose(sm, cluster, rank, side, n, relative ? 0 : 1, out, n_images, img) && !relative && threadIdx.x == 0) out[img] = sm.pyr[0];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Ground-truth preparation of the training step in ONE launch (network/module.py:68, 74-78, 119-127, 134-149 +
+// utils.py:195-211): bicubic resize to 128x128 (CP:308-311), mask (+1e-4 everywhere, invalid -> 1.0001), geometric-
+// mean normalisation, decomposition n = 7, and the ordinal target: SID labels of the 8x8 resize of the masked map,
+// whose normalised decomposition supplies D_0 of the component targets.
+// One cluster of 8 CTAs per image; CTA r owns rows 16r..16r+15 of the 128x128 map:
+//   1. resize + mask rows 16r-1 .. 16r+16 (one halo row either side, recomputed rather than exchanged) into shared
+//      memory; the own rows go out as y;
+//   2. row r of the 8x8 resize (taps 16r+6..16r+9: inside the band) -> SID labels -> ord_target and CTA 0;
+//   3. sum of logs of the own rows, exchanged through distributed shared memory -> gm; the staged rows are divided by
+//      it (the reference normalises BEFORE it decomposes);
+//   4. band_decompose: F_7 rows of the band, D_6 to CTA 0, CTA 0 finishes levels 6..1;
+//   5. CTA 0: D_0 of the ordinal pyramid.
+constexpr int kGtSide = 128;
+constexpr int kGtBand = kGtSide / kBandCluster;        // 16 rows
+constexpr int kGtStageRows = kGtBand + 2;
+
+template <typename TIn>
+__global__ void __launch_bounds__(256) gt_prepare_kernel(const TIn* __restrict__ y_raw, int ih, int iw, int64_t n_images, double sid_K,
+                                                         double sid_alpha, double sid_log_ratio, double* __restrict__ y_out,
+                                                         double* __restrict__ pyr_out, int32_t* __restrict__ ord_out) {
+  extern __shared__ __align__(16) unsigned char band_raw[];
+  BandSmem& sm = *reinterpret_cast<BandSmem*>(band_raw);
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int64_t img = blockIdx.x / kBandCluster;
+  const int tid = threadIdx.x;
+  const TIn* src = y_raw + img * (int64_t)ih * iw;
+  const int row_lo = kGtBand * rank - 1;                       // global row of staged row 0
+  // ---- 1. resize (torch bicubic, align_corners=False, A=-0.75, clamped taps, horizontal first) + mask
+  {
+    const double sy = (double)ih / (double)kGtSide, sx = (double)iw / (double)kGtSide;
+    const float m_inv = 1.0f + 1e-4f, m_val = 1e-4f;           // `(y <= 0) + 1e-4` is an f32 tensor (MOD:77)
+    for (int i = tid; i < kGtStageRows * kGtSide; i += blockDim.x) {
+      const int rr = i / kGtSide, ox = i - rr * kGtSide;
+      const int oy = min(max(row_lo + rr, 0), kGtSide - 1);    // halo rows beyond the map repeat the border row (clamped taps of the stride-2 filter)
+      const double fy = sy * ((double)oy + 0.5) - 0.5, fx = sx * ((double)ox + 0.5) - 0.5;
+      const double fly = floor(fy), flx = floor(fx);
+      double wy[4], wx[4];
+      cubic_coeffs(fy - fly, wy);
+      cubic_coeffs(fx - flx, wx);
+      const int iy = (int)fly, ix = (int)flx;
+      double acc = 0.0;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int r = min(max(iy - 1 + a, 0), ih - 1);
+        double inner = 0.0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const int c = min(max(ix - 1 + b, 0), iw - 1);
+          const double v = (double)src[r * iw + c];
+          inner = (b == 0) ? __dmul_rn(v, wx[0]) : fma(v, wx[b], inner);
+        }
+        acc = (a == 0) ? __dmul_rn(inner, wy[0]) : fma(inner, wy[a], acc);
+      }
+      // MOD:74-78: y = gt * (gt > 0) + ((gt <= 0) + 1e-4)
+      const double y = __dadd_rn(__dmul_rn(acc, acc > 0.0 ? 1.0 : 0.0), (double)(acc <= 0.0 ? m_inv : m_val));
+      sm.Y[i] = y;
+      if (rr >= 1 && rr <= kGtBand) y_out[img * (kGtSide * kGtSide) + (row_lo + rr) * kGtSide + ox] = y;
+    }
+  }
+  __syncthreads();
+  // ---- 2. row `rank` of cp.resize(y, 8) (scale 16: taps 16 rank + 6 .. + 9), utils.depth2label_sid
+  if (tid < 8) {
+    const double s8 = (double)kGtSide / 8.0;
+    const double fy = s8 * ((double)rank + 0.5) - 0.5, fx = s8 * ((double)tid + 0.5) - 0.5;
+    const double fly = floor(fy), flx = floor(fx);
+    double wy[4], wx[4];
+    cubic_coeffs(fy - fly, wy);
+    cubic_coeffs(fx - flx, wx);
+    const int iy = (int)fly, ix = (int)flx;
+    double acc = 0.0;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int r = min(max(iy - 1 + a, 0), kGtSide - 1) - row_lo;   // staged row
+      double inner = 0.0;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int c = min(max(ix - 1 + b, 0), kGtSide - 1);
+        const double v = sm.Y[r * kGtSide + c];
+        inner = (b == 0) ? __dmul_rn(v, wx[0]) : fma(v, wx[b], inner);
+      }
+      acc = (a == 0) ? __dmul_rn(inner, wy[0]) : fma(inner, wy[a], acc);
+    }
+    // label = K * log(depth / alpha) / log(beta / alpha), max(label, 0), .int()  (f32 scalars, f64 tensor: utils.py:195-211)
+    const double label = __ddiv_rn(__dmul_rn(sid_K, log(__ddiv_rn(acc, sid_alpha))), sid_log_ratio);
+    const int lab = __double2int_rz(fmax(label, 0.0));         // a NaN label (negative depth) becomes 0 like torch's CUDA cast
+    ord_out[img * 64 + rank * 8 + tid] = lab;
+    *cluster.map_shared_rank(&sm.labels[rank * 8 + tid], 0) = lab;
+  }
+  // ---- 3. geometric mean over the whole map (MOD:145-149, rc = 128: the true geometric mean) as exp(mean log)
+  {
+    double a0 = 0.0;
+    for (int i = tid; i < kGtBand * kGtSide; i += blockDim.x) a0 += log(sm.Y[kGtSide + i]);
+    const double mine = block_sum<double>(a0, sm.scratch);
+    if (tid == 0) sm.part = mine;
+  }
+  cluster.sync();
+  double gm = 0.0;
+  for (int r = 0; r < kBandCluster; ++r) gm += *cluster.map_shared_rank(&sm.part, r);   // rank order: deterministic
+  gm = exp(gm * (1.0 / ((double)kGtSide * (double)kGtSide)));
+  for (int i = tid; i < kGtStageRows * kGtSide; i += blockDim.x) sm.Y[i] = sm.Y[i] / gm;
+  __syncthreads();
+  // ---- 4. F_7 band, D_6 -> CTA 0, levels 6..1 (D_0 of the ground truth itself is not a target: MOD:127 replaces it)
+  if (!band_decompose(sm, cluster, rank, kGtSide, 7, 1, pyr_out, n_images, img)) return;
+  // ---- 5. ordinal D_0: normalize(labels) in f32 like torch (int -> pow(., 1/64) f32 product, int / gm in f32), then the
+  // 8x8 map decomposed in f64 (MOD:126)
+  {
+    const float pw = tid < 64 ? pow_as<float>((float)sm.labels[tid], 1.0 / 64.0) : 1.0f;
+    const float gmf = block_prod<float>(pw, sm.fscratch);
+    __syncthreads();
+    if (tid < 64) sm.pyr[off_level(3) + tid] = (double)((float)sm.labels[tid] / gmf);
+    __syncthreads();
+    pyramid_down(sm.pyr, 3, [&](int, int, double) {});
+    __syncthreads();
+    if (tid == 0) pyr_out[img] = sm.pyr[0];
+  }
+}
+
 static int grid_cap(int64_t items, int per_block) {
   int64_t blocks = (items + per_block - 1) / per_block;
   if (blocks > (int64_t)kNumSMs * 16) blocks = (int64_t)kNumSMs * 16;   // 8 resident CTAs of 256 threads per SM, two waves
@@ -817,6 +953,8 @@ static size_t smem_set_decompose_bwd_kernel_double_[64];
 static size_t smem_set_decompose_bwd_kernel_float_[64];
 static size_t smem_set_decompose_kernel_double_[64];
 static size_t smem_set_decompose_kernel_float_[64];
+static size_t smem_set_decompose_cluster_double_[64];
+static size_t smem_set_decompose_cluster_float_[64];
 static size_t smem_set_fuse_tail_kernel[64];
 static size_t smem_set_recombination_bwd_kernel_double_[64];
 static size_t smem_set_recombination_bwd_kernel_float_[64];
@@ -885,38 +1023,46 @@ extern "C" int rdm_decompose(const void* in, int32_t in_is_f64, int64_t n_images
   if (len == 0) return 0;
   const size_t smem = kPyrDoubles * sizeof(double);
   cudaError_t e;
-  // A top level of side >= 64 is banded over the whole chip (8 output rows per CTA, 128-bit accesses); the
-  // launch parks D_{k-1} in the F_{k-1} slot of the output, where the per-image kernel (one CTA per image, the
-  // remaining <= 64x64 pyramid in shared memory) reads ALL of it before it writes F_{k-1} there.  Only ONE
-  // banded launch: a second one would read its input from the slot its own CTAs overwrite (the bicubic halo
-  // rows of a band belong to the neighbouring band's CTA - a race that showed up on one box as a 4e-5 error in
-  // D_0 of a 128x128 decomposition).
-  const void* cur = in;
-  int cur_f64 = in_is_f64, s = side, nc = n;
-  const int base = relative_map ? 0 : 1;
-  if (s >= 64) {
-    const size_t tsm = (size_t)(10 * s + 4 * (s / 2)) * sizeof(double);
-    RDM_REQUIRE(n_images * (s / 8) < (1ll << 31), "rdm_decompose: too many images");
-    const unsigned ctas = (unsigned)(n_images * (s / 8));
-    if (cur_f64)
-      decompose_top_kernel<double><<<ctas, 256, tsm, (cudaStream_t)stream>>>((const double*)cur, s, nc, relative_map, pyramid_out, n_images);
+  if (side >= 64) {
+    // one cluster of 8 CTAs per image: banded top level, D_{n-1} gathered in CTA 0 through distributed shared memory
+    RDM_REQUIRE(n_images * kBandCluster < (1ll << 31), "rdm_decompose: too many images");
+    const size_t bsm = sizeof(BandSmem);
+    e = in_is_f64 ? ensure_dyn_smem(decompose_cluster_kernel<double>, bsm, smem_set_decompose_cluster_double_)
+                  : ensure_dyn_smem(decompose_cluster_kernel<float>, bsm, smem_set_decompose_cluster_float_);
+    if (e != cudaSuccess) {
+      set_error("rdm_decompose: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(n_images * kBandCluster));
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = bsm;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kBandCluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (in_is_f64)
+      e = cudaLaunchKernelEx(&cfg, decompose_cluster_kernel<double>, (const double*)in, (int)side, n, (int)relative_map, pyramid_out, n_images);
     else
-      decompose_top_kernel<float><<<ctas, 256, tsm, (cudaStream_t)stream>>>((const float*)cur, s, nc, relative_map, pyramid_out, n_images);
-    int rc = launch_status("decompose_top_kernel");
-    if (rc) return rc;
-    cur = pyramid_out + n_images * (base + off_fine(nc - 1));
-    cur_f64 = 1;
-    s >>= 1;
-    --nc;
+      e = cudaLaunchKernelEx(&cfg, decompose_cluster_kernel<float>, (const float*)in, (int)side, n, (int)relative_map, pyramid_out, n_images);
+    if (e != cudaSuccess) {
+      set_error("rdm_decompose: launch: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    return launch_status("decompose_cluster_kernel");
   }
-  if (cur_f64) {
+  if (in_is_f64) {
     e = ensure_dyn_smem(decompose_kernel<double>, smem, smem_set_decompose_kernel_double_);
     if (e == cudaSuccess)
-      decompose_kernel<double><<<(unsigned)n_images, 256, smem, (cudaStream_t)stream>>>((const double*)cur, s, nc, relative_map, pyramid_out, n_images);
+      decompose_kernel<double><<<(unsigned)n_images, 256, smem, (cudaStream_t)stream>>>((const double*)in, side, n, relative_map, pyramid_out, n_images);
   } else {
     e = ensure_dyn_smem(decompose_kernel<float>, smem, smem_set_decompose_kernel_float_);
     if (e == cudaSuccess)
-      decompose_kernel<float><<<(unsigned)n_images, 256, smem, (cudaStream_t)stream>>>((const float*)cur, s, nc, relative_map, pyramid_out, n_images);
+      decompose_kernel<float><<<(unsigned)n_images, 256, smem, (cudaStream_t)stream>>>((const float*)in, side, n, relative_map, pyramid_out, n_images);
   }
   if (e != cudaSuccess) {
     set_error("rdm_decompose: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -1192,4 +1338,47 @@ extern "C" int rdm_fuse_tail(const int64_t* x_d1, const float* const* rel, const
     return (int)e;
   }
   return launch_status("fuse_tail_kernel");
+}
+
+static size_t smem_set_gt_prepare_float_[64];
+static size_t smem_set_gt_prepare_double_[64];
+
+extern "C" int rdm_gt_prepare(const void* y_raw, int32_t in_is_f64, int64_t n_images, int32_t in_h, int32_t in_w, double sid_K,
+                              double sid_alpha, double sid_log_ratio, double* y_out, double* pyramid_out, int32_t* ord_target_out,
+                              rdm_stream_t stream) {
+  RDM_REQUIRE(y_raw && y_out && pyramid_out && ord_target_out, "rdm_gt_prepare: null pointer");
+  RDM_REQUIRE(in_h >= 1 && in_w >= 1 && in_h <= 4096 && in_w <= 4096, "rdm_gt_prepare: bad input size %d x %d", in_h, in_w);
+  RDM_REQUIRE(n_images >= 0 && n_images * kBandCluster < (1ll << 31), "rdm_gt_prepare: bad n_images");
+  RDM_REQUIRE(sid_alpha > 0.0 && sid_log_ratio != 0.0, "rdm_gt_prepare: bad SID parameters");
+  if (n_images == 0) return 0;
+  const size_t smem = sizeof(BandSmem);
+  cudaError_t e = in_is_f64 ? ensure_dyn_smem(gt_prepare_kernel<double>, smem, smem_set_gt_prepare_double_)
+                            : ensure_dyn_smem(gt_prepare_kernel<float>, smem, smem_set_gt_prepare_float_);
+  if (e != cudaSuccess) {
+    set_error("rdm_gt_prepare: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    return (int)e;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(n_images * kBandCluster));
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kBandCluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (in_is_f64)
+    e = cudaLaunchKernelEx(&cfg, gt_prepare_kernel<double>, (const double*)y_raw, (int)in_h, (int)in_w, n_images, sid_K, sid_alpha,
+                           sid_log_ratio, y_out, pyramid_out, ord_target_out);
+  else
+    e = cudaLaunchKernelEx(&cfg, gt_prepare_kernel<float>, (const float*)y_raw, (int)in_h, (int)in_w, n_images, sid_K, sid_alpha,
+                           sid_log_ratio, y_out, pyramid_out, ord_target_out);
+  if (e != cudaSuccess) {
+    set_error("rdm_gt_prepare: launch: %s", cudaGetErrorString(e));
+    return (int)e;
+  }
+  return launch_status("gt_prepare_kernel");
 }

@@ -412,6 +412,48 @@ def _decompose_backward(ctx, g):
 decompose.register_autograd(_decompose_backward, setup_context=_decompose_setup)
 
 
+_SID_CONST = {}
+
+
+def _sid_constants(K: float = 90.0, alpha: float = 0.02, beta: float = 10.0):
+    """The f32 scalars utils.depth2label_sid holds (utils.py:196-198, 205), as Python floats: K, alpha and
+    log(beta / alpha) evaluated by torch in f32 exactly like the reference does."""
+    key = (K, alpha, beta)
+    if key not in _SID_CONST:
+        a, b, k = torch.tensor(alpha), torch.tensor(beta), torch.tensor(K)
+        _SID_CONST[key] = (float(k), float(a), float(torch.log(b / a)))
+    return _SID_CONST[key]
+
+
+@torch.library.custom_op("rdm::gt_prepare", mutates_args=())
+def gt_prepare(y_raw: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+    """Ground-truth preparation of the training step in one launch (network/module.py:68, 74-78, 119-127, 134-149,
+    utils.py:195-211): y_raw (B,1,H,W) f32|f64 -> (y (B,1,128,128) f64 masked, packed component targets (level-major,
+    see `unpack_pyramid(packed, B, 128, False)`; slot 0 = the ordinal D_0), SID labels (B,1,8,8) int32)."""
+    _need_cuda("gt_prepare", y_raw)
+    if y_raw.dim() != 4 or y_raw.shape[1] != 1 or y_raw.dtype not in (torch.float32, torch.float64):
+        raise RuntimeError("rdm::gt_prepare: expected (B,1,H,W) f32 or f64")
+    x = y_raw.contiguous()
+    B, _, H, W = x.shape
+    dev = x.device
+    lib = load()
+    y = torch.empty((B, 1, 128, 128), dtype=torch.float64, device=dev)
+    pyr = torch.empty((B * lib.rdm_pyramid_len(128, 0),), dtype=torch.float64, device=dev)
+    ord_t = torch.empty((B, 1, 8, 8), dtype=torch.int32, device=dev)
+    K, a, lr = _sid_constants()
+    with torch.cuda.device(dev):
+        check(lib.rdm_gt_prepare(_p(x), 1 if x.dtype == torch.float64 else 0, B, H, W, K, a, lr, _p(y), _p(pyr), _p(ord_t), _stream()),
+              "rdm_gt_prepare")
+    return y, pyr, ord_t
+
+
+@gt_prepare.register_fake
+def _(y_raw):
+    B = y_raw.shape[0]
+    return (y_raw.new_empty((B, 1, 128, 128), dtype=torch.float64), y_raw.new_empty((B * 21845,), dtype=torch.float64),
+            y_raw.new_empty((B, 1, 8, 8), dtype=torch.int32))
+
+
 def unpack_pyramid(packed: Tensor, batch: int, side: int, relative_map: bool) -> List[Tensor]:
     """Dense views [D_0?, F_1, ..., F_n], each (B,1,2^k,2^k), of the level-major pyramid buffer."""
     n = int(math.log2(side))

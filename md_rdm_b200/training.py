@@ -41,6 +41,8 @@ class TrainingStep:
         self.y_raw = torch.ones((self.B, 1, gt_side, gt_side), dtype=f64, device=dev)
         self.fused_gt = bool(fused_gt) and hasattr(R, "gt_prepare")
         self._host: Optional[Dict[str, torch.Tensor]] = None
+        self._graph: Optional[torch.cuda.CUDAGraph] = None
+        self._graph_out: Optional[Dict[str, torch.Tensor]] = None
         self._loss_host: Optional[torch.Tensor] = None
         self._grad_host: Optional[torch.Tensor] = None
 
@@ -87,6 +89,32 @@ class TrainingStep:
         loss.backward()
         return {"loss": loss.detach(), "mse": mse.detach(), "fine": fine, "ord": ord_loss.detach(), "final": final.detach()}
 
+    # ------------------------------------------------------------------ CUDA graph of the whole step
+    def capture(self) -> None:
+        """Record one whole step (forward, losses, backward) into a CUDA graph: the step is ~60 small launches, so
+        replaying it removes the host dispatch that otherwise dominates.  Inputs are the static buffers filled by
+        `load()` / `step_from_host()`; the loss terms and the gradients land in static tensors."""
+        with torch.cuda.device(self.device):
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):                      # warm-up outside capture (lazy initialisations, allocator)
+                    self.step()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = self.step()
+            self._graph, self._graph_out = g, out
+
+    def replay(self) -> Dict[str, torch.Tensor]:
+        """One step from the captured graph; `weights.grad` / `logits.grad` and the returned loss terms are the
+        graph's static tensors (overwritten by the next replay)."""
+        if self._graph is None:
+            self.capture()
+        self._graph.replay()
+        return self._graph_out
+
     def launches_per_step(self) -> int:
         """Kernels of librdm_b200 per step (torch's own elementwise kernels for the losses come on top)."""
         gt = 1 if self.fused_gt else 7
@@ -114,7 +142,7 @@ class TrainingStep:
                 self.plan.src[s].copy_(t, non_blocking=True)
             self.y_raw.copy_(h["y_raw"], non_blocking=True)
             self.logits.copy_(h["logits"], non_blocking=True)
-        out = self.step()
+        out = self.replay() if self._graph is not None else self.step()
         self._loss_host.copy_(out["loss"], non_blocking=True)
         self._grad_host.copy_(self.weights.grad, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()

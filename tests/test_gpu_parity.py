@@ -1032,3 +1032,44 @@ def test_stress_tail_bands_and_gm_cluster(dev, books):
         assert torch.equal(R.gm_normalize(y), n0), rep
         assert torch.equal(R.decompose(n0, False), p0), rep
     assert torch.equal(R.gm_normalize(y[:3]), n0[:3])
+
+
+def test_gt_prepare_one_launch(dev):
+    """resize 226->128 + mask + gm-normalise + decompose n=7 + ordinal target in ONE launch
+    (rdm::gt_prepare) against the oracle's restatement of MOD:68-78, 119-127 (<= 1e-11; the oracle itself is pinned to the
+    reference by gt_decompose_b2.npz, whose stored map is already masked and so cannot be fed through the mask again) and,
+    bit for bit, against the stand-alone ops it replaces."""
+    import bench
+    import md_rdm_b200.computations as cp
+    from md_rdm_b200.loss import depth2label_sid
+    from md_rdm_b200.ops import unpack_pyramid
+    for seed, smooth in ((11, True), (12, False)):
+        if smooth:
+            y_raw, _ = bench.synthetic_gt(5, seed)
+        else:
+            gen = torch.Generator().manual_seed(seed)
+            y_raw = 0.5 + 9.5 * torch.rand(5, 1, 226, 226, generator=gen, dtype=torch.float64)
+            y_raw = y_raw * (torch.rand(5, 1, 226, 226, generator=gen) > 0.05)
+        for dt in (torch.float64, torch.float32):
+            yr = y_raw.to(dt)
+            y, pyr, ord_t = R.gt_prepare(yr.to(dev))
+            comps = unpack_pyramid(pyr, 5, 128, False)
+            # oracle (CPU): MOD:68, 74-78, 119-127
+            y_ref = fr.mask_target(fr.resize(yr, 128))
+            tg = fr.training_targets(y_ref)
+            lab_ref = fr.depth2label_sid(fr.resize(y_ref, 8))
+            # (masked pixels sit at 1e-4 + a bicubic residue: the residue's rounding shows at ~1e-12 relative)
+            assert torch.allclose(y.cpu(), y_ref, rtol=1e-12, atol=1e-13)
+            for i in range(1, 8):
+                assert torch.allclose(comps[i].cpu(), tg[i], rtol=1e-11, atol=1e-12), (seed, i)
+            # stand-alone ops on the same device (the previous four-launch path): labels and ordinal D_0 identical
+            y2 = cp.resize(yr.to(dev), 128)
+            y2 = (y2 * (y2 > 0)) + ((y2 <= 0) + 1e-4)
+            assert torch.equal(y2, y)
+            lab2 = depth2label_sid(cp.resize(y2, 8))
+            assert torch.equal(ord_t, lab2)
+            d0 = cp.decompose_depth_map([], R.gm_normalize(lab2.long()), 3)[::-1][0]
+            assert _eq_nan(comps[0], d0)
+            if smooth:      # white-noise ground truth drives the 8x8 bicubic below zero -> NaN labels in the reference
+                assert torch.equal(ord_t.cpu(), lab_ref)
+                assert _rel_err(comps[0].cpu(), tg[0]) < 1e-6
