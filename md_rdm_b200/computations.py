@@ -83,10 +83,13 @@ def split_matrix(d_n, d_n_1):
     return first, second
 
 
-def reconstruct(splits):
+def reconstruct(splits, correct_tiling=False):
     """CP:218-238, as written: every block-column repeats the vertical stack of the first
-    `ratio` pages (pages >= ratio never reach the output)."""
+    `ratio` pages (pages >= ratio never reach the output).  `correct_tiling=True` (not in the
+    reference) puts page i*ratio+j at block (i, j), the inverse of split_matrix."""
     ratio = int(len(splits) ** (1 / 2))
+    if correct_tiling:
+        return torch.cat([torch.cat(splits[i * ratio:(i + 1) * ratio], 3) for i in range(ratio)], 2)
     rows = [torch.cat(splits[0:ratio], 2) for _ in range(ratio)]
     return torch.cat(rows, dim=3)
 

@@ -58,7 +58,8 @@ struct AlsScaleDev {
   int32_t kind, rows, pages, side, limit;
   int32_t cta_begin;   // first blockIdx.x of this scale
   int32_t cta_count;   // working CTAs of this scale (64-row: groups x cluster; pages: CTAs that walk the (group, page) items with this stride)
-  int32_t dense_only;  // page scale: every item is iterated here (RDM_ALS_DENSE_ONLY, or a source kind the compact kernel does not take)
+  int32_t dense_only;  // page scale: every item is iterated here (RDM_ALS_DENSE_ONLY / TRUE_TRANSPOSE, or a source kind the compact kernel does not take)
+  int32_t flags;       // RDM_ALS_* bits
 };
 
 struct AlsParams {
@@ -78,6 +79,7 @@ struct AlsSmem {
   float thr_f[kThrPad];
   float lvl_f[kLvl + 3];
   float inv_f[4][64];                 // 1/d (pair build fused, 64-row units)
+  float qT[8][64];                    // RDM_ALS_TRUE_TRANSPOSE: per-warp column sums of R^T p
   float rm[256];                      // group rmse record (64-row: one row of 64 per unit team)
   float recu[128];                    // SSE record of the unit just iterated (page fallback)
   double recg[128];                   // group SSE record accumulated over the units (page fallback)
@@ -462,9 +464,11 @@ constexpr float kDirectFrac = 0.015f;
 // floats of shared scratch.  Without RECORD the same iterates are computed (bit-identical: the record never
 // feeds back into p or q) and nothing else: this is how the selected iterate p_k* is re-materialised once the
 // group-wide arg-min is known, instead of keeping every iterate.
+// tt (RDM_ALS_TRUE_TRANSPOSE, off by default): the q-update uses R^T - q_c = sum_i R[i][c] p_i / (|p|^2 + lambda) - instead of
+// the reference's R.view(B,W,H) reshape (CP:64, CP:133).
 template <int G, bool RECORD>
 __device__ __forceinline__ float als_iterate(const float2 (&R)[4][8], AlsSmem& sm, float* __restrict__ E, int unit, int lt, int n_iter,
-                                             float* __restrict__ rec) {
+                                             float* __restrict__ rec, bool tt) {
   constexpr int NW = 2 * G;
   constexpr int NT = 64 * G;
   constexpr int EH = NT / 2;                     // two rows (lanes l, l^4) share one slot
@@ -531,17 +535,44 @@ __device__ __forceinline__ float als_iterate(const float2 (&R)[4][8], AlsSmem& s
       const float er = (r2h - (sm1 - bb)) + (ph - bb);
       ef = fmaxf(sm1 + (er + (r2l + pl)), 0.f);
     }
-    float u, pseg;
-    tile_dot(R, pop, m.cb, u, pseg);             // this row's share of q_{ib+cb}; |p segment r'|^2
-    sts_f32(qpart + 4 * (64 * qp_row + m.ib + m.cb), u);
-    if constexpr (G == 4) {
-      if (m.lw < 4 && m.lane == 0) sts_f32(ppart + 4 * m.rp, pseg);
-    }
-    unit_barrier(bar_id, NT);                    // B: q partials (and |p|^2 segments) visible
-    float npp = pseg;
-    if constexpr (G == 4) {
-      const float4 a = lds_v4f32(ppart);
-      npp = (a.x + a.y) + (a.z + a.w);
+    float npp;
+    if (tt) {
+      // column sums of this thread's 4 x 16 tile against its four p entries, reduced over the 8 lanes of the warp that
+      // hold the same columns, then over the unit's warps through shared memory (fixed order: deterministic)
+      float pj[4], c16[16];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) pj[j] = lds_f32(ps + 4 * m.row(j));
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        c16[2 * e] = fmaf(R[3][e].x, pj[3], fmaf(R[2][e].x, pj[2], fmaf(R[1][e].x, pj[1], R[0][e].x * pj[0])));
+        c16[2 * e + 1] = fmaf(R[3][e].y, pj[3], fmaf(R[2][e].y, pj[2], fmaf(R[1][e].y, pj[1], R[0][e].y * pj[0])));
+      }
+#pragma unroll
+      for (int o = 4; o <= 16; o <<= 1)
+#pragma unroll
+        for (int e = 0; e < 16; ++e) c16[e] += __shfl_xor_sync(0xffffffffu, c16[e], o);
+      if ((m.lane >> 2) == 0)
+#pragma unroll
+        for (int e = 0; e < 16; ++e) sm.qT[gw][16 * m.cb + e] = c16[e];
+      const float w = warp_sum(p * p);
+      if (m.lane == 0) sts_f32(ppart + 4 * gw, w);
+      unit_barrier(bar_id, NT);                  // B: column sums and |p|^2 parts visible
+      npp = 0.f;
+#pragma unroll
+      for (int w2 = 0; w2 < NW; ++w2) npp += lds_f32(ppart + 4 * (unit * NW + w2));
+    } else {
+      float u, pseg;
+      tile_dot(R, pop, m.cb, u, pseg);           // this row's share of q_{ib+cb}; |p segment r'|^2
+      sts_f32(qpart + 4 * (64 * qp_row + m.ib + m.cb), u);
+      if constexpr (G == 4) {
+        if (m.lw < 4 && m.lane == 0) sts_f32(ppart + 4 * m.rp, pseg);
+      }
+      unit_barrier(bar_id, NT);                  // B: q partials (and |p|^2 segments) visible
+      npp = pseg;
+      if constexpr (G == 4) {
+        const float4 a = lds_v4f32(ppart);
+        npp = (a.x + a.y) + (a.z + a.w);
+      }
     }
     // the direct evaluation (rare on noise-like maps) needs p_k (ps) and q_{k-1} (this warp's old q copy)
     const uint32_t qop_k = qop;
@@ -549,7 +580,14 @@ __device__ __forceinline__ float als_iterate(const float2 (&R)[4][8], AlsSmem& s
     if (k < n_iter) {
       // every warp finalises q for itself (no further barrier), into its other q buffer
       float u0, u1;
-      if constexpr (G == 4) {
+      if (tt) {
+        u0 = u1 = 0.f;
+#pragma unroll
+        for (int w2 = 0; w2 < NW; ++w2) {
+          u0 += sm.qT[unit * NW + w2][m.lane];
+          u1 += sm.qT[unit * NW + w2][m.lane + 32];
+        }
+      } else if constexpr (G == 4) {
         const uint32_t q0a = qpart + 4 * m.lane;
         const float a0 = lds_f32(q0a), a1 = lds_f32(q0a + 256), a2 = lds_f32(q0a + 512), a3 = lds_f32(q0a + 768);
         const float b0 = lds_f32(q0a + 128), b1 = lds_f32(q0a + 384), b2 = lds_f32(q0a + 640), b3 = lds_f32(q0a + 896);
@@ -640,12 +678,7 @@ __device__ __forceinline__ void emit_unit(const AlsScaleDev& sc, AlsSmem& sm, in
   const int bar_id = (G == 4) ? 0 : 1 + unit;
   const int64_t img = unit_idx / sc.pages;
   const int pg = (int)(unit_idx - img * sc.pages);
-  float pw;
-  {
-    const float x = logf(p) * (1.0f / ((float)ROWS * (float)ROWS));
-    pw = 1.0f + fmaf(fmaf(x, 1.0f / 6.0f, 0.5f) * x, x, x);
-    if (!(p > 0.0f) || !(fabsf(x) < 3e-3f)) pw = (float)pow((double)p, 1.0 / ((double)ROWS * (double)ROWS));   // zeros, negatives, NaN, huge ratios
-  }
+  const float pw = gm_factor(p, ROWS, (sc.flags & RDM_ALS_TRUE_GM) != 0);
   const float prod = warp_prod(pw);
   unit_barrier(bar_id, NT);
   float* scratch = sm.p_s + unit * 64;
@@ -663,9 +696,12 @@ __device__ __forceinline__ void emit_unit(const AlsScaleDev& sc, AlsSmem& sm, in
     } else {
       const int side = sc.side, ratio = side >> 4;
       float* mp = sc.map_out + img * (int64_t)side * side;
-      // CP:218-238 as written: block-row j of every block-column holds page j (< ratio)
-      if (pg < ratio)
+      if (sc.flags & RDM_ALS_CORRECT_TILING) {   // page (i, j) to block (i, j): what CP:218-238 evidently intended
+        const int pi = pg / ratio, pj = pg - pi * ratio;
+        mp[(16 * pi + (row >> 4)) * side + 16 * pj + (row & 15)] = out;
+      } else if (pg < ratio) {   // CP:218-238 as written: block-row j of every block-column holds page j (< ratio)
         for (int bc = 0; bc < ratio; ++bc) mp[(16 * pg + (row >> 4)) * side + 16 * bc + (row & 15)] = out;
+      }
     }
   }
 }
@@ -747,6 +783,7 @@ __global__ void __launch_bounds__(kAlsThreads, 2) als_kernel(const __grid_consta
   }
   __syncthreads();
   const int limit = sc.limit;
+  const bool tt = (sc.flags & RDM_ALS_TRUE_TRANSPOSE) != 0;
 
   if (pages) {
     // ---- page items without pair structure: sequential units, the record scratch E aliases the staging tile
@@ -760,7 +797,7 @@ __global__ void __launch_bounds__(kAlsThreads, 2) als_kernel(const __grid_consta
       for (int b = 0; b < group; ++b) {
         const int64_t unit_idx = (g * group + b) * sc.pages + pg;
         load_unit<4>(R, sc, sm, tile, unit_idx, 0, tid, true);
-        als_iterate<4, true>(R, sm, tile, 0, tid, limit, sm.recu);
+        als_iterate<4, true>(R, sm, tile, 0, tid, limit, sm.recu, tt);
         __syncthreads();
         for (int k = tid; k <= limit; k += kAlsThreads) sm.recg[k] += (double)sm.recu[k];   // images in order, as CP:172-173 sums them
         __syncthreads();
@@ -775,7 +812,7 @@ __global__ void __launch_bounds__(kAlsThreads, 2) als_kernel(const __grid_consta
       for (int b = 0; b < group; ++b) {
         const int64_t unit_idx = (g * group + b) * sc.pages + pg;
         load_unit<4>(R, sc, sm, tile, unit_idx, 0, tid, false);
-        const float p = als_iterate<4, false>(R, sm, tile, 0, tid, kstar, nullptr);
+        const float p = als_iterate<4, false>(R, sm, tile, 0, tid, kstar, nullptr, tt);
         emit_unit<4>(sc, sm, unit_idx, 0, tid, p);
         __syncthreads();
       }
@@ -798,7 +835,7 @@ __global__ void __launch_bounds__(kAlsThreads, 2) als_kernel(const __grid_consta
     if (b < group) {
       const int64_t unit_idx = g * group + b;
       load_unit<1>(R, sc, sm, tile_u, unit_idx, unit, lt, true);
-      als_iterate<1, true>(R, sm, E_u, unit, lt, limit, sc.ws + unit_idx * stride64);
+      als_iterate<1, true>(R, sm, E_u, unit, lt, limit, sc.ws + unit_idx * stride64, tt);
     }
   }
   __threadfence();
@@ -832,7 +869,7 @@ __global__ void __launch_bounds__(kAlsThreads, 2) als_kernel(const __grid_consta
     if (b < group) {
       const int64_t unit_idx = g * group + b;
       if (rounds > 1) load_unit<1>(R, sc, sm, tile_u, unit_idx, unit, lt, false);   // single round: the tile is still in registers
-      const float p = als_iterate<1, false>(R, sm, E_u, unit, lt, kstar, nullptr);
+      const float p = als_iterate<1, false>(R, sm, E_u, unit, lt, kstar, nullptr, tt);
       emit_unit<1>(sc, sm, unit_idx, unit, lt, p);
     }
   }
@@ -941,9 +978,10 @@ extern "C" int rdm_als_fused_phases(const rdm_als_scale_t* scales, int32_t n_sca
     d.cta_begin = (int32_t)ctas;
     // page scales the compact kernel can take (rdm_als_sparse.cu) keep a few strided fallback CTAs here, each of
     // which normally finds nothing to do; every other page scale gets one CTA per (group, page) item
-    const bool compact_eligible = h.rows == 256 && !(h.flags & RDM_ALS_DENSE_ONLY) &&
+    const bool compact_eligible = h.rows == 256 && !(h.flags & (RDM_ALS_DENSE_ONLY | RDM_ALS_TRUE_TRANSPOSE)) &&
                                   (h.src_kind == RDM_SRC_RAW_F64 || h.src_kind == RDM_SRC_VAL_F64 || h.src_kind == RDM_SRC_MAP_F32);
     d.dense_only = (h.rows == 256 && !compact_eligible) ? 1 : 0;
+    d.flags = h.flags;
     int64_t n;
     if (h.rows == 64) {
       n = n_groups * cluster;

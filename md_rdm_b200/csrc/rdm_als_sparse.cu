@@ -417,6 +417,7 @@ struct PagesScaleDev {
   int32_t* kstar_out;
   int32_t pages, side, limit;
   int32_t cta_begin;   // first (group, page) item of this scale
+  int32_t flags;       // RDM_ALS_TRUE_GM | RDM_ALS_CORRECT_TILING
 };
 struct PagesParams {
   PagesScaleDev s[kMaxSparseScales];
@@ -711,14 +712,9 @@ __device__ __forceinline__ void pages_emit(const PagesScaleDev& sc, int64_t unit
   const int row_base = 32 * rh + 4 * kq;
   const int off_s[2] = {row_base + 16 * (rh & 1), row_base + 16 * ((rh & 1) ^ 1)};
   float prod = 1.0f;
+  const bool true_gm = (sc.flags & RDM_ALS_TRUE_GM) != 0;
 #pragma unroll
-  for (int t = 0; t < 8; ++t) {
-    const float p = pv[t];
-    const float x = logf(p) * (1.0f / 65536.0f);
-    float pw = 1.0f + fmaf(fmaf(x, 1.0f / 6.0f, 0.5f) * x, x, x);
-    if (!(p > 0.0f) || !(fabsf(x) < 3e-3f)) pw = (float)pow((double)p, 1.0 / 65536.0);   // zeros, negatives, NaN, huge ratios
-    prod *= pw;
-  }
+  for (int t = 0; t < 8; ++t) prod *= gm_factor(pv[t], 256, true_gm);
   const float gm = warp_prod(prod);
   const int64_t img = unit_idx / sc.pages;
   const int pg = (int)(unit_idx - img * sc.pages);
@@ -730,8 +726,12 @@ __device__ __forceinline__ void pages_emit(const PagesScaleDev& sc, int64_t unit
     if (sc.map_out) {
       const int side = sc.side, ratio = side >> 4;
       float* mp = sc.map_out + img * (int64_t)side * side;
-      if (pg < ratio)
+      if (sc.flags & RDM_ALS_CORRECT_TILING) {   // page (i, j) to block (i, j): what CP:218-238 evidently intended
+        const int pi = pg / ratio, pj = pg - pi * ratio;
+        *reinterpret_cast<float4*>(mp + (16 * pi + (row >> 4)) * side + 16 * pj + (row & 15)) = o;
+      } else if (pg < ratio) {
         for (int bc = 0; bc < ratio; ++bc) *reinterpret_cast<float4*>(mp + (16 * pg + (row >> 4)) * side + 16 * bc + (row & 15)) = o;
+      }
     }
   }
 }
@@ -874,7 +874,7 @@ int als_sparse_launch(const rdm_als_scale_t* scales, int32_t n_scales, int64_t n
   const int64_t n_groups = n_images / group;
   for (int k = 0; k < n_scales; ++k) {
     const rdm_als_scale_t& h = scales[k];
-    if (h.rows != 256 || (h.flags & RDM_ALS_DENSE_ONLY)) continue;
+    if (h.rows != 256 || (h.flags & (RDM_ALS_DENSE_ONLY | RDM_ALS_TRUE_TRANSPOSE))) continue;   // the transpose variant lives in the dense kernel
     const bool is_map = h.src_kind == RDM_SRC_MAP_F32;
     if (!(is_map || h.src_kind == RDM_SRC_RAW_F64 || h.src_kind == RDM_SRC_VAL_F64)) continue;
     const bool quant = h.src_kind != RDM_SRC_VAL_F64;
@@ -905,6 +905,7 @@ int als_sparse_launch(const rdm_als_scale_t* scales, int32_t n_scales, int64_t n
     a.side = h.side;
     a.limit = h.limit;
     a.cta_begin = (int32_t)n_items;
+    a.flags = h.flags;
     n_items += n_groups * h.pages;
   }
   if (n_items == 0) return 0;

@@ -61,6 +61,21 @@ __host__ __device__ __forceinline__ int64_t als_ws_stride(int rows, int limit) {
   return rows == 256 ? kCompactFloats + 8 : ((limit + 1 + 3) & ~3);
 }
 
+// ---- the normaliser of an ALS map ----------------------------------------------------------------------
+// quick_gm(p, H) (CP:76, CP:146, CP:244-255) raises every entry to 1 / rc^2 with rc = H = rows, i.e. to 1 / rows^2 -
+// not the geometric mean (that would be 1 / rows).  RDM_ALS_TRUE_GM asks for the geometric mean.
+// Reference exponent 2^-12 / 2^-16: p^(e) = exp(x) with |x| = |ln p| e < 3e-3, so 1 + x + x^2/2 + x^3/6 is exact to f32
+// rounding (x^4/24 < 4e-12) and p = 1 gives exactly 1; anything else goes through pow() in f64.
+__device__ __forceinline__ float gm_factor(float p, int rows, bool true_gm) {
+  if (!true_gm) {
+    const float x = logf(p) * (1.0f / ((float)rows * (float)rows));
+    const float pw = 1.0f + fmaf(fmaf(x, 1.0f / 6.0f, 0.5f) * x, x, x);
+    if (p > 0.0f && fabsf(x) < 3e-3f) return pw;
+    return (float)pow((double)p, 1.0 / ((double)rows * (double)rows));   // zeros, negatives, NaN, huge ratios
+  }
+  return (float)pow((double)p, 1.0 / (double)rows);
+}
+
 // ---- warp helpers -------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -21,11 +21,14 @@ LIMIT_PAGE = 100  # RN:378, RN:392
 
 
 class Ordinal_Layer(nn.Module):
-    def __init__(self, decoder_id, DORN, quantizer):
+    def __init__(self, decoder_id, DORN, quantizer, flags: int = 0):
+        """`flags` (not in the reference): `_cabi.ALS_TRUE_TRANSPOSE | ALS_TRUE_GM | ALS_CORRECT_TILING`, the
+        "paper-correct" knobs of SURVEY 8f rank 4; 0 = the reference's behaviour."""
         super().__init__()
         self.quant = quantizer
         self.id = decoder_id - 3
         self.dorn = DORN
+        self.flags = int(flags)
 
     # ------------------------------------------------------------------ codebooks
     def _tables(self, id, device):
@@ -88,7 +91,7 @@ class Ordinal_Layer(nn.Module):
         # pair build + Lloyd + ALS + normalisation (+ page split / re-tiling for id > 4) in one
         # fused call; the pair matrix never exists in HBM.  One arg-min group per call (CP:172-173).
         rows, limit = (64, LIMIT_8) if self.id == 3 else (256, LIMIT_PAGE)
-        return R.als_rank1(x.float(), _cabi.SRC_MAP_F32, rows, side, limit, B, thr, lvl, False, False)[0]
+        return R.als_rank1(x.float(), _cabi.SRC_MAP_F32, rows, side, limit, B, thr, lvl, False, False, self.flags)[0]
 
 
 class Weights(nn.Module):

@@ -167,7 +167,11 @@ def _ridge_step(ratings: torch.Tensor, fixed: torch.Tensor) -> torch.Tensor:
     return (ratings @ fixed) @ torch.inverse(A)
 
 
-def als_rank1(Rq: torch.Tensor, limit: int, force_k=None):
+# "paper-correct" knobs, OFF by default; same bits as rdm_als_scale_t.flags in include/rdm_b200.h
+FLAG_TRUE_TRANSPOSE, FLAG_TRUE_GM, FLAG_CORRECT_TILING = 2, 4, 8
+
+
+def als_rank1(Rq: torch.Tensor, limit: int, force_k=None, flags: int = 0):
     """CP:38-85 (H=W=64) and CP:95-155 (H=256, W=64) in one routine.
 
     Returns (map (B,1,sqrt(H),sqrt(H)) f32, rmse record list[limit+1] of python
@@ -186,7 +190,8 @@ def als_rank1(Rq: torch.Tensor, limit: int, force_k=None):
 
     record.append(rmse())
     vecs.append(p)
-    Rv = R.view(B, W, H)
+    # CP:64 / CP:133 pass R.view(B,W,H) - a reshape; FLAG_TRUE_TRANSPOSE uses the transpose the ALS update calls for
+    Rv = R.transpose(1, 2).contiguous() if flags & FLAG_TRUE_TRANSPOSE else R.view(B, W, H)
     for _ in range(limit):
         p = _ridge_step(R, q)
         record.append(rmse())
@@ -198,21 +203,25 @@ def als_rank1(Rq: torch.Tensor, limit: int, force_k=None):
     # and no two implementations - or BLAS builds - agree on it; parity is then stated on the record and
     # on the iterate at a common index.
     p = vecs[kstar if force_k is None else force_k]
-    gm = torch.prod(torch.pow(p, 1 / (H * H)), dim=1)          # CP:248-253 with rc=H
+    # CP:248-253 with rc=H: exponent 1/H^2; FLAG_TRUE_GM: the geometric mean (exponent 1/H)
+    gm = torch.prod(torch.pow(p, 1 / H if flags & FLAG_TRUE_GM else 1 / (H * H)), dim=1)
     p = torch.div(p, gm.expand(B, H).view(B, H, 1))
     side = int(round(math.sqrt(H)))
     return p.view(B, 1, side, side), [float(r) for r in record], kstar
 
 
-def retile_pages(pages: Sequence[torch.Tensor]) -> torch.Tensor:
+def retile_pages(pages: Sequence[torch.Tensor], flags: int = 0) -> torch.Tensor:
     """CP:218-238 `reconstruct`, bug included: every block-column repeats the
-    vertical stack of pages[0:ratio]; pages >= ratio never reach the output."""
+    vertical stack of pages[0:ratio]; pages >= ratio never reach the output.
+    FLAG_CORRECT_TILING: page i*ratio+j goes to block (i, j), the inverse of split_matrix (CP:201-216)."""
     ratio = int(len(pages) ** 0.5)
+    if flags & FLAG_CORRECT_TILING:
+        return torch.cat([torch.cat(list(pages[i * ratio:(i + 1) * ratio]), 3) for i in range(ratio)], 2)
     col = torch.cat(list(pages[0:ratio]), 2)
     return torch.cat([col] * ratio, dim=3)
 
 
-def relative_decoder_tail(x: torch.Tensor, books, want_intermediates: bool = False, force_k=None):
+def relative_decoder_tail(x: torch.Tensor, books, want_intermediates: bool = False, force_k=None, flags: int = 0):
     """RN:358-396: non-DORN `Ordinal_Layer.forward` for a (B,1,s,s) f32 decoder
     map, s in {8,16,32,64,128}.  Returns the filled relative map (B,1,s,s) f32
     and, optionally, per-page intermediates (raw, bins, kstar, record)."""
@@ -222,7 +231,7 @@ def relative_decoder_tail(x: torch.Tensor, books, want_intermediates: bool = Fal
     if s == 8:
         raw = pair_v1(x)
         vals, bins = lloyd(raw, q, lv)
-        out, rec, k = als_rank1(vals, LIMIT_8, None if force_k is None else force_k[0])
+        out, rec, k = als_rank1(vals, LIMIT_8, None if force_k is None else force_k[0], flags)
         inter.append(dict(raw=raw, bins=bins, kstar=k, record=rec, page=out))
     else:
         dn_1 = resize_half(x)
@@ -230,10 +239,10 @@ def relative_decoder_tail(x: torch.Tensor, books, want_intermediates: bool = Fal
         for pi, (page, parent) in enumerate(split_pages(x, dn_1)):
             raw = pair_id(page, parent)
             vals, bins = lloyd(raw, q, lv)
-            o, rec, k = als_rank1(vals, LIMIT_PAGE, None if force_k is None else force_k[pi])
+            o, rec, k = als_rank1(vals, LIMIT_PAGE, None if force_k is None else force_k[pi], flags)
             outs.append(o)
             inter.append(dict(raw=raw, bins=bins, kstar=k, record=rec, page=o))
-        out = outs[0] if s == 16 else retile_pages(outs)
+        out = outs[0] if s == 16 else retile_pages(outs, flags)
     return (out, inter) if want_intermediates else out
 
 
@@ -316,7 +325,7 @@ def recombination(comps: Sequence[torch.Tensor], n: int = 7) -> torch.Tensor:
 
 # --------------------------------------------------------------------------- whole path
 def fusion_forward(x_d1: torch.Tensor, rel_maps: Sequence[torch.Tensor], weights: Sequence[torch.Tensor],
-                   books=None, want_intermediates: bool = False, force_k=None):
+                   books=None, want_intermediates: bool = False, force_k=None, flags: int = 0):
     """The path RN:103-133 executes with decoder 1 plus relative decoders at the
     scales of `rel_maps` (8, 16, 32, ... in that order), followed by
     `recombination` (MOD:132).
@@ -328,7 +337,7 @@ def fusion_forward(x_d1: torch.Tensor, rel_maps: Sequence[torch.Tensor], weights
     B = x_d1.shape[0]
     filled, inter = [], []
     for i, x in enumerate(rel_maps):
-        o, it = relative_decoder_tail(x, books, want_intermediates=True, force_k=None if force_k is None else force_k[i])
+        o, it = relative_decoder_tail(x, books, want_intermediates=True, force_k=None if force_k is None else force_k[i], flags=flags)
         filled.append(o)
         inter.append(it)
     rows = [decompose(gm_normalize(x_d1), 3)]                       # RN:117
