@@ -332,6 +332,13 @@ def stage_kernel_table(dev, batch):
         "gt_prepare_226": (lambda: R.gt_prepare(y226), batch * (226 * 226 * 8 + 131072 + 174760 + 256)),
         "recombination_128": (lambda: R.recombination(comps, 7), batch * (131072 + 4 * 21845)),
     }
+    # conv heads (RN:146) of decoders 7 / 8 fused with the pair build (reads C*s*s f32 per image)
+    from md_rdm_b200.fusion import FusionPlan
+    cplan = FusionPlan(batch, (16, 32), "map", device=dev, want_bins=False)
+    cf = {16: torch.randn(batch, 1664, 16, 16, generator=g).to(dev), 32: torch.randn(batch, 832, 32, 32, generator=g).to(dev)}
+    cw = {16: torch.randn(1664, generator=g).to(dev) * 0.01, 32: torch.randn(832, generator=g).to(dev) * 0.01}
+    cb = {16: torch.ones(1).to(dev) * 2, 32: torch.ones(1).to(dev) * 2}
+    cases["conv_head_16+32_with_pair_build"] = (lambda: cplan.enqueue_conv_heads(cf, cw, cb), batch * 4 * (1664 * 256 + 832 * 1024))
     out = {}
     for name, (fn, nbytes) in cases.items():
         stream = torch.cuda.Stream()

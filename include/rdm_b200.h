@@ -149,6 +149,18 @@ int rdm_als_fused(const rdm_als_scale_t* scales, int32_t n_scales, int64_t n_ima
  * ordered by an event); they are independent of each other. */
 int rdm_als_fused_phases(const rdm_als_scale_t* scales, int32_t n_scales, int64_t n_images,
                          int32_t group, int32_t phase_mask, rdm_stream_t stream);
+/* SURVEY 8f rank 3 - RN:146, RN:157 `Decoder.conv1` (1x1 conv, C channels -> the one-channel relative map) fused with
+ * the pair build of RN:259-284: feat (N,C,side,side) f32, weight (C) f32 (conv1.weight.view(-1)), bias (1) f32 or NULL.
+ * map_out (optional, NULL allowed when page_scale is given): (N,side,side) f32 decoder map.  page_scale (HOST pointer,
+ * optional, side >= 16): the scale descriptor a following rdm_als_fused_phases(..., RDM_ALS_PHASE_PAGES |
+ * RDM_ALS_PHASE_DENSE, ...) call will use - its ws receives the compact page form exactly as RDM_ALS_PHASE_SPARSIFY
+ * would leave it (so that phase is skipped and the map never touches HBM), bins_out / values_out are honoured.
+ * C must be a multiple of 8, side in {8,16,32,64}.  The map agrees with torch's conv to f32 rounding (different
+ * summation order); Lloyd bins are exact for the map this kernel produces. */
+int rdm_conv_head_f32(const float* feat, const float* weight, const float* bias, int64_t n_images,
+                      int32_t channels, int32_t side, float* map_out,
+                      const rdm_als_scale_t* page_scale, rdm_stream_t stream);
+
 /* Host-side copy of the compact page form's geometry (RN:266-273 + CP:269-295 window anchoring), for tests:
  * window_cols i32[256*9] = the nine window columns of every matrix row (row-major over the 3x3 window),
  * fill_col i32[256] = a column outside every window of that pixel row, compact u8[256*16] = source of each

@@ -51,6 +51,7 @@ PROTOTYPES = {
     "rdm_als_fused_phases": (c_int, [POINTER(AlsScale), c_int32, c_int64, c_int32, c_int32, c_void_p]),
     "rdm_als_ws_floats": (c_int64, [c_int32, c_int32, c_int32]),
     "rdm_sparsify_geometry": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "rdm_conv_head_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, POINTER(AlsScale), c_void_p]),
     "rdm_als_step_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_float, c_void_p, c_void_p]),
     "rdm_quick_gm": (c_int, [c_void_p, c_int32, c_int64, c_int64, c_int32, c_void_p, c_void_p]),
     "rdm_gm_normalize": (c_int, [c_void_p, c_int32, c_int64, c_int32, c_void_p, c_void_p]),

@@ -34,7 +34,9 @@
 // A unit whose matrix fails the check (an arbitrary matrix handed to cp.alternating_least_squares) is
 // left to the dense kernel (rdm_als.cu), which in turn skips the units flagged here.
 #include "rdm_common.cuh"
+#include <cooperative_groups.h>
 #include <type_traits>
+namespace cg = cooperative_groups;
 
 namespace rdm {
 
@@ -281,31 +283,23 @@ __global__ void __launch_bounds__(kBandRows) als_sparsify_raw_kernel(const __gri
   if (tid == 0) compact[kCompactFloats + band] = all_ok ? 1.0f : 0.0f;
 }
 
-// grid = units; thread = matrix row (pixel of the page).  RN:259-284 + CP:269-295 + CP:308-311 fused.
-__global__ void __launch_bounds__(256) als_sparsify_map_kernel(const __grid_constant__ SparseParams P) {
-  __shared__ double thr_d[kThrPad];
-  __shared__ double inv_d[64];
-  __shared__ float lvl_f[kLvl + 3];
-  __shared__ int sorted;
-  const int tid = threadIdx.x;
-  const int gunit = blockIdx.x;
-  const SparseScaleDev& sc = find_scale(P, gunit);
-  const int64_t unit = gunit - sc.unit_begin;
-  const int side = sc.side, ratio = side >> 4;
-  const int64_t img = unit / sc.pages;
-  const int pg = (int)(unit - img * sc.pages);
+// The compact form of ONE page straight from the decoder map (RN:259-284 + CP:269-295 + CP:308-311 fused: the pair
+// matrix never exists).  Called by the 256 threads of a CTA, thread = matrix row = pixel of the page; `map` may be
+// global or shared memory.  inv_d: 64 doubles of shared scratch.
+__device__ __forceinline__ void compact_page_from_map(const SparseScaleDev& sc, int64_t unit, const float* __restrict__ map, int side, int pg,
+                                                      const double* thr_d, const float* lvl_f, int srt, double* inv_d, int tid) {
+  const int ratio = side >> 4;
   const int pi = pg / ratio, pj = pg - pi * ratio;
-  const float* map = reinterpret_cast<const float*>(sc.src) + img * (int64_t)side * side;
   if (tid < 64) {
     const int y = 8 * pi + (tid >> 3), x = 8 * pj + (tid & 7);
     const double v = bicubic_half_at([&](int r, int c) { return (double)map[r * side + c]; }, y, x, side);
     inv_d[tid] = 1.0 / v;   // torch.pow(area,-1): IEEE reciprocal
   }
-  load_book(sc, thr_d, lvl_f, &sorted, tid, 256);   // ends with __syncthreads
-  const int srt = sorted;
+  __syncthreads();
   const int row = tid;
   const double d = (double)map[(16 * pi + (row >> 4)) * side + 16 * pj + (row & 15)];
-  const int r0 = min(row >> 5, 5), c0 = min((row & 15) >> 1, 5), span0 = min(((row & 15) >> 2) * 2, 4);
+  const RowGeom gm(row);
+  const int r0 = gm.r0, c0 = gm.c0, span0 = gm.span0;
   const int bf = lloyd_bin<double>(d, thr_d, srt);   // 55 of 64 columns hold d itself
   const float f = lvl_f[bf];
   float* compact = sc.ws + unit * als_ws_stride(256, sc.limit);
@@ -353,6 +347,131 @@ __global__ void __launch_bounds__(256) als_sparsify_map_kernel(const __grid_cons
       if (sc.bins) *reinterpret_cast<uint32_t*>(sc.bins + off + 4 * c4) = pk;
       if (sc.values) *reinterpret_cast<float4*>(sc.values + off + 4 * c4) = make_float4(v[0], v[1], v[2], v[3]);
     }
+  }
+}
+
+// grid = units; one page per CTA.
+__global__ void __launch_bounds__(256) als_sparsify_map_kernel(const __grid_constant__ SparseParams P) {
+  __shared__ double thr_d[kThrPad];
+  __shared__ double inv_d[64];
+  __shared__ float lvl_f[kLvl + 3];
+  __shared__ int sorted;
+  const int tid = threadIdx.x;
+  const int gunit = blockIdx.x;
+  const SparseScaleDev& sc = find_scale(P, gunit);
+  const int64_t unit = gunit - sc.unit_begin;
+  const int side = sc.side;
+  const int64_t img = unit / sc.pages;
+  const int pg = (int)(unit - img * sc.pages);
+  const float* map = reinterpret_cast<const float*>(sc.src) + img * (int64_t)side * side;
+  load_book(sc, thr_d, lvl_f, &sorted, tid, 256);   // ends with __syncthreads
+  compact_page_from_map(sc, unit, map, side, pg, thr_d, lvl_f, sorted, inv_d, tid);
+}
+
+// ---- the decoder's 1x1 conv head (RN:146, RN:157) fused with the pair build -----------------
+// conv1 maps the (C, s, s) feature block of a relative decoder to its one-channel map: out[p] = bias + sum_c w_c x[c][p].
+// That is a C-long reduction per pixel over C s^2 floats per image (0.5 .. 7 MB) - it moves more bytes than the whole
+// fusion path - so it is split over a thread-block CLUSTER of 8 CTAs per image: CTA r reduces channels
+// [r C/8, (r+1) C/8) for all pixels with coalesced 128-bit streaming loads (eight in flight per thread), the eight
+// partial maps are reduce-scattered through distributed shared memory (CTA r sums pixel slice r in rank order
+// and adds the bias), and the finished slices are broadcast back.  Every CTA then holds the map in shared memory and
+// builds the compact pair-matrix form of its share of the 16x16 pages (compact_page_from_map): for scales >= 16 the
+// decoder map never touches HBM (it is written only if the caller asks for it; the 8x8 scale, which the dense ALS
+// kernel reads from HBM, always asks).
+// Summation order: channels in increasing order within a lane, then lanes, then CTAs - fixed, but not cuDNN's or
+// MKL-DNN's: the map agrees with torch.nn.Conv2d to f32 rounding (~1e-6), so a ratio within that distance of a Lloyd
+// threshold can land in the neighbouring bin.  Bins are exact with respect to the map THIS kernel produces.
+constexpr int kConvCluster = 8;
+constexpr int kConvMaxPixels = 64 * 64;
+
+struct ConvSmem {
+  float part[kConvMaxPixels];        // this CTA's partial map (its channel range)
+  float map[kConvMaxPixels];         // the finished map
+  float lanes[4096];                 // cross-lane reduction scratch when pixels/4 < 256
+  double thr_d[kThrPad];
+  double inv_d[64];
+  float lvl_f[kLvl + 3];
+  int sorted;
+};
+
+__global__ void __launch_bounds__(256) conv_head_kernel(const float* __restrict__ feat, const float* __restrict__ weight,
+                                                        const float* __restrict__ bias, int channels, int side, float* __restrict__ map_out,
+                                                        const __grid_constant__ SparseScaleDev sc, int build_pages) {
+  extern __shared__ __align__(16) unsigned char conv_raw[];
+  ConvSmem& sm = *reinterpret_cast<ConvSmem*>(conv_raw);
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int64_t img = blockIdx.x / kConvCluster;
+  const int tid = threadIdx.x;
+  const int M = side * side, quads = M >> 2;
+  const int c_per = channels / kConvCluster, c_lo = rank * c_per;
+  const float* x = feat + (img * channels + c_lo) * (int64_t)M;
+  // ---- this CTA's channel range: thread (quad, lane): channels lane, lane + nl, ...
+  const int nl = quads >= 256 ? 1 : 256 / quads;         // channel lanes per pixel quad
+  for (int q0 = 0; q0 < quads; q0 += 256) {
+    const int quad = quads >= 256 ? q0 + tid : tid % quads;
+    const int cl = quads >= 256 ? 0 : tid / quads;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int c = cl;
+    for (; c + 7 * nl < c_per; c += 8 * nl) {
+      float4 v[8];
+      float w[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        v[u] = ldg_stream_f32x4(x + (int64_t)(c + u * nl) * M + 4 * quad);
+        w[u] = weight[c_lo + c + u * nl];
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        acc.x = fmaf(w[u], v[u].x, acc.x);
+        acc.y = fmaf(w[u], v[u].y, acc.y);
+        acc.z = fmaf(w[u], v[u].z, acc.z);
+        acc.w = fmaf(w[u], v[u].w, acc.w);
+      }
+    }
+    for (; c < c_per; c += nl) {
+      const float4 v = ldg_stream_f32x4(x + (int64_t)c * M + 4 * quad);
+      const float w = weight[c_lo + c];
+      acc.x = fmaf(w, v.x, acc.x);
+      acc.y = fmaf(w, v.y, acc.y);
+      acc.z = fmaf(w, v.z, acc.z);
+      acc.w = fmaf(w, v.w, acc.w);
+    }
+    if (nl == 1) {
+      *reinterpret_cast<float4*>(&sm.part[4 * quad]) = acc;
+    } else {
+      *reinterpret_cast<float4*>(&sm.lanes[4 * (cl * quads + quad)]) = acc;
+    }
+  }
+  if (nl > 1) {
+    __syncthreads();
+    for (int p = tid; p < M; p += 256) {
+      float t = 0.f;
+      for (int l = 0; l < nl; ++l) t += sm.lanes[l * M + p];   // lanes in order
+      sm.part[p] = t;
+    }
+  }
+  cluster.sync();   // every partial map is complete
+  // ---- reduce-scatter: CTA `rank` finishes pixels [rank M/8, (rank+1) M/8), then broadcasts them
+  {
+    const int per = M / kConvCluster;
+    const float b0 = bias ? bias[0] : 0.f;
+    for (int i = tid; i < per; i += 256) {
+      const int p = rank * per + i;
+      float t = 0.f;
+      for (int r = 0; r < kConvCluster; ++r) t += *cluster.map_shared_rank(&sm.part[p], r);   // CTAs in rank order
+      t += b0;
+      if (map_out) map_out[img * M + p] = t;
+      for (int r = 0; r < kConvCluster; ++r) *cluster.map_shared_rank(&sm.map[p], r) = t;
+    }
+  }
+  cluster.sync();   // the map is complete everywhere; no remote access after this
+  if (!build_pages) return;
+  // ---- compact page form of pages rank, rank + 8, ...
+  load_book(sc, sm.thr_d, sm.lvl_f, &sm.sorted, tid, 256);
+  for (int pg = rank; pg < sc.pages; pg += kConvCluster) {
+    compact_page_from_map(sc, img * sc.pages + pg, sm.map, side, pg, sm.thr_d, sm.lvl_f, sm.sorted, sm.inv_d, tid);
+    __syncthreads();   // inv_d is reused by the next page
   }
 }
 
@@ -940,6 +1059,63 @@ int als_sparse_launch(const rdm_als_scale_t* scales, int32_t n_scales, int64_t n
 }
 
 }  // namespace rdm
+
+extern "C" int rdm_conv_head_f32(const float* feat, const float* weight, const float* bias, int64_t n_images, int32_t channels, int32_t side,
+                                 float* map_out, const rdm_als_scale_t* page_scale, rdm_stream_t stream) {
+  using namespace rdm;
+  RDM_REQUIRE(feat && weight, "rdm_conv_head_f32: null pointer");
+  RDM_REQUIRE(side == 8 || side == 16 || side == 32 || side == 64, "rdm_conv_head_f32: side must be 8, 16, 32 or 64 (got %d)", side);
+  RDM_REQUIRE(channels >= kConvCluster && channels % kConvCluster == 0, "rdm_conv_head_f32: channels (%d) must be a multiple of %d", channels, kConvCluster);
+  RDM_REQUIRE(aligned16(feat) && (!map_out || aligned16(map_out)), "rdm_conv_head_f32: feat and map_out must be 16-byte aligned");
+  RDM_REQUIRE(n_images >= 0 && n_images * kConvCluster < (1ll << 31), "rdm_conv_head_f32: bad n_images");
+  RDM_REQUIRE(map_out || page_scale, "rdm_conv_head_f32: nothing to produce (map_out and page_scale are both NULL)");
+  SparseScaleDev d{};
+  int build = 0;
+  if (page_scale) {
+    const rdm_als_scale_t& h = *page_scale;
+    RDM_REQUIRE(side >= 16, "rdm_conv_head_f32: the compact page form exists for sides >= 16 (the 8x8 scale takes map_out)");
+    RDM_REQUIRE(h.rows == 256 && h.side == side && h.pages == (side / 16) * (side / 16), "rdm_conv_head_f32: page_scale does not describe a %dx%d map", side, side);
+    RDM_REQUIRE(h.ws && aligned16(h.ws) && h.thresholds && h.levels, "rdm_conv_head_f32: page_scale needs ws (16-byte aligned) and the codebook");
+    RDM_REQUIRE(h.limit >= 0 && h.limit <= 127, "rdm_conv_head_f32: limit out of range");
+    d.src = nullptr;
+    d.thr = h.thresholds;
+    d.lvl = h.levels;
+    d.bins = h.bins_out;
+    d.values = h.values_out;
+    d.ws = h.ws;
+    d.kind = RDM_SRC_MAP_F32;
+    d.pages = h.pages;
+    d.side = side;
+    d.limit = h.limit;
+    d.unit_begin = 0;
+    build = 1;
+  }
+  if (n_images == 0) return 0;
+  static size_t smem_conv[64];
+  cudaError_t e = ensure_dyn_smem(conv_head_kernel, sizeof(ConvSmem), smem_conv);
+  if (e != cudaSuccess) {
+    set_error("rdm_conv_head_f32: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    return (int)e;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(n_images * kConvCluster));
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = sizeof(ConvSmem);
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kConvCluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, conv_head_kernel, feat, weight, bias, (int)channels, (int)side, map_out, d, build);
+  if (e != cudaSuccess) {
+    set_error("rdm_conv_head_f32: launch: %s", cudaGetErrorString(e));
+    return (int)e;
+  }
+  return launch_status("conv_head_kernel");
+}
 
 // Host copy of the compact page form's geometry (computed by the same RowGeom the kernels use), so that the CPU test
 // suite can check it against the oracle's window mask without a GPU: per matrix row the nine window columns

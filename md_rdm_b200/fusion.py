@@ -16,6 +16,7 @@ source = "raw": inputs are materialised raw pair matrices (f32 64x64 for scale 8
 from __future__ import annotations
 
 import contextlib
+import ctypes
 import weakref
 from collections import OrderedDict
 from ctypes import c_void_p
@@ -196,6 +197,42 @@ class FusionPlan:
                 cur.wait_stream(side)
             else:
                 check(lib.rdm_als_fused(descs, n, self.N, self.group, st), "rdm_als_fused")
+
+    def run_from_features(self, feats: Dict[int, torch.Tensor], conv_w: Dict[int, torch.Tensor], conv_b: Dict[int, Optional[torch.Tensor]],
+                          write_maps: bool = False) -> torch.Tensor:
+        """start one step earlier, from the feature blocks the relative decoders' 1x1 conv heads
+        consume (RN:146, RN:157): feats[s] (N,C_s,s,s) f32, conv_w[s] = conv1.weight (1,C_s,1,1) or (C_s,), conv_b[s] =
+        conv1.bias (1,) or None.  One launch per scale does the conv AND builds the compact pair-matrix form, so
+        for s >= 16 the decoder map never reaches HBM (unless `write_maps`); then the page ALS, the dense ALS (8x8 map)
+        and the tail run as in run().  Needs source == "map".  `x_d1` and `weights` are taken from the plan's buffers."""
+        if self.source != "map":
+            raise RuntimeError("run_from_features needs a plan built with source='map'")
+        lib = self.lib
+        with self._guard():
+            st = c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            self.enqueue_conv_heads(feats, conv_w, conv_b, write_maps)
+            if self.scales:
+                check(lib.rdm_als_fused_phases(self._descs, len(self.scales), self.N, self.group, _cabi.PHASE_PAGES | _cabi.PHASE_DENSE, st),
+                      "rdm_als_fused_phases")
+            self._run_tail()
+        return self.depth
+
+    def enqueue_conv_heads(self, feats, conv_w, conv_b, write_maps: bool = False) -> None:
+        """The conv-head launches of run_from_features alone (one per scale)."""
+        st = c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        for i, s in enumerate(self.scales):
+            f = feats[s]
+            if f.dtype != torch.float32 or f.dim() != 4 or f.shape[0] != self.N or f.shape[2] != s or f.shape[3] != s or not f.is_contiguous():
+                raise RuntimeError(f"run_from_features: feats[{s}] must be a contiguous ({self.N},C,{s},{s}) f32 tensor")
+            w = conv_w[s].reshape(-1).float().contiguous()
+            b = conv_b.get(s)
+            b = None if b is None else b.reshape(-1).float().contiguous()
+            if w.numel() != f.shape[1]:
+                raise RuntimeError(f"run_from_features: conv_w[{s}] has {w.numel()} weights for {f.shape[1]} channels")
+            map_out = c_void_p(self.src[s].data_ptr()) if (s == 8 or write_maps) else c_void_p(0)
+            desc = ctypes.pointer(self._descs[i]) if s >= 16 else None
+            check(self.lib.rdm_conv_head_f32(c_void_p(f.data_ptr()), c_void_p(w.data_ptr()), c_void_p(b.data_ptr()) if b is not None else c_void_p(0),
+                                             self.N, int(f.shape[1]), s, map_out, desc, st), "rdm_conv_head_f32")
 
     def run_als_phase(self, phase_mask: int) -> None:
         """Only the ALS launches selected by phase_mask (`_cabi.PHASE_*`): used by bench.py to time the kernels one by one."""

@@ -1122,3 +1122,49 @@ def test_paper_correct_flags_vs_oracle(dev, books, flag_name):
     torch.cuda.synchronize()
     assert _eq_nan(a.depth, b.depth) and all(torch.equal(a.rel[s], b.rel[s]) for s in scales)
     assert _depth_ok(a.depth.cpu(), ref0["depth"])
+
+
+def test_conv_head_fused_with_pair_build(dev, books):
+    """the decoders' 1x1 conv heads (RN:146, RN:157) fused with the pair build.  The conv map agrees
+    with torch's own f32 conv to rounding; everything downstream is EXACT with respect to the map the kernel produced
+    (bins bit-equal to the oracle fed with that map, k* equal, depth within tolerance); for s >= 16 the map is only
+    written to HBM on request."""
+    from md_rdm_b200.fusion import FusionPlan
+    scales = (8, 16, 32, 64)
+    chans = {8: 2208, 16: 1664, 32: 832, 64: 416}          # _wsm_output_planes(6..9), RN:555-565
+    B = 3
+    g = torch.Generator().manual_seed(146)
+    x_d1, _, weights = fr.synthetic_batch(B, scales, seed=147)
+    feats, cw, cb, ref_maps = {}, {}, {}, {}
+    for s in scales:
+        C = chans[s]
+        f = torch.randn(B, C, s, s, generator=g) * 0.5
+        w = torch.randn(1, C, 1, 1, generator=g) / math.sqrt(C) * 0.6
+        b = torch.tensor([1.5])                                # keeps the map positive like a trained decoder's
+        ref_maps[s] = torch.nn.functional.conv2d(f.double(), w.double(), b.double())     # exact reference for the map
+        feats[s], cw[s], cb[s] = f.to(dev), w.to(dev), b.to(dev)
+    plan = FusionPlan(B, scales, "map", device=dev)
+    plan.load_inputs(x_d1.to(dev), [torch.ones(B, 1, s, s) for s in scales], torch.cat([t.reshape(-1) for t in weights]).to(dev))
+    for s in scales:
+        plan.src[s].fill_(-5.0)
+    plan.run_from_features(feats, cw, cb)
+    torch.cuda.synchronize()
+    assert float(plan.src[16].max()) == -5.0 and float(plan.src[64].max()) == -5.0     # maps of s >= 16 never written
+    first = {s: plan.rel[s].clone() for s in scales}
+    depth1 = plan.depth.clone()
+    plan.run_from_features(feats, cw, cb, write_maps=True)
+    torch.cuda.synchronize()
+    assert _eq_nan(plan.depth, depth1) and all(torch.equal(plan.rel[s], first[s]) for s in scales)
+    maps = [plan.src[s].cpu().clone() for s in scales]
+    for s, m in zip(scales, maps):
+        assert m.min() > 0
+        assert torch.allclose(m.double(), ref_maps[s], rtol=2e-6, atol=2e-6), s          # f32 summation of up to 2208 terms
+        f32 = torch.nn.functional.conv2d(feats[s].cpu(), cw[s].cpu(), cb[s].cpu())
+        assert (m - f32).abs().max() <= 4e-6                                               # torch's own f32 conv: same ball park
+    ref = fr.fusion_forward(x_d1, maps, weights, books, want_intermediates=True)
+    for si, s in enumerate(scales):
+        for pi, it in enumerate(ref["inter"][si]):
+            assert torch.equal(plan.bins[s][:, pi].cpu(), it["bins"]), (s, pi)
+            assert int(plan.kstar[s].view(-1)[pi]) == it["kstar"], (s, pi)
+        assert _rel_err(plan.rel[s].cpu(), ref["rel"][si]) < REL_MAP
+    assert _depth_ok(plan.depth.cpu(), ref["depth"])
