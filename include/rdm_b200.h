@@ -254,13 +254,17 @@ int rdm_recombination_bwd(const double* grad_out, void* const* grad_comps, const
  * x_d1: (N,64) i64; rel[k]: (N,side_k,side_k) f32, side_k <= 64, HOST array of device ptrs;
  * weights: device f32, slots concatenated in slot order [d0 | f1 | ... ], within a slot in
  * decoder order (decoder 1 first); weight count per slot is implied by `sides`.
- * yhat_out (optional): (N, sum_{k<=kmax} 4^k) f32 packed by slot; depth_out: (N,128,128) f64;
+ * yhat_out (optional): (N, sum_{k<=kmax} 4^k) f32 packed by slot; depth_out: (N,128,128) f64 (may be NULL if
+ * depth_compact_out is given); depth_compact_out (optional): (N,2^kmax,2^kmax) f64, kmax = log2 of the largest side
+ * (>= 3) - the log-depth map is constant on blocks of 2^(7-kmax) pixels (no component is finer), so this holds every
+ * distinct value of it: depth[b,y,x] == compact[b, y >> (7-kmax), x >> (7-kmax)] bit for bit;
  * A_out (optional): HOST array of 8 device pointers (entries may be NULL), A_out[k] receives the
  * slot-k fine-detail matrix (N, K_k, 4^k) f64 exactly as cp.relative_fine_detail_matrix builds it
  * (what the backward needs). */
 int rdm_fuse_tail(const int64_t* x_d1, const float* const* rel, const int32_t* sides,
                   int32_t n_rel, const float* weights, int64_t n_images, float* yhat_out,
-                  double* depth_out, double* const* A_out, rdm_stream_t stream);
+                  double* depth_out, double* depth_compact_out, double* const* A_out,
+                  rdm_stream_t stream);
 /* number of f32 weights rdm_fuse_tail expects for these relative decoder sides (-1 = bad sides) */
 int64_t rdm_fuse_tail_weight_count(const int32_t* sides, int32_t n_rel);
 

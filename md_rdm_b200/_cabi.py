@@ -67,7 +67,7 @@ PROTOTYPES = {
     "rdm_make_pred_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int64, c_void_p, c_void_p, c_void_p]),
     "rdm_recombination_f64": (c_int, [POINTER(c_void_p), POINTER(c_int32), c_int32, c_int32, c_int64, c_int32, c_void_p, c_void_p]),
     "rdm_recombination_bwd": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_int32), c_int32, c_int32, c_int64, c_int32, c_void_p]),
-    "rdm_fuse_tail": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_int32), c_int32, c_void_p, c_int64, c_void_p, c_void_p,
+    "rdm_fuse_tail": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_int32), c_int32, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
                               POINTER(c_void_p), c_void_p]),
     "rdm_fuse_tail_weight_count": (c_int64, [POINTER(c_int32), c_int32]),
     "rdm_dorn_regression_f32": (c_int, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),

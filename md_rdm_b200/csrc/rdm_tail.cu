@@ -533,7 +533,8 @@ struct TailParams {
   const float* rel[kMaxRel];
   const float* w;
   float* yhat_out;
-  double* depth_out;
+  double* depth_out;        // (N,128,128) f64 or NULL
+  double* depth_compact;    // (N,2^kmax,2^kmax) f64 or NULL: one value per constant block of the map
   double* A_out[8];
   int32_t side[kMaxRel];
   int32_t n_rel;
@@ -689,7 +690,7 @@ __global__ void __launch_bounds__(RDM_TAIL_THREADS) fuse_tail_kernel(const __gri
     for (int i = tid; i < ylen; i += blockDim.x) P.yhat_out[img * ylen + i] = yh[i];
   // ---- recombination of this CTA's band (CP:394-421): d0 + ((f1 + f2) + ... + f_kmax)
   const int rows = 128 / P.bands;
-  double* out = P.depth_out + img * 16384 + (int64_t)band * rows * 128;
+  double* out = P.depth_out ? P.depth_out + img * 16384 + (int64_t)band * rows * 128 : nullptr;
   const double d0 = (double)yh[0];
   // Levels above kmax do not exist, so the sum is constant on blocks of bs x bs pixels (bs = 2^(7-kmax)):
   // one gather-sum per block, then bs rows of 128-bit stores.
@@ -706,10 +707,12 @@ __global__ void __launch_bounds__(RDM_TAIL_THREADS) fuse_tail_kernel(const __gri
         a = (k == 1) ? v : a + v;
       }
       const double v = d0 + a;
-      for (int r = 0; r < bs; ++r)
-        for (int c = 0; c < bs; c += 2) stg_stream_f64x2(out + ((by << bsh) + r) * 128 + x + c, v, v);
+      if (P.depth_compact) P.depth_compact[img * (int64_t)(bpr * bpr) + (y >> bsh) * bpr + bx] = v;
+      if (out)
+        for (int r = 0; r < bs; ++r)
+          for (int c = 0; c < bs; c += 2) stg_stream_f64x2(out + ((by << bsh) + r) * 128 + x + c, v, v);
     }
-  } else {
+  } else if (out) {
     for (int o = tid; o < rows * 64; o += blockDim.x) {
       const int y = band * rows + (o >> 6), x = (o & 63) * 2;
       double a0 = 0.0, a1 = 0.0;
@@ -1256,11 +1259,11 @@ extern "C" int64_t rdm_fuse_tail_weight_count(const int32_t* sides, int32_t n_re
 
 extern "C" int rdm_fuse_tail(const int64_t* x_d1, const float* const* rel, const int32_t* sides, int32_t n_rel,
                              const float* weights, int64_t n_images, float* yhat_out, double* depth_out,
-                             double* const* A_out, rdm_stream_t stream) {
-  RDM_REQUIRE(x_d1 && weights && depth_out, "rdm_fuse_tail: null pointer");
+                             double* depth_compact_out, double* const* A_out, rdm_stream_t stream) {
+  RDM_REQUIRE(x_d1 && weights && (depth_out || depth_compact_out), "rdm_fuse_tail: null pointer");
   RDM_REQUIRE(n_rel >= 0 && n_rel <= kMaxRel, "rdm_fuse_tail: n_rel must be 0..%d (got %d)", kMaxRel, n_rel);
   RDM_REQUIRE(n_rel == 0 || (rel && sides), "rdm_fuse_tail: rel/sides required");
-  RDM_REQUIRE(aligned16(depth_out), "rdm_fuse_tail: depth_out must be 16-byte aligned");
+  RDM_REQUIRE(!depth_out || aligned16(depth_out), "rdm_fuse_tail: depth_out must be 16-byte aligned");
   RDM_REQUIRE(n_images >= 0, "rdm_fuse_tail: bad n_images");
   if (n_images == 0) return 0;
   TailParams P{};
@@ -1268,6 +1271,7 @@ extern "C" int rdm_fuse_tail(const int64_t* x_d1, const float* const* rel, const
   P.w = weights;
   P.yhat_out = yhat_out;
   P.depth_out = depth_out;
+  P.depth_compact = depth_compact_out;
   P.n_rel = n_rel;
   P.kmax = 3;
   for (int k = 0; k < 8; ++k) {

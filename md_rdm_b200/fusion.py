@@ -36,7 +36,8 @@ LIMIT_PAGE = 100
 class FusionPlan:
     def __init__(self, n_images: int, scales: Sequence[int] = (8, 16, 32), source: str = "map", group: Optional[int] = None,
                  device="cuda", quant: Optional[Quantization] = None, want_bins: bool = True, want_values: bool = False,
-                 want_A: bool = False, limit_8: int = LIMIT_8, limit_page: int = LIMIT_PAGE, overlap: bool = False, flags: int = 0):
+                 want_A: bool = False, limit_8: int = LIMIT_8, limit_page: int = LIMIT_PAGE, overlap: bool = False, flags: int = 0,
+                 compact_result: bool = False):
         if source not in ("map", "raw"):
             raise ValueError("source must be 'map' or 'raw'")
         self.lib = load()                      # raises if librdm_b200.so is missing: no fallback
@@ -123,6 +124,12 @@ class FusionPlan:
         self._descs = descs
         self.yhat = torch.empty((N, (4 ** (kmax + 1) - 1) // 3), dtype=f32, device=dev)
         self.depth = torch.empty((N, 1, 128, 128), dtype=f64, device=dev)
+        # Opt-in compact result: no decoder is finer than 2^kmax, so the log-depth map is constant on blocks of
+        # 2^(7-kmax) pixels; `depth_compact` (N,1,2^kmax,2^kmax) holds every distinct value (depth == its nearest-
+        # neighbour upsampling, bit for bit) in 1/4^(7-kmax) of the bytes.  The pinned end-to-end call then returns it
+        # INSTEAD of the full map (expand_compact() rebuilds the full map on the host).
+        self.compact_result = bool(compact_result)
+        self.depth_compact = torch.empty((N, 1, 1 << kmax, 1 << kmax), dtype=f64, device=dev) if compact_result else None
         self.A: List[torch.Tensor] = [torch.empty((N, K[k], 4 ** k), dtype=f64, device=dev) for k in range(kmax + 1)] if want_A else []
         self._rel_ptrs = ptr_array([self.rel[s].data_ptr() for s in self.scales])
         self._sides = i32_array(list(self.scales))
@@ -244,7 +251,14 @@ class FusionPlan:
         st = c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         check(self.lib.rdm_fuse_tail(c_void_p(self.x_d1.data_ptr()), self._rel_ptrs, self._sides, len(self.scales),
                                      c_void_p(self.weights.data_ptr()), self.N, c_void_p(self.yhat.data_ptr()),
-                                     c_void_p(self.depth.data_ptr()), self._a_ptrs, st), "rdm_fuse_tail")
+                                     c_void_p(self.depth.data_ptr()),
+                                     c_void_p(self.depth_compact.data_ptr()) if self.depth_compact is not None else c_void_p(0),
+                                     self._a_ptrs, st), "rdm_fuse_tail")
+
+    def expand_compact(self, compact: torch.Tensor) -> torch.Tensor:
+        """(N,1,2^kmax,2^kmax) compact result -> the (N,1,128,128) map it stands for (nearest-neighbour, exact)."""
+        r = 1 << (7 - self.kmax)
+        return compact.repeat_interleave(r, 2).repeat_interleave(r, 3)
 
     def run_tail(self) -> None:
         with self._guard():
@@ -289,21 +303,21 @@ class FusionPlan:
             h_in = torch.zeros((self._in_bytes,), dtype=torch.uint8).pin_memory()
             v = self._views(h_in)
             self._pinned = dict(packed=h_in, x_d1=v["x_d1"], src={s: v[s] for s in self.scales},
-                                depth=torch.empty(self.depth.shape, dtype=self.depth.dtype).pin_memory())
+                                depth=torch.empty((self.depth_compact if self.compact_result else self.depth).shape, dtype=self.depth.dtype).pin_memory())
         return self._pinned
 
     def h2d_bytes(self) -> int:
         return self.x_d1.numel() * 8 + sum(t.numel() * t.element_size() for t in self.src.values())
 
     def d2h_bytes(self) -> int:
-        return self.depth.numel() * 8
+        return (self.depth_compact if self.compact_result else self.depth).numel() * 8
 
     def _enqueue_e2e(self) -> None:
         hb = self._host_buffers()
         with self._guard():
             self._in_dev.copy_(hb["packed"], non_blocking=True)      # one H2D copy for all inputs
             self.run()
-            hb["depth"].copy_(self.depth, non_blocking=True)          # D2H of the fused log-depth maps
+            hb["depth"].copy_(self.depth_compact if self.compact_result else self.depth, non_blocking=True)   # D2H of the fused log-depth maps
 
     def capture_e2e(self) -> None:
         """CUDA graph of the whole host call: H2D copy node, the kernels of run(), D2H copy node."""

@@ -662,7 +662,7 @@ def fuse_tail(x_d1: Tensor, rel: Sequence[Tensor], weights: Tensor, want_A: bool
     a_ptrs = ptr_array([A[k].data_ptr() if (want_A and k <= kmax) else None for k in range(8)])
     with torch.cuda.device(dev):
         check(load().rdm_fuse_tail(_p(x_d1.contiguous()), ptr_array([r.data_ptr() for r in rc]), i32_array(sides), len(rc),
-                                   _p(weights.contiguous()), B, _p(yhat), _p(depth), a_ptrs, _stream()), "rdm_fuse_tail")
+                                   _p(weights.contiguous()), B, _p(yhat), _p(depth), c_void_p(0), a_ptrs, _stream()), "rdm_fuse_tail")
     return depth, yhat, A
 
 

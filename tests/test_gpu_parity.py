@@ -1168,3 +1168,22 @@ def test_conv_head_fused_with_pair_build(dev, books):
             assert int(plan.kstar[s].view(-1)[pi]) == it["kstar"], (s, pi)
         assert _rel_err(plan.rel[s].cpu(), ref["rel"][si]) < REL_MAP
     assert _depth_ok(plan.depth.cpu(), ref["depth"])
+
+
+def test_compact_result_is_the_map(dev, books):
+    """Opt-in compact result (e2e scaling): no decoder is finer than 2^kmax, so the log-depth map is
+    constant on 2^(7-kmax) blocks; depth_compact holds its distinct values and expands to the full map bit for bit, on
+    the device path and through the pinned host call."""
+    from md_rdm_b200.fusion import FusionPlan
+    for scales in ((8, 16, 32), (8, 16, 32, 64), ()):
+        x_d1, rel, weights = fr.synthetic_batch(4, scales, seed=7 + len(scales))
+        w = torch.cat([t.reshape(-1) for t in weights]).to(dev)
+        plan = FusionPlan(4, scales, "map", device=dev, compact_result=True)
+        plan.load_inputs(x_d1.to(dev), [r.to(dev) for r in rel], w)
+        plan.run()
+        torch.cuda.synchronize()
+        assert plan.depth_compact.shape == (4, 1, 1 << plan.kmax, 1 << plan.kmax)
+        assert _eq_nan(plan.expand_compact(plan.depth_compact), plan.depth)
+        host = plan.run_host(x_d1, rel)
+        assert host.shape == plan.depth_compact.shape and _eq_nan(plan.expand_compact(host), plan.depth.cpu())
+        assert plan.d2h_bytes() == 4 * 8 * 4 ** plan.kmax
