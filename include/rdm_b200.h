@@ -280,6 +280,12 @@ int rdm_dorn_regression_bwd(const float* x, const double* ord, const double* gra
                             int64_t n_images, int32_t K, int32_t HW, float* grad_x,
                             rdm_stream_t stream);
 
+/* utils.py:195-211 depth2label_sid (the ordinal target of network/module.py:126, 134-143): depth (n) f32|f64 ->
+ * labels (n) i32 = int(max(K * log(depth / alpha) / log(beta / alpha), 0)).  K, alpha and log_ratio = log(beta / alpha)
+ * are the f32-rounded scalars the reference's torch code holds (K = 90, alpha = 0.02, beta = 10). */
+int rdm_depth2label_sid(const void* depth, int32_t is_f64, int64_t n, double sid_K, double sid_alpha,
+                        double sid_log_ratio, int32_t* labels_out, rdm_stream_t stream);
+
 /* loss.py:17-59 Ordinal_Loss.calc: ord (N,K,H,W) f64, target (N,H*W) i32 SID labels ->
  * loss_out[0] = -(sum_{k<=t} log(f32(clamp(ord))) + sum_{k>t} log(f32(clamp(1-ord)))) / (N H W), f32.
  * ws: caller workspace of rdm_ordinal_loss_ws_doubles() f64 values. */

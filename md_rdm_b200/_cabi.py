@@ -74,6 +74,7 @@ PROTOTYPES = {
     "rdm_dorn_regression_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p]),
     "rdm_ordinal_loss_f64": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "rdm_ordinal_loss_ws_doubles": (c_int64, []),
+    "rdm_depth2label_sid": (c_int, [c_void_p, c_int32, c_int64, c_double, c_double, c_double, c_void_p, c_void_p]),
     "rdm_ordinal_loss_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p]),
 }
 

@@ -10,7 +10,6 @@
 
 namespace rdm {
 
-constexpr double kClampLo = 1e-8, kClampHi = 1e4;   // RN:334 torch.clamp(C, min=1e-8, max=1e4)
 
 static int grid_cap2(int64_t items) {
   int64_t blocks = (items + 255) / 256;
@@ -20,8 +19,14 @@ static int grid_cap2(int64_t items) {
 
 
 
+// torch.clamp(x, min=1e-8, max=1e4) on an f32 tensor: the bounds become f32 scalars, NaN stays NaN
+__device__ __forceinline__ float clamp_f32(float v) {
+  return v != v ? v : fminf(fmaxf(v, 1e-8f), 1e4f);
+}
+
 // softmax over the pair (A, B) as ATen computes it: exp(x - max) / sum, in f64; returns P(B).
 __device__ __forceinline__ double pair_softmax_b(double a, double b) {
+  if (a != a || b != b) return a + b;   // a NaN logit makes the whole pair NaN, as ATen's softmax does
   const double m = fmax(a, b);
   const double ea = exp(a - m), eb = exp(b - m);
   return eb / (ea + eb);
@@ -36,8 +41,8 @@ __global__ void __launch_bounds__(256) dorn_ord_kernel(const float* __restrict__
     const uint32_t hw = o % HW, nk = o / HW;
     const uint32_t k = nk % K, n = nk / K;
     const size_t ia = ((size_t)n * 2 * K + 2 * k) * HW + hw;
-    const double a = fmin(fmax((double)x[ia], kClampLo), kClampHi);
-    const double b = fmin(fmax((double)x[ia + HW], kClampLo), kClampHi);
+    // RN:334 clamps the f32 tensor (bounds rounded to f32) and only then widens it; torch.clamp propagates NaN
+    const double a = (double)clamp_f32(x[ia]), b = (double)clamp_f32(x[ia + HW]);
     ord[o] = pair_softmax_b(a, b);
   }
 }
@@ -67,9 +72,10 @@ __global__ void __launch_bounds__(256) dorn_regression_bwd_kernel(const float* _
     const int64_t ia = (n * 2 * K + 2 * k) * HW + hw, ib = ia + HW;
     const double p = ord[o];
     const double g = g_ord[o] * p * (1.0 - p);
-    const double a = (double)x[ia], b = (double)x[ib];
-    gx[ia] = (a >= kClampLo && a <= kClampHi) ? (float)(-g) : 0.f;
-    gx[ib] = (b >= kClampLo && b <= kClampHi) ? (float)g : 0.f;
+    // clamp backward passes the gradient where min <= x <= max (f32 bounds); a NaN logit has a NaN ord, hence a NaN g
+    const float a = x[ia], b = x[ib];
+    gx[ia] = (a != a) ? (float)(-g) : ((a >= 1e-8f && a <= 1e4f) ? (float)(-g) : 0.f);
+    gx[ib] = (b != b) ? (float)g : ((b >= 1e-8f && b <= 1e4f) ? (float)g : 0.f);
   }
 }
 
@@ -123,6 +129,23 @@ __global__ void __launch_bounds__(256) ordinal_loss_bwd_kernel(const double* __r
     // d/dv log(float(clamp(v))) = 1/v inside the clamp range, 0 outside; dv/dp = +1 (k<=t) or -1
     double d = (v >= 1e-8 && v <= 1e8) ? 1.0 / (double)(float)v : 0.0;
     g_ord[o] = g * ((k <= t) ? d : -d);
+  }
+}
+
+// utils.py:195-211 depth2label_sid: label = K * log(depth / alpha) / log(beta / alpha), max(label, 0), .int().  The
+// reference holds K, alpha, beta as 0-dim f32 tensors, so an f64 depth map is processed in f64 with f32-rounded
+// scalars and an f32 map entirely in f32; log_ratio = log(beta / alpha) is evaluated by the caller (torch, f32).
+template <typename T>
+__global__ void __launch_bounds__(256) depth2label_kernel(const T* __restrict__ depth, int64_t n, double K, double alpha, double log_ratio,
+                                                          int32_t* __restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    if constexpr (sizeof(T) == 8) {
+      const double label = __ddiv_rn(__dmul_rn(K, log(__ddiv_rn(depth[i], alpha))), log_ratio);
+      out[i] = __double2int_rz(fmax(label, 0.0));
+    } else {
+      const float label = __fdiv_rn(__fmul_rn((float)K, logf(__fdiv_rn(depth[i], (float)alpha))), (float)log_ratio);
+      out[i] = __float2int_rz(fmaxf(label, 0.0f));
+    }
   }
 }
 
@@ -182,4 +205,19 @@ extern "C" int rdm_ordinal_loss_bwd(const double* ord, const int32_t* target, co
   ordinal_loss_bwd_kernel<<<grid_cap2(total), 256, 0, (cudaStream_t)stream>>>(ord, target, grad_loss, total, K, HW,
                                                                               -1.0 / ((double)n_images * HW), grad_ord);
   return launch_status("ordinal_loss_bwd_kernel");
+}
+
+extern "C" int rdm_depth2label_sid(const void* depth, int32_t is_f64, int64_t n, double sid_K, double sid_alpha, double sid_log_ratio,
+                                   int32_t* labels_out, rdm_stream_t stream) {
+  RDM_REQUIRE(n >= 0, "rdm_depth2label_sid: negative n");
+  if (n == 0) return 0;
+  RDM_REQUIRE(depth && labels_out, "rdm_depth2label_sid: null pointer");
+  RDM_REQUIRE(sid_alpha > 0.0 && sid_log_ratio != 0.0, "rdm_depth2label_sid: bad SID parameters");
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > rdm::kNumSMs * 8) blocks = rdm::kNumSMs * 8;
+  if (is_f64)
+    rdm::depth2label_kernel<double><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const double*)depth, n, sid_K, sid_alpha, sid_log_ratio, labels_out);
+  else
+    rdm::depth2label_kernel<float><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const float*)depth, n, sid_K, sid_alpha, sid_log_ratio, labels_out);
+  return rdm::launch_status("depth2label_kernel");
 }

@@ -20,8 +20,8 @@ class Ordinal_Loss():
 
 
 def depth2label_sid(depth, K=90.0, alpha=0.02, beta=10.0, cuda=True):
-    """utils.py:195-211 (caller glue; elementwise torch on the tensor's device, f32 scalars as in the reference)."""
-    dev = depth.device
-    a, b, k = torch.tensor(alpha, device=dev), torch.tensor(beta, device=dev), torch.tensor(K, device=dev)
-    label = k * torch.log(depth / a) / torch.log(b / a)
-    return torch.max(label, torch.zeros(label.shape, device=dev)).int()
+    """utils.py:195-211 in one elementwise kernel (f32 scalars K, alpha, beta as in the reference; an f64 map is
+    processed in f64, an f32 map in f32).  Other dtypes are widened to f64 first."""
+    if depth.dtype not in (torch.float32, torch.float64):
+        depth = depth.double()
+    return torch.ops.rdm.depth2label_sid(depth, float(K), float(alpha), float(beta))

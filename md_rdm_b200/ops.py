@@ -846,3 +846,23 @@ def _oloss_backward(ctx, g):
 
 
 ordinal_loss.register_autograd(_oloss_backward, setup_context=_oloss_setup)
+
+
+@torch.library.custom_op("rdm::depth2label_sid", mutates_args=())
+def depth2label_sid(depth: Tensor, K: float, alpha: float, beta: float) -> Tensor:
+    """utils.py:195-211: depth (any shape) f32|f64 -> SID labels int32 of the same shape."""
+    _need_cuda("depth2label_sid", depth)
+    if depth.dtype not in (torch.float32, torch.float64):
+        raise RuntimeError("rdm::depth2label_sid: expected an f32 or f64 tensor")
+    d = depth.contiguous()
+    out = torch.empty(d.shape, dtype=torch.int32, device=d.device)
+    k, a, lr = _sid_constants(K, alpha, beta)
+    with torch.cuda.device(d.device):
+        check(load().rdm_depth2label_sid(_p(d), 1 if d.dtype == torch.float64 else 0, d.numel(), k, a, lr, _p(out), _stream()),
+              "rdm_depth2label_sid")
+    return out
+
+
+@depth2label_sid.register_fake
+def _(depth, K, alpha, beta):
+    return depth.new_empty(depth.shape, dtype=torch.int32)

@@ -1187,3 +1187,38 @@ def test_compact_result_is_the_map(dev, books):
         host = plan.run_host(x_d1, rel)
         assert host.shape == plan.depth_compact.shape and _eq_nan(plan.expand_compact(host), plan.depth.cpu())
         assert plan.d2h_bytes() == 4 * 8 * 4 ** plan.kmax
+
+
+def test_dorn_clamp_is_f32_and_nan_propagates(dev):
+    """RN:334 clamps the f32 logits (f32 bounds) before widening, and torch.clamp / softmax propagate NaN."""
+    from md_rdm_b200.rdm_net import Ordinal_Layer
+    x = torch.zeros(1, 6, 8, 8)
+    x[0, 0, 0, 0], x[0, 1, 0, 0] = 1e-9, 5e-9          # both below the lower bound: clamp to float32(1e-8) exactly
+    x[0, 2, 0, 1] = float("nan")
+    x[0, 4, 0, 2], x[0, 5, 0, 2] = 2e4, -3.0            # above / below the bounds
+    xd = x.to(dev).requires_grad_(True)
+    decode, ord_ = Ordinal_Layer(1, True, None)(xd)
+    dref, oref = fr.dorn_regression(x)
+    assert torch.equal(torch.isnan(ord_.cpu()), torch.isnan(oref))
+    assert torch.allclose(torch.nan_to_num(ord_.detach().cpu(), nan=0.0), torch.nan_to_num(oref, nan=0.0), rtol=1e-14, atol=0)
+    assert torch.equal(decode.cpu(), dref)
+    ord_.nan_to_num(nan=0.0).sum().backward()
+    assert float(xd.grad[0, 4, 0, 2]) == 0.0 and float(xd.grad[0, 5, 0, 2]) == 0.0      # clamped: no gradient
+
+
+def test_depth2label_sid_kernel(dev):
+    """utils.py:195-211 as one kernel: f64 maps bit-equal to the reference formula evaluated by torch
+    on the CPU (the oracle), f32 maps equal except where the f32 log lands within an ulp of an integer."""
+    from md_rdm_b200.loss import depth2label_sid
+    g = torch.Generator().manual_seed(195)
+    d64 = 0.02 + 12.0 * torch.rand(7, 1, 8, 8, generator=g, dtype=torch.float64)
+    d64[0, 0, 0, 0] = 0.01                                # below alpha: negative label -> 0
+    assert torch.equal(depth2label_sid(d64.to(dev)).cpu(), fr.depth2label_sid(d64))
+    d32 = d64.float()
+    ours, ref = depth2label_sid(d32.to(dev)).cpu(), fr.depth2label_sid(d32)
+    assert ours.dtype == torch.int32 and (ours - ref).abs().max() <= 1 and (ours != ref).float().mean() < 0.01
+    gold = load_golden("dorn_loss.npz")
+    gen = torch.Generator().manual_seed(808)
+    torch.randn(3, 180, 8, 8, generator=gen)
+    depth = 0.5 + 9.5 * torch.rand(3, 1, 8, 8, generator=gen, dtype=torch.float64)
+    assert torch.equal(depth2label_sid(depth.to(dev)).cpu(), torch.from_numpy(gold["target"]))
