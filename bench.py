@@ -91,7 +91,6 @@ def algorithmic_bytes(scales=SCALES):
     out["sparsify_kernel"] = sum(raw[s] + Rq[s] + bins[s] for s in pg)
     out["als_sparse_kernel"] = sum(Rq[s] + mp[s] for s in pg)
     out["als_dense_kernel"] = sum(raw[s] + 2 * Rq[s] + bins[s] + mp[s] for s in scales if s == 8)
-    out["als_select_kernel"] = sum(mp[s] for s in scales)
     out["tail_kernel"] = out["decompose"] + out["reconstruct"]
     return out
 
@@ -520,7 +519,7 @@ def run_fusion(args, kind="fusion"):
     if os.path.exists(tpath):
         traffic = json.load(open(tpath))
     kernel_b = {"als_sparsify": ab["sparsify_kernel"], "als_sparse": ab["als_sparse_kernel"], "als_dense": ab["als_dense_kernel"],
-                "als_select": ab["als_select_kernel"], "fuse_tail": ab["tail_kernel"]}
+                "fuse_tail": ab["tail_kernel"]}
     # dominant kernel by time: the compact-page ALS iterations
     dom = max((k for k in kernel_s if k in kernel_b), key=lambda k: kernel_s[k])
     total_images = world * K * images_per_step
