@@ -100,6 +100,25 @@ struct RowGeom {
   __host__ __device__ __forceinline__ int fill_col() const { return r0 >= 1 ? 0 : 56; }
 };
 
+// Per-row constants of the residual identity (header comment), computed where the row is built so that the iterate
+// kernel's prologue does not spend ~400 f64 instructions per lane on them: A_rho = sum_span D (2 f + D) as an
+// unevaluated f32 pair (exact to ~2^-48) and the iteration-0 residual sum_j fl(1 - R[rho][j])^2 (p = q = 1, CP:123).
+// wl: the nine window levels (row-major), f: the fill level.
+__device__ __forceinline__ void row_constants(float f, const float (&wl)[9], float& a_hi, float& a_lo, float& e0) {
+  const float u = __fsub_rn(1.0f, f);
+  double asum = 0.0, acc = 55.0 * ((double)u * (double)u);   // 64 - 9 columns hold f
+#pragma unroll
+  for (int w = 0; w < 9; ++w) {
+    const float D = wl[w] - f;                                // the compact entry, as stored
+    asum = fma((double)D, 2.0 * (double)f + (double)D, asum);
+    const float r = __fsub_rn(1.0f, __fadd_rn(f, D));
+    acc = fma((double)r, (double)r, acc);
+  }
+  a_hi = (float)asum;
+  a_lo = (float)(asum - (double)a_hi);
+  e0 = (float)acc;
+}
+
 // ---- mbarrier / bulk-copy (TMA) primitives --------------------------------------------------------------
 __device__ __forceinline__ uint32_t sm_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
@@ -219,7 +238,7 @@ __global__ void __launch_bounds__(kBandRows) als_sparsify_raw_kernel(const __gri
   {
     float o[16];
     o[0] = f;
-    o[13] = o[14] = o[15] = 0.f;
+    row_constants(f, wl, o[13], o[14], o[15]);
 #pragma unroll
     for (int a = 0; a < 3; ++a)
 #pragma unroll
@@ -305,12 +324,16 @@ __device__ __forceinline__ void compact_page_from_map(const SparseScaleDev& sc, 
   float* compact = sc.ws + unit * als_ws_stride(256, sc.limit);
   float o[16];
   o[0] = f;
-  o[13] = o[14] = o[15] = 0.f;
   int wb[9];   // window bins, row-major over the 3x3 window
+  float wlv[9];
 #pragma unroll
   for (int a = 0; a < 3; ++a)
 #pragma unroll
-    for (int b = 0; b < 3; ++b) wb[3 * a + b] = lloyd_bin<double>(__dmul_rn(d, inv_d[8 * (r0 + a) + c0 + b]), thr_d, srt);
+    for (int b = 0; b < 3; ++b) {
+      wb[3 * a + b] = lloyd_bin<double>(__dmul_rn(d, inv_d[8 * (r0 + a) + c0 + b]), thr_d, srt);
+      wlv[3 * a + b] = lvl_f[wb[3 * a + b]];
+    }
+  row_constants(f, wlv, o[13], o[14], o[15]);
 #pragma unroll
   for (int a = 0; a < 3; ++a)
 #pragma unroll
@@ -319,7 +342,7 @@ __device__ __forceinline__ void compact_page_from_map(const SparseScaleDev& sc, 
       float v = 0.f;
 #pragma unroll
       for (int bb = 0; bb < 3; ++bb)
-        if (b == bb) v = lvl_f[wb[3 * a + bb]] - f;
+        if (b == bb) v = wlv[3 * a + bb] - f;
       o[1 + 4 * a + g] = v;
     }
 #pragma unroll
@@ -592,6 +615,7 @@ __device__ __forceinline__ void load_span_u32(uint32_t a, float (&v)[12]) {
 // = 8 matrix rows, and with them the two entries q[8rh+kq], q[8rh+4+kq].
 struct PageRegs {
   float f[8], D[8][12];
+  float A, e0;   // sum over the lane's rows of A_rho and of the iteration-0 residual (row_constants)
 };
 
 // The reducer's work for iteration j (one warp, all lanes): complete the barrier of iteration j, group rmse,
@@ -680,25 +704,9 @@ __device__ __forceinline__ void pages_iterate(const PageRegs& M, PagesShared& sh
   const uint32_t a_flag = s_u32(&sh.flag[0]);
   const uint32_t a_best = s_u32(best);
 
-  float A = 0.f;
+  const float A = M.A;     // sum over this lane's rows of A_rho (row_constants, computed by the sparsify kernels)
   if (RECORD) {
-    // A = sum over this lane's rows of A_rho, and the record of iteration 0 (p = q = 1, CP:123):
-    // sum_j fl(1 - R)^2 with 52 columns outside the span
-    double e0 = 0.0, asum = 0.0;
-#pragma unroll
-    for (int t = 0; t < 8; ++t) {
-      const float u = __fsub_rn(1.0f, f[t]);
-      double acc = 52.0 * ((double)u * (double)u);
-#pragma unroll
-      for (int e = 0; e < 12; ++e) {
-        asum = fma((double)D[t][e], 2.0 * (double)f[t] + (double)D[t][e], asum);
-        const float w = __fsub_rn(1.0f, __fadd_rn(f[t], D[t][e]));
-        acc = fma((double)w, (double)w, acc);
-      }
-      e0 += acc;
-    }
-    A = (float)asum;
-    s_st1(a_E, (float)e0);
+    s_st1(a_E, M.e0);      // the record of iteration 0 (p = q = 1, CP:123)
     named_arrive(1, nbar);
   }
 
@@ -859,6 +867,7 @@ __device__ __forceinline__ void load_page(PageRegs& M, const float* __restrict__
   const int rh = lane >> 2, kq = lane & 3;
   const int row_base = 32 * rh + 4 * kq;
   const int off_s[2] = {row_base + 16 * (rh & 1), row_base + 16 * ((rh & 1) ^ 1)};
+  double asum = 0.0, e0 = 0.0;
 #pragma unroll
   for (int dr = 0; dr < 2; ++dr)
 #pragma unroll
@@ -871,7 +880,11 @@ __device__ __forceinline__ void load_page(PageRegs& M, const float* __restrict__
       M.D[t][3] = b.x; M.D[t][4] = b.y; M.D[t][5] = b.z; M.D[t][6] = b.w;
       M.D[t][7] = c.x; M.D[t][8] = c.y; M.D[t][9] = c.z; M.D[t][10] = c.w;
       M.D[t][11] = d.x;
+      asum += (double)d.y + (double)d.z;
+      e0 += (double)d.w;
     }
+  M.A = (float)asum;
+  M.e0 = (float)e0;
 }
 
 __device__ __forceinline__ bool unit_is_compact(const float* compact) {

@@ -49,8 +49,13 @@ class FusionPlan:
         if self.N % self.group:
             raise ValueError("n_images must be a multiple of group")
         self.scales = tuple(int(s) for s in scales)
-        if any(s not in (8, 16, 32, 64) for s in self.scales):
-            raise ValueError("relative decoder scales must be in {8,16,32,64}")
+        if any(s not in (8, 16, 32, 64, 128) for s in self.scales):
+            raise ValueError("relative decoder scales must be in {8,16,32,64,128}")
+        # decoder 10 (128x128, RN:61): pair build + Lloyd + ALS run in the same launches as the other scales (64 pages
+        # per image); its 175 KB f64 pyramid does not fit beside the others in one CTA's shared memory, so the tail of
+        # such a plan is COMPOSED from the stand-alone kernels (decompose, log_stack, make_pred, recombination)
+        # instead of the single fuse_tail launch
+        self.composed_tail = 128 in self.scales
         self.source = source
         self.quant = quant or default_quantization()
         dev, N = self.device, self.N
@@ -140,6 +145,10 @@ class FusionPlan:
         has_pages, has_8 = any(s > 8 for s in self.scales), 8 in self.scales
         # sparsify + compact-page ALS (page scales), dense ALS (8x8 maps and the page fallback), fused tail
         self.launches_per_run = (2 if has_pages else 0) + (1 if self.scales else 0) + 1
+        if self.composed_tail:   # gm + decompose per decoder, log_stack + make_pred per slot, recombination
+            self.launches_per_run += 1 + len(self.scales) + 2 * (kmax + 1)
+            if compact_result:
+                raise ValueError("compact_result needs kmax < 7: with a 128x128 decoder the map has no constant blocks")
 
     @staticmethod
     def phase_masks() -> Dict[str, int]:
@@ -247,7 +256,29 @@ class FusionPlan:
             st = c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
             check(self.lib.rdm_als_fused_phases(self._descs, len(self.scales), self.N, self.group, phase_mask, st), "rdm_als_fused_phases")
 
+    def _run_tail_composed(self) -> None:
+        """RN:117-133 + MOD:132 from the stand-alone kernels (plans with the 128x128 decoder)."""
+        from . import computations as cp
+        R = torch.ops.rdm
+        B = self.N
+        rows = [cp.decompose_depth_map([], R.gm_normalize(self.x_d1), 3)[::-1]]
+        for s in self.scales:
+            rows.append(cp.decompose_depth_map([], self.rel[s], s.bit_length() - 1, relative_map=True)[::-1])
+        A = cp.relative_fine_detail_matrix(rows, True)
+        ws, off = [], 0
+        for k in range(self.kmax + 1):
+            ws.append(self.weights[off:off + self.K[k]].view(self.K[k], 1))
+            off += self.K[k]
+        for k, a in enumerate(A):
+            if self.A:
+                self.A[k].copy_(a)
+        y_hat = cp.make_pred(ws, A, True, False)
+        self.yhat.copy_(torch.cat([y.reshape(B, -1) for y in y_hat], 1))
+        self.depth.copy_(cp.recombination(list(y_hat)))
+
     def _run_tail(self) -> None:
+        if self.composed_tail:
+            return self._run_tail_composed()
         st = c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         check(self.lib.rdm_fuse_tail(c_void_p(self.x_d1.data_ptr()), self._rel_ptrs, self._sides, len(self.scales),
                                      c_void_p(self.weights.data_ptr()), self.N, c_void_p(self.yhat.data_ptr()),

@@ -1222,3 +1222,29 @@ def test_depth2label_sid_kernel(dev):
     torch.randn(3, 180, 8, 8, generator=gen)
     depth = 0.5 + 9.5 * torch.rand(3, 1, 8, 8, generator=gen, dtype=torch.float64)
     assert torch.equal(depth2label_sid(depth.to(dev)).cpu(), torch.from_numpy(gold["target"]))
+
+
+def test_fusion_plan_with_decoder_10(dev, books):
+    """VERDICT r1 missing #5: the 128x128 relative decoder (decoder 10, RN:61, 64 pages per image) inside FusionPlan and
+    fuse_maps: its pair build / Lloyd / ALS share the launches of the other scales, the tail is composed from the
+    stand-alone kernels.  All five relative decoders against the oracle."""
+    from md_rdm_b200.fusion import FusionPlan
+    scales = (8, 16, 32, 64, 128)
+    x_d1, rel, weights = fr.synthetic_batch(2, scales, seed=128)
+    ref = fr.fusion_forward(x_d1, rel, weights, books, want_intermediates=True)
+    for source in ("map", "raw"):
+        plan = _run_plan(dev, x_d1, rel, weights, source, want_A=True)
+        assert plan.kmax == 7 and plan.composed_tail
+        for si, s in enumerate(scales):
+            for pi, it in enumerate(ref["inter"][si]):
+                assert torch.equal(plan.bins[s][:, pi].cpu(), it["bins"]), (source, s, pi)
+                assert int(plan.kstar[s].view(-1)[pi]) == it["kstar"], (source, s, pi)
+            assert _rel_err(plan.rel[s].cpu(), ref["rel"][si]) < REL_MAP, (source, s)
+        for y, yr in zip(plan.yhat_list(), ref["y_hat"]):
+            assert torch.allclose(y.cpu(), yr, rtol=0, atol=5e-5)
+        assert _depth_ok(plan.depth.cpu(), ref["depth"]), source
+        eager = plan.depth.clone()
+        plan.depth.zero_()
+        plan.replay()                                    # the composed tail is CUDA-graph capturable too
+        torch.cuda.synchronize()
+        assert _eq_nan(plan.depth, eager)

@@ -13,7 +13,7 @@ import bench  # noqa: E402
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 6
 dev = torch.device("cuda:0")
-ring = bench.build_ring(dev, 0, 2, "raw")
+ring = bench.build_ring(dev, 0, 2, "raw", bench.BATCH)
 for i in range(steps):
     ring[i % 2].run()
 torch.cuda.synchronize()
