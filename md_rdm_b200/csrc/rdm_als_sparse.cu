@@ -893,7 +893,11 @@ __device__ __forceinline__ bool unit_is_compact(const float* compact) {
 }
 
 // grid = (group, page) items of every page scale; block = 32 x min(group, 16).
+#ifdef RDM_PAGES_MAXNREG   // A/B builds: leave part of the register file to a co-resident CTA of another kernel
+__global__ void __maxnreg__(RDM_PAGES_MAXNREG) als_pages_kernel(const __grid_constant__ PagesParams P) {
+#else
 __global__ void __launch_bounds__(32 * kGroupWarps, 1) als_pages_kernel(const __grid_constant__ PagesParams P) {
+#endif
   extern __shared__ __align__(16) unsigned char smem_raw[];
   PagesShared& sh = *reinterpret_cast<PagesShared*>(smem_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
