@@ -826,7 +826,7 @@ def main():
     ap.add_argument("--e2e-lanes", type=int, default=8, help="host calls in flight in the e2e measurement")
     ap.add_argument("--e2e-lanes-compact", type=int, default=32, help="... with the opt-in compact result (not PCIe-bound: latency-bound)")
     ap.add_argument("--ring", type=int, default=128, help="resident input batches (ring > L2) = calls per step")
-    ap.add_argument("--group-batches", type=int, default=32, help="batches per call of the grouped-call table")
+    ap.add_argument("--group-batches", type=int, default=29, help="batches per call of the grouped-call table (29 x 5 page items = 145 CTAs of the page kernel: one wave on 148 SMs)")
     ap.add_argument("--cpu-calls", type=int, default=3, help="calls of 16 images timed for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stage-table", action="store_true")
