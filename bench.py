@@ -46,6 +46,7 @@ METRIC = "fused_depth_maps_per_sec"
 UNIT = "maps/s"
 BATCH = 16
 SCALES = (8, 16, 32)
+PLAN_FLAGS = int(os.environ.get("RDM_BENCH_PLAN_FLAGS", "0"))   # A/B measurements: rdm_als_scale_t.flags for every plan of the bench
 
 
 def shared_config(kind: str = "fusion"):
@@ -254,7 +255,7 @@ def build_ring(dev, rank, n_plans, source, call_images, want_bins=True, compact=
     ring = []
     for b in range(n_plans):
         x_d1, rel, weights = synthetic_batch(call_images, SCALES, seed=batch_seed(rank, b))
-        plan = FusionPlan(call_images, SCALES, source, device=dev, want_bins=want_bins, compact_result=compact)
+        plan = FusionPlan(call_images, SCALES, source, device=dev, want_bins=want_bins, compact_result=compact, flags=PLAN_FLAGS)
         rel_d = [r.to(dev) for r in rel]
         if source == "raw":   # raw pair matrices derived from the maps with the pair-build kernels (not timed)
             srcs = [R.pair_v1(r) if r.shape[2] == 8 else R.pair_id(r)[0] for r in rel_d]
@@ -598,7 +599,7 @@ def grouped_call_table(dev, rank, ab, args):
     plans = []
     for b in range(n_ring):
         x_d1, rel, weights = synthetic_batch(BATCH * nb, SCALES, seed=batch_seed(rank, 5000 + b))
-        plan = FusionPlan(BATCH * nb, SCALES, "raw", group=BATCH, device=dev, want_bins=True)
+        plan = FusionPlan(BATCH * nb, SCALES, "raw", group=BATCH, device=dev, want_bins=True, flags=PLAN_FLAGS)
         rel_d = [r.to(dev) for r in rel]
         srcs = [R.pair_v1(r) if r.shape[2] == 8 else R.pair_id(r)[0] for r in rel_d]
         plan.load_inputs(x_d1.to(dev), srcs, torch.cat([w.reshape(-1) for w in weights]).to(dev))

@@ -102,7 +102,10 @@ enum {
   RDM_ALS_TRUE_TRANSPOSE = 2, /* "paper-correct" knobs of SURVEY 8f rank 4, OFF by default (see below) */
   RDM_ALS_TRUE_GM = 4,
   RDM_ALS_CORRECT_TILING = 8,
-  RDM_ALS_FLAGS_ALL = 15
+  RDM_ALS_PAGES_ONE_CTA = 16, /* page ALS: the 16 images of a batch in ONE CTA per page (best when the chip is full) */
+  RDM_ALS_PAGES_CLUSTER = 32, /* page ALS: a cluster of 4 CTAs per (batch, page) (lowest latency of a small launch);
+                                 neither bit = chosen from the launch size; same results bit for bit either way */
+  RDM_ALS_FLAGS_ALL = 63
 };
 /* rdm_als_fused_phases phase_mask bits: the launches of rdm_als_fused, selectable one by one (profiling) */
 enum {

@@ -670,13 +670,171 @@ __device__ __noinline__ void pages_reduce(PagesShared& sh, int j, int W, int lan
   __syncwarp();
 }
 
+// ---- how the warps of a group meet ------------------------------------------------------------------------
+// LocalSync: all warps of the group in ONE CTA (named barriers, shared-memory flags; pages_reduce above).
+struct LocalSync {
+  PagesShared& sh;
+  int warp, lane, W, nbar, next_red;
+  double inv_cnt;
+  float* record_out;
+  uint32_t a_E, a_flag;
+  __device__ __forceinline__ LocalSync(PagesShared& s, int warp_, int lane_, int W_, double ic, float* rec)
+      : sh(s), warp(warp_), lane(lane_), W(W_), nbar((W_ + 1) * 32), next_red(warp_), inv_cnt(ic), record_out(rec) {
+    uint32_t e = s_u32(&sh.E[0][warp][lane]);
+    asm volatile("mov.b32 %0, %0;" : "+r"(e));   // keep it in a register (see pages_iterate)
+    a_E = e;
+    a_flag = s_u32(&sh.flag[0]);
+  }
+  __device__ __forceinline__ void publish(int k, float e) {   // this lane's residual of iteration k
+    const uint32_t slot = (uint32_t)k & (kRing - 1);
+    s_st1(a_E + (slot << 11), e);
+    named_arrive(1 + (int)slot, nbar);
+  }
+  template <bool DECIDE>
+  __device__ __forceinline__ void duty(int j) {               // called with j = k - kRedDelay at the top of step k, and in the drain
+    if (j == next_red) {
+      pages_reduce<DECIDE>(sh, j, W, lane, inv_cnt, record_out);
+      next_red += W;
+    }
+  }
+  __device__ __forceinline__ bool verdict(int j) {            // blocks until the verdict on iteration j is out
+    const uint32_t fa = a_flag + 4 * (j & (kRing - 1));
+    int v;
+    do {
+      v = s_ld_flag(fa);
+    } while (v < 2 * j);             // the slot's previous verdict (or -1) is smaller
+    return (v & 1) != 0;
+  }
+};
+
+// ClusterSync: the 16 warps of a group spread over a thread-block CLUSTER of 4 CTAs x 4 warps (a lone call then runs on
+// 20 SMs instead of 5, and the small CTAs pack beside other kernels).  Same protocol, different plumbing:
+//  * the residuals of iteration j go to the CTA of its reducer (global warp j % 16) through distributed shared memory
+//    with st.async, which also counts the bytes on the reducer's mbarrier: fire and forget;
+//  * the reducer arms that mbarrier (arrive.expect_tx 16 x 128 bytes), waits on it, takes the group rmse, waits for the verdict on
+//    j - 1 in its own copy of the flags, and BROADCASTS one 64-bit word to the flag[j & 3] of all four CTAs:
+//    (j + 1) << 33 | new_minimum << 32 | bits of the running minimum after j - so the running minimum travels with the
+//    verdicts and nothing else is shared;
+//  * every warp spins on its own CTA's copy of the flag.
+// Slot s of a CTA's mbarriers / E buffer serves the iterations j = 16 n + 4 rank + s: phase parity n & 1.
+constexpr int kClusterCtas = 4;
+constexpr int kClusterWarps = kGroupWarps / kClusterCtas;   // warps (images) per CTA
+
+struct PagesClusterShared {
+  float E[kRing][kGroupWarps][32];            // residuals of the iterations this CTA reduces
+  unsigned long long flag[kRing];             // this CTA's copy of the verdicts
+  unsigned long long mbar[kRing];
+  int all_compact;
+};
+
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ unsigned long long s_ld_u64_volatile(uint32_t a) {
+  unsigned long long v;
+  asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(v) : "r"(a) : "memory");
+  return v;
+}
+
+// The reducer's work for iteration j (ClusterSync), out of line like pages_reduce.
+__device__ __noinline__ void cluster_reduce(PagesClusterShared& sh, int j, int lane, double inv_cnt, float* record_out, uint32_t a_flag, uint32_t a_mbar) {
+  const uint32_t slot = (uint32_t)j & (kRing - 1), parity = ((uint32_t)j >> 4) & 1u;
+  // the phase completes when this one arrival is in and the 16 warps' 16 x 128 bytes have landed (complete_tx may
+  // run ahead of expect_tx: the transaction count is signed)
+  if (lane == 0)
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a_mbar + 8 * slot), "r"(kGroupWarps * 128) : "memory");
+  asm volatile(
+      "{\n\t.reg .pred p;\n"
+      "W_%=:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+      "@!p bra W_%=;\n\t}"
+      ::"r"(a_mbar + 8 * slot), "r"(parity) : "memory");
+  const int u = lane & 15, h = lane >> 4;
+  double t = 0.0;
+  const float4* e4 = reinterpret_cast<const float4*>(&sh.E[slot][u][16 * h]);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 x = e4[i];
+    t += (double)x.x;
+    t += (double)x.y;
+    t += (double)x.z;
+    t += (double)x.w;
+  }
+  t += __shfl_xor_sync(kFull, t, 16);
+  double g = h == 0 ? (double)(float)t : 0.0;   // unit record rounded to f32, then the group sum in f64
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) g += __shfl_xor_sync(kFull, g, o);
+  if (lane == 0) {
+    const float rm = (float)sqrt(g * inv_cnt);   // CP:172-173 over the whole reference batch
+    float best = __int_as_float(0x7f800000);
+    if (j > 0) {                                 // verdicts are issued in iteration order (see LocalSync / pages_reduce)
+      const uint32_t fa = a_flag + 8 * ((uint32_t)(j - 1) & (kRing - 1));
+      unsigned long long w;
+      do {
+        w = s_ld_u64_volatile(fa);
+      } while ((w >> 33) < (unsigned long long)j);
+      best = __uint_as_float((unsigned)w);
+    }
+    const bool better = rm < best;               // strict: the first minimum wins (CP:143)
+    const unsigned long long word = ((unsigned long long)(j + 1) << 33) | ((unsigned long long)(better ? 1 : 0) << 32) |
+                                    (unsigned long long)__float_as_uint(better ? rm : best);
+    if (record_out) record_out[j] = rm;
+#pragma unroll
+    for (uint32_t r = 0; r < (uint32_t)kClusterCtas; ++r)
+      asm volatile("st.shared::cluster.u64 [%0], %1;" ::"r"(mapa_u32(a_flag + 8 * slot, r)), "l"(word) : "memory");
+  }
+  __syncwarp();
+}
+
+struct ClusterSync {
+  PagesClusterShared& sh;
+  int gw, lane, next_red, kstar;
+  uint32_t crank;
+  double inv_cnt;
+  float* record_out;
+  uint32_t a_E, a_flag, a_mbar;   // local shared addresses: &E[0][gw][lane], &flag[0], &mbar[0]
+  __device__ __forceinline__ ClusterSync(PagesClusterShared& s, int gw_, int lane_, uint32_t crank_, double ic, float* rec)
+      : sh(s), gw(gw_), lane(lane_), next_red(gw_), kstar(0), crank(crank_), inv_cnt(ic), record_out(rec) {
+    uint32_t e = s_u32(&sh.E[0][gw][lane]);
+    asm volatile("mov.b32 %0, %0;" : "+r"(e));
+    a_E = e;
+    a_flag = s_u32(&sh.flag[0]);
+    a_mbar = s_u32(&sh.mbar[0]);
+  }
+  __device__ __forceinline__ void publish(int k, float e) {
+    const uint32_t slot = (uint32_t)k & (kRing - 1), dst = ((uint32_t)k & (kGroupWarps - 1)) / kClusterWarps;   // the reducer's CTA
+    // st.async: the value lands in the reducer's E buffer and 4 bytes are counted on its mbarrier - no fence, no
+    // round trip on this warp's critical path (a release-arrive per iteration costs a DSMEM round trip: measured 2x)
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
+                 ::"r"(mapa_u32(a_E + (slot << 11), dst)), "r"(__float_as_uint(e)), "r"(mapa_u32(a_mbar + 8 * slot, dst)) : "memory");
+  }
+  template <bool DECIDE>
+  __device__ __forceinline__ void duty(int j) {
+    if (j == next_red) {
+      cluster_reduce(sh, j, lane, inv_cnt, record_out, a_flag, a_mbar);
+      next_red += kGroupWarps;
+    }
+  }
+  __device__ __forceinline__ bool verdict(int j) {
+    const uint32_t fa = a_flag + 8 * ((uint32_t)j & (kRing - 1));
+    unsigned long long w;
+    do {
+      w = s_ld_u64_volatile(fa);
+    } while ((w >> 33) < (unsigned long long)(j + 1));
+    const bool better = ((w >> 32) & 1ull) != 0;
+    if (better) kstar = j;
+    return better;
+  }
+};
+
 // MODE 0: record + online arg-min (single-round groups); MODE 1: record only, accumulated into sh.recg
 // (multi-round groups, pass 1); MODE 2: no record, n_iter iterations, the last iterate is returned in p_out
 // (multi-round groups, pass 2).
-template <int MODE>
-__device__ __forceinline__ void pages_iterate(const PageRegs& M, PagesShared& sh, float* __restrict__ ps, float* __restrict__ qs,
-                                              float* __restrict__ best, int lane, int warp, int W, int n_iter, double inv_cnt,
-                                              float* __restrict__ record_out, float (&p_out)[8]) {
+template <int MODE, typename Sync>
+__device__ __forceinline__ void pages_iterate(const PageRegs& M, Sync& sync, float* __restrict__ ps, float* __restrict__ qs,
+                                              float* __restrict__ best, int lane, int n_iter, float (&p_out)[8]) {
   const int rh = lane >> 2, kq = lane & 3;
   const int r0 = min(rh, 5), span0 = min(2 * kq, 4);
   const int sp = 8 * r0 + span0;            // first span column
@@ -685,7 +843,6 @@ __device__ __forceinline__ void pages_iterate(const PageRegs& M, PagesShared& sh
   // in the opposite order, so that the 128-bit stores of p (8 lanes = rh, rh+1 per wavefront) hit 32 distinct
   // banks.  Nothing else depends on the order: both pixel rows share the window.
   const int off_s[2] = {row_base + 16 * (rh & 1), row_base + 16 * ((rh & 1) ^ 1)};
-  const int nbar = (W + 1) * 32;
   constexpr bool RECORD = MODE != 2;
   const float (&f)[8] = M.f;
   const float (&D)[8][12] = M.D;
@@ -700,23 +857,14 @@ __device__ __forceinline__ void pages_iterate(const PageRegs& M, PagesShared& sh
   const uint32_t a_qspan = keep(a_qs + 4 * sp);
   const uint32_t o_s0 = keep(4 * off_s[0]), o_s1 = keep(4 * off_s[1]), o_span = 4 * sp;
   const uint32_t a_q0 = keep(a_qs + 4 * (off_s[0] >> 2)), a_q1 = keep(a_qs + 4 * (off_s[1] >> 2));   // q index of row rho is rho >> 2
-  const uint32_t a_E = keep(s_u32(&sh.E[0][warp][lane]));
-  const uint32_t a_flag = s_u32(&sh.flag[0]);
   const uint32_t a_best = s_u32(best);
 
   const float A = M.A;     // sum over this lane's rows of A_rho (row_constants, computed by the sparsify kernels)
-  if (RECORD) {
-    s_st1(a_E, M.e0);      // the record of iteration 0 (p = q = 1, CP:123)
-    named_arrive(1, nbar);
-  }
+  if (RECORD) sync.publish(0, M.e0);   // the record of iteration 0 (p = q = 1, CP:123)
 
   auto keep_if_best = [&](int j) {   // end of step j + kLag: wait for the verdict on iteration j
-    const uint32_t fa = a_flag + 4 * (j & (kRing - 1));
-    int v;
-    do {
-      v = s_ld_flag(fa);
-    } while (v < 2 * j);             // the slot's previous verdict (or -1) is smaller
-    if (MODE == 0 && (v & 1)) {
+    const bool better = sync.verdict(j);
+    if (MODE == 0 && better) {
       if (j == 0) {
         s_st4(a_best + o_s0, 1.f, 1.f, 1.f, 1.f);
         s_st4(a_best + o_s1, 1.f, 1.f, 1.f, 1.f);
@@ -735,12 +883,8 @@ __device__ __forceinline__ void pages_iterate(const PageRegs& M, PagesShared& sh
 #pragma unroll
   for (int t = 0; t < 8; ++t) p_out[t] = 1.0f;
   __syncwarp();
-  int next_red = warp;   // next iteration this warp is the reducer of (j % W == warp)
   for (int k = 1; k <= n_iter; ++k) {
-    if (RECORD && k - kRedDelay == next_red) {
-      pages_reduce<MODE == 0>(sh, next_red, W, lane, inv_cnt, record_out);
-      next_red += W;
-    }
+    if (RECORD) sync.template duty<MODE == 0>(k - kRedDelay);   // this warp's turn as the reducer of iteration k - kRedDelay?
     const uint32_t slot = (uint32_t)k & (kRing - 1);
     // ---- statistics of q_{k-1} about m: S1 = sum (q - m), V = sum (q - m)^2
     const float da = qa - m, db = qb - m;
@@ -778,10 +922,7 @@ __device__ __forceinline__ void pages_iterate(const PageRegs& M, PagesShared& sh
     const uint32_t pk = a_ps + (slot << 10);
     s_st4(pk + o_s0, p[0], p[1], p[2], p[3]);
     s_st4(pk + o_s1, p[4], p[5], p[6], p[7]);
-    if (RECORD) {
-      s_st1(a_E + (slot << 11), fmaf(-2.0f, fmaf(S1, pg, psd), fmaf(64.0f, gg, fmaf(V, pp, A))));
-      named_arrive(1 + (int)slot, nbar);
-    }
+    if (RECORD) sync.publish(k, fmaf(-2.0f, fmaf(S1, pg, psd), fmaf(64.0f, gg, fmaf(V, pp, A))));
     __syncwarp();
     if (k == n_iter) {   // the reference's last q-update is never used
       if (!RECORD) {
@@ -821,11 +962,7 @@ __device__ __forceinline__ void pages_iterate(const PageRegs& M, PagesShared& sh
   if (RECORD) {
     // drain: the reducers of the last kRedDelay iterations, and the verdicts not yet read (the loop read those up to
     // n_iter - 1 - kLag).  Reducers first, in iteration order: every verdict awaited below is then on its way.
-    for (int j = max(n_iter - kRedDelay + 1, 0); j <= n_iter; ++j)
-      if (j == next_red) {
-        pages_reduce<MODE == 0>(sh, j, W, lane, inv_cnt, record_out);
-        next_red += W;
-      }
+    for (int j = max(n_iter - kRedDelay + 1, 0); j <= n_iter; ++j) sync.template duty<MODE == 0>(j);
     for (int j = max(n_iter - kLag, 0); j <= n_iter; ++j) keep_if_best(j);
   }
 }
@@ -942,7 +1079,8 @@ __global__ void __launch_bounds__(32 * kGroupWarps, 1) als_pages_kernel(const __
     for (int dr = 0; dr < 2; ++dr)
       *reinterpret_cast<float4*>(best + 32 * (lane >> 2) + 4 * (lane & 3) + 16 * dr) = make_float4(1.f, 1.f, 1.f, 1.f);
     __syncwarp();
-    pages_iterate<0>(M, sh, ps, qs, best, lane, warp, W0, limit, inv_cnt, record_out, pv);
+    LocalSync sync(sh, warp, lane, W0, inv_cnt, record_out);
+    pages_iterate<0>(M, sync, ps, qs, best, lane, limit, pv);
     {
       const int rh = lane >> 2, kq = lane & 3;
       const int row_base = 32 * rh + 4 * kq;
@@ -963,7 +1101,8 @@ __global__ void __launch_bounds__(32 * kGroupWarps, 1) als_pages_kernel(const __
     const int Wr = min(W0, group - r * W0);
     if (warp < Wr) {
       load_page(M, sc.ws + unit_of(r) * stride, lane);
-      pages_iterate<1>(M, sh, ps, qs, best, lane, warp, Wr, limit, inv_cnt, nullptr, pv);
+      LocalSync sync(sh, warp, lane, Wr, inv_cnt, nullptr);
+      pages_iterate<1>(M, sync, ps, qs, best, lane, limit, pv);
     }
     __syncthreads();
     if (threadIdx.x < kRing) sh.flag[threadIdx.x] = -1;
@@ -992,9 +1131,76 @@ __global__ void __launch_bounds__(32 * kGroupWarps, 1) als_pages_kernel(const __
   for (int r = 0; r < rounds; ++r) {
     if (r * W0 + warp >= group) break;
     load_page(M, sc.ws + unit_of(r) * stride, lane);
-    pages_iterate<2>(M, sh, ps, qs, best, lane, warp, 1, kstar, inv_cnt, nullptr, pv);
+    LocalSync sync(sh, warp, lane, 1, inv_cnt, nullptr);
+    pages_iterate<2>(M, sync, ps, qs, best, lane, kstar, pv);
     pages_emit(sc, unit_of(r), pv, lane);
   }
+}
+
+// The same work with the 16 warps of a group spread over a cluster of 4 CTAs (ClusterSync).  grid = 4 x (group, page)
+// items; group must be 16.
+__global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(32 * kClusterWarps, 4)
+    als_pages_cluster_kernel(const __grid_constant__ PagesParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  PagesClusterShared& sh = *reinterpret_cast<PagesClusterShared*>(smem_raw);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* wrow = reinterpret_cast<float*>(smem_raw + ((sizeof(PagesClusterShared) + 15) & ~size_t(15))) + warp * kWarpFloats;
+  float* ps = wrow;
+  float* qs = wrow + kRing * 256;
+  float* best = qs + 64;
+  uint32_t crank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+  const int item_all = (int)(blockIdx.x / kClusterCtas);
+  int si = 0;
+#pragma unroll 1
+  for (int k = 1; k < P.n_scales; ++k)
+    if (item_all >= P.s[k].cta_begin) si = k;
+  const PagesScaleDev& sc = P.s[si];
+  const int item = item_all - sc.cta_begin;
+  const int g = item / sc.pages, pg = item - g * sc.pages;
+  const int limit = sc.limit;
+  const int gw = (int)crank * kClusterWarps + warp;                 // image of the group this warp iterates
+  const int64_t stride = als_ws_stride(256, limit);
+  const double inv_cnt = 1.0 / ((double)kGroupWarps * (double)(256 * 64));
+  float* record_out = sc.record_out ? sc.record_out + ((int64_t)g * sc.pages + pg) * (limit + 1) : nullptr;
+  const int64_t unit = ((int64_t)g * kGroupWarps + gw) * sc.pages + pg;
+  if (threadIdx.x < kRing) {
+    sh.flag[threadIdx.x] = 0ull;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(&sh.mbar[threadIdx.x])), "r"(1) : "memory");
+  }
+  if (threadIdx.x == 0) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  // every CTA checks all 16 units of the item itself, so that the four CTAs decide alike without talking
+  if (warp == 0) {
+    const bool ok = lane >= kGroupWarps || unit_is_compact(sc.ws + (((int64_t)g * kGroupWarps + lane) * sc.pages + pg) * stride);
+    const unsigned all = __ballot_sync(kFull, ok);
+    if (lane == 0) sh.all_compact = all == kFull ? 1 : 0;
+  }
+  __syncthreads();
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");   // mbarriers and flags are initialised everywhere
+  if (!sh.all_compact) return;   // the dense kernel takes the whole item
+  PageRegs M;
+  float pv[8];
+  load_page(M, sc.ws + unit * stride, lane);
+#pragma unroll
+  for (int dr = 0; dr < 2; ++dr)
+    *reinterpret_cast<float4*>(best + 32 * (lane >> 2) + 4 * (lane & 3) + 16 * dr) = make_float4(1.f, 1.f, 1.f, 1.f);
+  __syncwarp();
+  ClusterSync sync(sh, gw, lane, crank, inv_cnt, record_out);
+  pages_iterate<0>(M, sync, ps, qs, best, lane, limit, pv);
+  {
+    const int rh = lane >> 2, kq = lane & 3;
+    const int row_base = 32 * rh + 4 * kq;
+    const int off_s[2] = {row_base + 16 * (rh & 1), row_base + 16 * ((rh & 1) ^ 1)};
+#pragma unroll
+    for (int ds = 0; ds < 2; ++ds) {
+      const float4 b = *reinterpret_cast<const float4*>(best + off_s[ds]);
+      pv[4 * ds] = b.x; pv[4 * ds + 1] = b.y; pv[4 * ds + 2] = b.z; pv[4 * ds + 3] = b.w;
+    }
+  }
+  pages_emit(sc, unit, pv, lane);
+  if (gw == 0 && lane == 0 && sc.kstar_out) sc.kstar_out[(int64_t)g * sc.pages + pg] = sync.kstar;
+  // nobody leaves while a sibling may still store into its shared memory
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 }  // namespace
@@ -1063,6 +1269,26 @@ int als_sparse_launch(const rdm_als_scale_t* scales, int32_t n_scales, int64_t n
     if (rc) return rc;
   }
   if (!iterate) return 0;
+  // Two forms of the page kernel, same results bit for bit.  One CTA of 16 warps per (batch, page) has the better
+  // throughput once the chip is full (4.7 vs 7.5 us per batch at 29 batches per launch); a cluster of 4 CTAs of 4
+  // warps spreads a SMALL launch over 4x the SMs (a lone batch-16 call: 82 vs 131 us).  Default: the cluster form
+  // while the items would leave SMs short of two CTAs each; RDM_ALS_PAGES_ONE_CTA / RDM_ALS_PAGES_CLUSTER force one.
+  bool one_cta = group != kGroupWarps || n_items >= 2 * (int64_t)kNumSMs;
+  for (int k = 0; k < n_scales; ++k) {
+    if (scales[k].flags & RDM_ALS_PAGES_CLUSTER) one_cta = group != kGroupWarps;
+    if (scales[k].flags & RDM_ALS_PAGES_ONE_CTA) one_cta = true;
+  }
+  if (!one_cta) {
+    const size_t dync = ((sizeof(PagesClusterShared) + 15) & ~size_t(15)) + (size_t)kClusterWarps * kWarpFloats * sizeof(float);
+    static size_t smem_setc[64];
+    cudaError_t ec = ensure_dyn_smem(als_pages_cluster_kernel, dync, smem_setc);
+    if (ec != cudaSuccess) {
+      set_error("rdm_als_fused: cudaFuncSetAttribute(als_pages_cluster_kernel): %s", cudaGetErrorString(ec));
+      return (int)ec;
+    }
+    als_pages_cluster_kernel<<<(unsigned)(n_items * kClusterCtas), 32 * kClusterWarps, dync, stream>>>(all);
+    return launch_status("als_pages_cluster_kernel");
+  }
   const int warps = group < kGroupWarps ? group : kGroupWarps;
   const size_t dyn = ((sizeof(PagesShared) + 15) & ~size_t(15)) + (size_t)warps * kWarpFloats * sizeof(float);
   static size_t smem_set[64];

@@ -889,6 +889,36 @@ def test_stress_pages_argmin_protocol_repeatable(dev, books):
             assert rr[ks[pi]] <= rr.min() * (1 + 3e-6), (group, pi, ks[pi], int(rr.argmin()))
 
 
+def test_pages_kernel_forms_agree(dev, books):
+    """The page ALS exists as one CTA of 16 warps per (batch, page) and as a cluster of 4 CTAs of 4 warps exchanging
+    residuals through distributed shared memory (st.async + mbarrier).  The launch size picks one; both flags force
+    one.  Same k*, record and maps bit for bit, for one batch per launch and for many, run after run."""
+    from md_rdm_b200 import _cabi
+    from md_rdm_b200.fusion import FusionPlan
+    scales = (8, 16, 32)
+    for G in (1, 3, 20):
+        x_d1, rel, weights = fr.synthetic_batch(16 * G, scales, seed=777 + G)
+        w = torch.cat([t.reshape(-1) for t in weights]).to(dev)
+        snaps = {}
+        for name, flags in (("auto", 0), ("one_cta", _cabi.ALS_PAGES_ONE_CTA), ("cluster", _cabi.ALS_PAGES_CLUSTER)):
+            plan = FusionPlan(16 * G, scales, "map", group=16, device=dev, flags=flags)
+            plan.load_inputs(x_d1.to(dev), [t.to(dev) for t in rel], w)
+            for rep in range(5 if name == "cluster" else 1):
+                for s in scales:
+                    plan.rel[s].fill_(-1.0)
+                    plan.kstar[s].fill_(-1)
+                out = plan.run()
+                torch.cuda.synchronize()
+                snap = [plan.kstar[s].clone() for s in scales] + [plan.rel[s].clone() for s in scales] + [plan.record[s].clone() for s in scales] + [out.clone()]
+                if name in snaps:
+                    for u, v in zip(snaps[name], snap):
+                        assert torch.equal(u, v), (G, name, rep)
+                snaps[name] = snap
+        for name in ("one_cta", "cluster"):
+            for u, v in zip(snaps["auto"], snaps[name]):
+                assert torch.equal(u, v), (G, name)
+
+
 # ============================================================================ the literal call sequence of the reference
 def test_literal_call_sequence_rn_383_396(dev, books):
     """RN:383-396 written against the drop-in NAMES exactly as the reference calls them - cp.resize,

@@ -20,7 +20,7 @@ N = 16 * groups
 ring = []
 for b in range(max(64 // groups, 4)):
     x_d1, rel, weights = bench.synthetic_batch(N, bench.SCALES, seed=1234 + b)
-    plan = FusionPlan(N, bench.SCALES, source, group=16, device=dev, want_bins=True)
+    plan = FusionPlan(N, bench.SCALES, source, group=16, device=dev, want_bins=True, flags=bench.PLAN_FLAGS)
     rel_d = [r.to(dev) for r in rel]
     srcs = [R.pair_v1(r) if r.shape[2] == 8 else R.pair_id(r)[0] for r in rel_d] if source == "raw" else rel_d
     plan.load_inputs(x_d1.to(dev), srcs, torch.cat([w.reshape(-1) for w in weights]).to(dev))

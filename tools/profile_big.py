@@ -17,7 +17,7 @@ dev = torch.device("cuda:0")
 R = torch.ops.rdm
 N = 16 * groups
 x_d1, rel, weights = bench.synthetic_batch(N, bench.SCALES, seed=1234)
-plan = FusionPlan(N, bench.SCALES, "raw", group=16, device=dev, want_bins=True)
+plan = FusionPlan(N, bench.SCALES, "raw", group=16, device=dev, want_bins=True, flags=bench.PLAN_FLAGS)
 rel_d = [r.to(dev) for r in rel]
 srcs = [R.pair_v1(r) if r.shape[2] == 8 else R.pair_id(r)[0] for r in rel_d]
 plan.load_inputs(x_d1.to(dev), srcs, torch.cat([w.reshape(-1) for w in weights]).to(dev))
