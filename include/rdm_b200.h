@@ -207,6 +207,20 @@ int rdm_decompose_bwd(const void* in, int32_t in_is_f64, int64_t n_images, int32
 int rdm_gm_bwd(const void* x, int32_t is_f64, int64_t batch, int64_t n, int32_t rc,
                const void* grad_gm, const void* grad_norm, void* grad_x, rdm_stream_t stream);
 
+/* Backward of rdm_fuse_tail to `weights` in two launches (the training step, network/module.py:89-95: only the MSE on the
+ * final depth reaches Weights): grad_w[first_k + j] = sum_b sum_m f32(A_k[b,j,m]) * f32(pool_k(grad_depth)[b,m]), pool_k =
+ * the successive 2x2 sums of rdm_recombination_bwd (n = 7).  Bit-identical to rdm_recombination_bwd followed by
+ * rdm_make_pred_bwd slot by slot.  A: HOST array of kmax+1 device pointers (A_out of rdm_fuse_tail); K: HOST, candidates
+ * per slot; ws: n_images * (4^(kmax+1) - 1) / 3 floats of scratch; grad_w: sum K floats, overwritten. */
+int rdm_fuse_tail_bwd(const double* grad_depth, const double* const* A, const int32_t* K, int32_t kmax,
+                      int64_t n_images, float* ws, float* grad_w, rdm_stream_t stream);
+
+/* network/computations.py:499-510 (the detached per-scale component loss of the training step) in one launch:
+ * out[0] = sum_{k=0..kmax} mean((yhat_k - target_k)^2), f64.  yhat: (N, sum 4^k) f32 as rdm_fuse_tail packs it;
+ * target: level-major pyramid (rdm_gt_prepare / rdm_decompose with relative_map = 0). */
+int rdm_component_loss(const float* yhat, const double* target, int64_t n_images, int32_t kmax, double* out,
+                       rdm_stream_t stream);
+
 /* Ground-truth preparation of the training step in ONE launch: network/module.py:68 cp.resize(y, 128)
  * (bicubic), :74-78 mask (+1e-4 everywhere, invalid -> 1.0001), :145-149 normalize, :123 decompose n = 7, and the ordinal
  * target of :126-127 / :134-143: utils.depth2label_sid(cp.resize(y, 8)) (utils.py:195-211) whose normalised

@@ -1386,3 +1386,112 @@ extern "C" int rdm_gt_prepare(const void* y_raw, int32_t in_is_f64, int64_t n_im
   }
   return launch_status("gt_prepare_kernel");
 }
+
+// ---------------------------------------------------------------------------------------------
+// Training step, the two places where the per-slot ops left a trail of small launches.
+namespace rdm {
+
+struct TailBwdLevels {
+  const double* A[8];   // (B, K_k, 4^k) f64
+  int32_t K[8];
+  int32_t first[9];     // first[k] = K_0 + ... + K_{k-1}
+};
+
+// grad_w of every slot in one launch: CTA = one weight; the arithmetic (thread-strided f64 FMA, warp tree, warps in
+// order) is make_pred_bwd_w_kernel's, so the result is bit-identical to the slot-by-slot chain.
+__global__ void __launch_bounds__(512) make_pred_bwd_w_all_kernel(const __grid_constant__ TailBwdLevels lv, int kmax, int64_t batch,
+                                                                  const float* __restrict__ gs, float* __restrict__ grad_w) {
+  __shared__ double part[16];
+  int k = 0;
+  while (k < kmax && (int)blockIdx.x >= lv.first[k + 1]) ++k;
+  const int j = (int)blockIdx.x - lv.first[k], K = lv.K[k];
+  const int64_t M = (int64_t)1 << (2 * k);
+  const double* __restrict__ A = lv.A[k];
+  const float* __restrict__ g = gs + batch * off_level(k);   // level-major: level k is (B, 4^k)
+  double acc = 0.0;
+  for (int64_t o = threadIdx.x; o < batch * M; o += blockDim.x) {
+    const int64_t b = o / M, m = o - b * M;
+    acc = fma((double)(float)A[(b * K + j) * M + m], (double)g[o], acc);
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += part[i];
+    grad_w[blockIdx.x] = (float)t;
+  }
+}
+
+// CP:499-510 (the per-scale component loss of the training step): sum_k mean((yhat_k - target_k)^2) in f64, one CTA,
+// levels in order.  yhat is image-major (B, sum 4^k) f32, the targets are the level-major pyramid of rdm_gt_prepare /
+// rdm_decompose(relative_map = 0).
+__global__ void __launch_bounds__(1024) component_loss_kernel(const float* __restrict__ yhat, const double* __restrict__ target, int64_t batch,
+                                                              int kmax, double* __restrict__ out) {
+  __shared__ double part[32];
+  const int64_t row = off_level(kmax + 1);   // floats of yhat per image
+  double total = 0.0;
+  for (int k = 0; k <= kmax; ++k) {
+    const int64_t M = (int64_t)1 << (2 * k), n = batch * M;
+    const double* __restrict__ t = target + batch * off_level(k);
+    double acc = 0.0;
+    for (int64_t o = threadIdx.x; o < n; o += blockDim.x) {
+      const int64_t b = o / M, m = o - b * M;
+      const double d = (double)yhat[b * row + off_level(k) + m] - t[o];
+      acc = fma(d, d, acc);
+    }
+    acc = warp_sum(acc);
+    __syncthreads();   // part[] of the previous level has been read
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double s = 0.0;
+      for (int i = 0; i < 32; ++i) s += part[i];
+      total += s / (double)n;
+    }
+  }
+  if (threadIdx.x == 0) out[0] = total;
+}
+
+}  // namespace rdm
+
+extern "C" int rdm_fuse_tail_bwd(const double* grad_depth, const double* const* A, const int32_t* K, int32_t kmax, int64_t n_images,
+                                 float* ws, float* grad_w, rdm_stream_t stream) {
+  RDM_REQUIRE(grad_depth && A && K && ws && grad_w, "rdm_fuse_tail_bwd: null pointer");
+  RDM_REQUIRE(kmax >= 3 && kmax <= 6, "rdm_fuse_tail_bwd: kmax must be 3..6 (got %d)", kmax);
+  RDM_REQUIRE(n_images >= 0 && n_images < (1ll << 31), "rdm_fuse_tail_bwd: bad n_images");
+  TailBwdLevels lv{};
+  int total = 0;
+  for (int k = 0; k <= kmax; ++k) {
+    RDM_REQUIRE(A[k] && K[k] >= 1, "rdm_fuse_tail_bwd: slot %d: null A or K < 1", k);
+    lv.A[k] = A[k];
+    lv.K[k] = K[k];
+    lv.first[k] = total;
+    total += K[k];
+  }
+  lv.first[kmax + 1] = total;
+  if (n_images == 0) {
+    cudaMemsetAsync(grad_w, 0, sizeof(float) * total, (cudaStream_t)stream);
+    return launch_status("rdm_fuse_tail_bwd memset");
+  }
+  // pooled gradients of the recombination (128x128 output, n = 7), f32 like the per-slot chain, level-major in ws
+  void* gp[8];
+  int32_t sides[8];
+  for (int k = 0; k <= kmax; ++k) {
+    gp[k] = ws + n_images * off_level(k);
+    sides[k] = 1 << k;
+  }
+  int rc = rdm_recombination_bwd(grad_depth, gp, sides, kmax + 1, 0, n_images, 7, stream);
+  if (rc) return rc;
+  make_pred_bwd_w_all_kernel<<<(unsigned)total, 512, 0, (cudaStream_t)stream>>>(lv, kmax, n_images, ws, grad_w);
+  return launch_status("make_pred_bwd_w_all_kernel");
+}
+
+extern "C" int rdm_component_loss(const float* yhat, const double* target, int64_t n_images, int32_t kmax, double* out,
+                                  rdm_stream_t stream) {
+  RDM_REQUIRE(yhat && target && out, "rdm_component_loss: null pointer");
+  RDM_REQUIRE(kmax >= 0 && kmax <= 7, "rdm_component_loss: kmax must be 0..7 (got %d)", kmax);
+  RDM_REQUIRE(n_images >= 1 && n_images < (1ll << 31), "rdm_component_loss: bad n_images");
+  component_loss_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(yhat, target, n_images, kmax, out);
+  return launch_status("component_loss_kernel");
+}

@@ -676,6 +676,52 @@ def _(x_d1, rel, weights, want_A):
             x_d1.new_empty((B, (4 ** (kmax + 1) - 1) // 3), dtype=torch.float32), A)
 
 
+@torch.library.custom_op("rdm::fuse_tail_bwd", mutates_args=())
+def fuse_tail_bwd(grad_depth: Tensor, A: Sequence[Tensor]) -> Tensor:
+    """Gradient of fuse_tail's depth with respect to the flat weights, two launches (pooled gradients of the
+    recombination, then every weight's reduction); bit-identical to recombination_bwd + make_pred_bwd slot by slot."""
+    _need_cuda("fuse_tail_bwd", grad_depth, *A)
+    B = A[0].shape[0]
+    kmax = len(A) - 1
+    K = [int(a.shape[1]) for a in A]
+    dev = grad_depth.device
+    g = grad_depth.double().contiguous()
+    As = [a.contiguous() for a in A]
+    ws = torch.empty((B * ((4 ** (kmax + 1) - 1) // 3),), dtype=torch.float32, device=dev)
+    gw = torch.empty((sum(K),), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(load().rdm_fuse_tail_bwd(_p(g), ptr_array([a.data_ptr() for a in As]), i32_array(K), kmax, B, _p(ws), _p(gw), _stream()),
+              "rdm_fuse_tail_bwd")
+    return gw
+
+
+@fuse_tail_bwd.register_fake
+def _(grad_depth, A):
+    return grad_depth.new_empty((sum(int(a.shape[1]) for a in A),), dtype=torch.float32)
+
+
+@torch.library.custom_op("rdm::component_loss", mutates_args=())
+def component_loss(yhat: Tensor, target_pyramid: Tensor, kmax: int) -> Tensor:
+    """CP:499-510 in one launch: sum over k <= kmax of the MSE between y_hat_k (packed, fuse_tail) and the level-major
+    target pyramid (gt_prepare / decompose_packed); f64 scalar, no gradient (the reference detaches it)."""
+    _need_cuda("component_loss", yhat, target_pyramid)
+    if yhat.dtype != torch.float32 or target_pyramid.dtype != torch.float64 or yhat.dim() != 2:
+        raise RuntimeError("rdm::component_loss: yhat must be packed (B, sum 4^k) f32 and the targets an f64 pyramid")
+    B = yhat.shape[0]
+    if yhat.shape[1] != (4 ** (kmax + 1) - 1) // 3 or target_pyramid.numel() < B * ((4 ** (kmax + 1) - 1) // 3):
+        raise RuntimeError("rdm::component_loss: shapes do not match kmax")
+    out = torch.empty((), dtype=torch.float64, device=yhat.device)
+    with torch.cuda.device(yhat.device):
+        check(load().rdm_component_loss(_p(yhat.contiguous()), _p(target_pyramid.contiguous()), B, kmax, _p(out), _stream()),
+              "rdm_component_loss")
+    return out
+
+
+@component_loss.register_fake
+def _(yhat, target_pyramid, kmax):
+    return yhat.new_empty((), dtype=torch.float64)
+
+
 def split_yhat(yhat: Tensor, kmax: int) -> List[Tensor]:
     """Views of the packed y_hat as the reference's list of (B,1,2^k,2^k) f32 tensors."""
     B = yhat.shape[0]
@@ -697,6 +743,7 @@ class _FuseTailFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x_d1, weights, *rel):
         depth, yhat, A = torch.ops.rdm.fuse_tail(x_d1, list(rel), weights, True)
+        ctx.set_materialize_grads(False)   # y_hat feeds only the detached component loss: its gradient stays None
         sides = [int(r.shape[2]) for r in rel]
         K, off, kmax, _ = tail_layout(sides)
         ctx.layout = (K, off, kmax)
@@ -710,6 +757,8 @@ class _FuseTailFn(torch.autograd.Function):
         K, off, kmax = ctx.layout
         B = A[0].shape[0]
         sides = [2 ** k for k in range(kmax + 1)]
+        if g_depth is not None and g_yhat is None:   # the training step: two launches
+            return (None, torch.ops.rdm.fuse_tail_bwd(g_depth, list(A)).to(weights.dtype)) + tuple(None for _ in range(ctx.n_rel))
         if g_depth is not None:
             gs = torch.ops.rdm.recombination_bwd(g_depth, sides, False, 7)
         else:

@@ -34,7 +34,9 @@ class TrainingStep:
                  fused_gt: bool = True):
         self.device = torch.device(device)
         self.B, self.scales = int(batch), tuple(int(s) for s in scales)
-        self.plan = FusionPlan(self.B, self.scales, "map", device=self.device, want_bins=False)
+        # overlap: the dense ALS of the 8x8 maps runs beside the page ALS (a lone batch is latency-bound)
+        self.plan = FusionPlan(self.B, self.scales, "map", device=self.device, want_bins=False, overlap=True)
+        self._gt_stream: Optional[torch.cuda.Stream] = None
         dev, f32, f64 = self.device, torch.float32, torch.float64
         self.weights = torch.ones((self.plan.n_weights,), dtype=f32, device=dev, requires_grad=True)
         self.logits = torch.zeros((self.B, 2 * K, 8, 8), dtype=f32, device=dev, requires_grad=True)
@@ -61,28 +63,41 @@ class TrainingStep:
 
     # ------------------------------------------------------------------ ground truth (MOD:68, 74-78, 119-127)
     def targets(self):
-        """(y masked 128x128 f64, component targets [d0, f1..f7] f64, ordinal target (B,1,8,8) int32)."""
+        """(y masked 128x128 f64, packed level-major target pyramid or None, component targets [d0, f1..f7] f64,
+        ordinal target (B,1,8,8) int32)."""
         if self.fused_gt:
             y, pyr, ord_t = R.gt_prepare(self.y_raw)
-            return y, ops.unpack_pyramid(pyr, self.B, 128, False), ord_t
+            return y, pyr, ops.unpack_pyramid(pyr, self.B, 128, False), ord_t
         y = cp.resize(self.y_raw, 128)                                         # MOD:68
         y = (y * (y > 0)) + ((y <= 0) + 1e-4)                                  # MOD:74-78
         comps = cp.decompose_depth_map([], R.gm_normalize(y), 7)[::-1]        # MOD:123, MOD:145-149
         ord_t = depth2label_sid(cp.resize(y, 8))                               # MOD:126 / MOD:134-143 (same tensor)
         comps[0] = cp.decompose_depth_map([], R.gm_normalize(ord_t.long()), 3)[::-1][0]
-        return y, comps, ord_t
+        return y, None, comps, ord_t
 
     # ------------------------------------------------------------------ one step
     def step(self) -> Dict[str, torch.Tensor]:
         self.weights.grad = None
         self.logits.grad = None
+        cur = torch.cuda.current_stream(self.device)
+        # The ground truth does not depend on the network: it is prepared on a second stream that forks here and
+        # joins before the losses (plain stream waits: capturable, two parallel branches of the CUDA graph).  The fork
+        # also orders this step's allocations on that stream behind the previous step's work.
+        if self._gt_stream is None:
+            self._gt_stream = torch.cuda.Stream(self.device)
+        self._gt_stream.wait_stream(cur)
+        with torch.cuda.stream(self._gt_stream):
+            y, pyr, comps, ord_t = self.targets()
         x_d1, ord_ = R.dorn_regression(self.logits)                            # RN:313-345
         rel = self.plan.run_als()                                              # RN:358-396 for every relative decoder
         final, yhat = fuse_tail_autograd(x_d1, [rel[s] for s in self.scales], self.weights)   # RN:117-133 + MOD:132
-        y, comps, ord_t = self.targets()
+        cur.wait_stream(self._gt_stream)
         # CP:499-510: per-scale MSE, summed through torch.as_tensor => detached (no host sync here)
         with torch.no_grad():
-            fine = torch.stack([torch.nn.functional.mse_loss(a.double(), b) for a, b in zip(split_yhat(yhat, self.plan.kmax), comps)]).sum()
+            if pyr is not None:
+                fine = R.component_loss(yhat, pyr, self.plan.kmax)
+            else:
+                fine = torch.stack([torch.nn.functional.mse_loss(a.double(), b) for a, b in zip(split_yhat(yhat, self.plan.kmax), comps)]).sum()
         ord_loss = R.ordinal_loss(ord_, ord_t)                                 # loss.py:17-59
         mse = torch.nn.functional.mse_loss(final, y)                           # MOD:89
         loss = mse + fine + ord_loss                                           # MOD:90-92
@@ -117,8 +132,9 @@ class TrainingStep:
 
     def launches_per_step(self) -> int:
         """Kernels of librdm_b200 per step (torch's own elementwise kernels for the losses come on top)."""
-        gt = 1 if self.fused_gt else 7
-        return 2 + (self.plan.launches_per_run - 1) + 1 + gt + 2 + 2 + len(range(self.plan.kmax + 1))
+        gt = 2 if self.fused_gt else 7      # gt_prepare + component_loss
+        # dorn_regression (2) + ALS launches + fuse_tail + GT + ordinal loss (2) + backward: ordinal, dorn, tail (2)
+        return 2 + (self.plan.launches_per_run - 1) + 1 + gt + 2 + 2 + 2
 
     # ------------------------------------------------------------------ host end to end
     def pin_host(self) -> None:

@@ -1110,6 +1110,42 @@ def test_gt_prepare_one_launch(dev):
                 assert _rel_err(comps[0].cpu(), tg[0]) < 1e-6
 
 
+def test_training_fused_tail_backward_and_component_loss(dev):
+    """The training step's two fused pieces against the per-slot ops they replace: rdm::fuse_tail_bwd (pooled
+    gradients + every weight's reduction, two launches) is bit-identical to recombination_bwd + make_pred_bwd slot by
+    slot - also through autograd, where y_hat's absent gradient selects it - and rdm::component_loss (CP:499-510 in one
+    launch) equals the per-scale torch MSE sum to f64 rounding."""
+    from md_rdm_b200.ops import fuse_tail_autograd, split_yhat, tail_layout, unpack_pyramid
+    for scales in ((8, 16, 32), (8, 16, 32, 64), (16,)):
+        B = 5
+        x_d1, rel, weights = fr.synthetic_batch(B, scales, seed=31 + len(scales))
+        w = torch.cat([t.reshape(-1) for t in weights]).to(dev).requires_grad_(True)
+        rel_d = [r.to(dev) for r in rel]
+        K, off, kmax, nw = tail_layout(list(scales))
+        depth, yhat, A = R.fuse_tail(x_d1.to(dev), rel_d, w.detach(), True)
+        g = torch.randn(B, 1, 128, 128, dtype=torch.float64, generator=torch.Generator().manual_seed(5)).to(dev)
+        gw = R.fuse_tail_bwd(g, list(A))
+        gs = R.recombination_bwd(g, [2 ** k for k in range(kmax + 1)], False, 7)
+        ref = torch.zeros(nw, dtype=torch.float32, device=dev)
+        for k in range(kmax + 1):
+            _, gk = R.make_pred_bwd(A[k], w.detach()[off[k]:off[k] + K[k]], gs[k].reshape(B, -1))
+            ref[off[k]:off[k] + K[k]] = gk
+        assert torch.equal(gw, ref), scales
+        # through autograd: depth only (fused backward) vs depth + 0 * y_hat (slot-by-slot chain)
+        final, yh = fuse_tail_autograd(x_d1.to(dev), rel_d, w)
+        (g1,) = torch.autograd.grad((final * g).sum(), w)
+        final, yh = fuse_tail_autograd(x_d1.to(dev), rel_d, w)
+        (g2,) = torch.autograd.grad((final * g).sum() + 0.0 * yh.sum(), w)
+        assert torch.equal(g1, g2), scales
+        # component loss against the per-scale MSE sum
+        y_raw = 0.5 + 9.5 * torch.rand(B, 1, 226, 226, dtype=torch.float64, generator=torch.Generator().manual_seed(9))
+        _, pyr, _ = R.gt_prepare(y_raw.to(dev))
+        comps = unpack_pyramid(pyr, B, 128, False)
+        want = torch.stack([torch.nn.functional.mse_loss(a.double(), b) for a, b in zip(split_yhat(yhat, kmax), comps)]).sum()
+        got = R.component_loss(yhat, pyr, kmax)
+        assert got.dtype == torch.float64 and abs(float(got) - float(want)) <= 1e-12 * abs(float(want)), (float(got), float(want))
+
+
 # ============================================================================ SURVEY 8f rank 4: "paper-correct" flags
 @pytest.mark.parametrize("flag_name", ["true_gm", "correct_tiling", "true_transpose", "all"])
 def test_paper_correct_flags_vs_oracle(dev, books, flag_name):
