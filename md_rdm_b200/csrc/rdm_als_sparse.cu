@@ -1270,16 +1270,48 @@ int als_sparse_launch(const rdm_als_scale_t* scales, int32_t n_scales, int64_t n
   }
   if (!iterate) return 0;
   // Two forms of the page kernel, same results bit for bit.  One CTA of 16 warps per (batch, page) has the better
-  // throughput once the chip is full (4.7 vs 7.5 us per batch at 29 batches per launch); a cluster of 4 CTAs of 4
-  // warps spreads a SMALL launch over 4x the SMs (a lone batch-16 call: 82 vs 131 us).  Default: the cluster form
-  // while the items would leave SMs short of two CTAs each; RDM_ALS_PAGES_ONE_CTA / RDM_ALS_PAGES_CLUSTER force one.
-  bool one_cta = group != kGroupWarps || n_items >= 2 * (int64_t)kNumSMs;
+  // throughput once the chip is full; a cluster of 4 CTAs of 4 warps spreads a SMALL launch over 4x the SMs (a lone
+  // batch-16 call: 82 vs 131 us) and is as efficient per SM as long as every cluster is resident at once - a second
+  // wave of clusters costs a whole extra pass (29 batches per launch: 7.5 vs 4.7 us per batch).  Default: the cluster
+  // form while the clusters fill at most 4/5 of one wave; RDM_ALS_PAGES_ONE_CTA / RDM_ALS_PAGES_CLUSTER force one.
+  const size_t dync = ((sizeof(PagesClusterShared) + 15) & ~size_t(15)) + (size_t)kClusterWarps * kWarpFloats * sizeof(float);
+  bool one_cta = group != kGroupWarps;
+  if (!one_cta) {
+    static int max_clusters[64];   // per device, queried once (benign race)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int slot = dev >= 0 && dev < 64 ? dev : 0;
+    if (max_clusters[slot] == 0) {
+      static size_t smem_setq[64];
+      int n = 0;
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(kClusterCtas * 1024);
+      cfg.blockDim = dim3(32 * kClusterWarps);
+      cfg.dynamicSmemBytes = dync;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = kClusterCtas;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      if (ensure_dyn_smem(als_pages_cluster_kernel, dync, smem_setq) != cudaSuccess ||
+          cudaOccupancyMaxActiveClusters(&n, als_pages_cluster_kernel, &cfg) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        n = kNumSMs / 2;   // conservative
+      }
+      max_clusters[slot] = n;
+      if (getenv("RDM_B200_DEBUG")) fprintf(stderr, "rdm_b200: als_pages_cluster_kernel: %d clusters of %d CTAs resident at once\n", n, kClusterCtas);
+    }
+    // per SM the cluster form is ~12 % behind at equal occupancy (the exchange costs 60 instructions per iteration):
+    // measured crossover at ~115 of 142 resident clusters
+    one_cta = 5 * n_items > 4 * (int64_t)max_clusters[slot];
+  }
   for (int k = 0; k < n_scales; ++k) {
     if (scales[k].flags & RDM_ALS_PAGES_CLUSTER) one_cta = group != kGroupWarps;
     if (scales[k].flags & RDM_ALS_PAGES_ONE_CTA) one_cta = true;
   }
   if (!one_cta) {
-    const size_t dync = ((sizeof(PagesClusterShared) + 15) & ~size_t(15)) + (size_t)kClusterWarps * kWarpFloats * sizeof(float);
     static size_t smem_setc[64];
     cudaError_t ec = ensure_dyn_smem(als_pages_cluster_kernel, dync, smem_setc);
     if (ec != cudaSuccess) {
