@@ -543,6 +543,9 @@ __device__ __forceinline__ float row_dot(const float (&D)[12], const float (&v)[
 // Groups of more than 16 images take several rounds of 16 warps: pass 1 accumulates the group record over the
 // rounds (no iterate is kept), pass 2 re-runs the k* selected iterations of every unit (bit-identical
 // arithmetic) and emits them.  On noise-like maps k* <= 1, so pass 2 is a few per cent of pass 1.
+#ifndef RDM_PAGES_CLUSTER_MINB
+#define RDM_PAGES_CLUSTER_MINB 3   // resident CTAs per SM the cluster form is compiled for: 168 registers, no spills in the loop (4: 128 registers, a lone call 81 instead of 66 us; bench throughput equal)
+#endif
 constexpr int kLag = 3;
 constexpr int kRing = 4;
 constexpr int kRedDelay = 2;   // the reducer of iteration j works at the top of its step j + kRedDelay
@@ -1139,7 +1142,7 @@ __global__ void __launch_bounds__(32 * kGroupWarps, 1) als_pages_kernel(const __
 
 // The same work with the 16 warps of a group spread over a cluster of 4 CTAs (ClusterSync).  grid = 4 x (group, page)
 // items; group must be 16.
-__global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(32 * kClusterWarps, 4)
+__global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(32 * kClusterWarps, RDM_PAGES_CLUSTER_MINB)
     als_pages_cluster_kernel(const __grid_constant__ PagesParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   PagesClusterShared& sh = *reinterpret_cast<PagesClusterShared*>(smem_raw);
