@@ -93,6 +93,9 @@ def algorithmic_bytes(scales=SCALES):
     out["als_sparse_kernel"] = sum(Rq[s] + mp[s] for s in pg)
     out["als_dense_kernel"] = sum(raw[s] + 2 * Rq[s] + bins[s] + mp[s] for s in scales if s == 8)
     out["tail_kernel"] = out["decompose"] + out["reconstruct"]
+    # what the sparsify launch has to move through HBM: every raw pair matrix in, the compact page form out (16 floats
+    # per matrix row); the stage's logical outputs Rq and bins never exist in HBM unless a caller asks for them
+    out["sparsify_required"] = sum(raw[s] + (s // 16) ** 2 * 256 * 16 * 4 for s in pg)
     return out
 
 
@@ -546,8 +549,12 @@ def run_fusion(args, kind="fusion"):
     sp = "als_sparsify"
     if sp in kernel_s:
         t_sp = (grouped["kernel_us"][sp] * 1e-6 / grouped["batches_per_call"]) if grouped and sp in grouped["kernel_us"] else kernel_s[sp] / tiles
-        roof["streaming_kernel"] = {"kernel": ring[0].kernel_names().get(sp, sp), "achieved": kernel_b[sp] * BATCH / t_sp / 1e9,
-                                    "frac": kernel_b[sp] * BATCH / t_sp / 1e9 / peak, "seconds_per_batch": t_sp,
+        req = ab["sparsify_required"] * BATCH
+        roof["streaming_kernel"] = {"kernel": ring[0].kernel_names().get(sp, sp), "achieved": req / t_sp / 1e9, "frac": req / t_sp / 1e9 / peak,
+                                    "bytes_per_batch": req, "seconds_per_batch": t_sp,
+                                    "bytes_note": "raw pair matrices in + compact page form out (what the launch must move); the "
+                                                  "stage's contract bytes (SURVEY 8d: + Rq and bins, which never reach HBM here) would give "
+                                                  f"{kernel_b[sp] * BATCH / t_sp / 1e9:.0f} GB/s",
                                     "traffic": traffic.get("als_sparsify_grouped_dram_bytes_per_launch")}
 
     out = {

@@ -50,7 +50,8 @@ def dram_bytes(rows, name):
     hdr, units = rows[0], rows[1]
     ki = hdr.index("Kernel Name")
     mult = {"Mbyte": 1e6, "Kbyte": 1e3, "byte": 1, "Gbyte": 1e9}
-    r = [r for r in rows[2:] if name in r[ki]]
+    names = name if isinstance(name, tuple) else (name,)
+    r = [r for r in rows[2:] if any(n in r[ki] for n in names)]
     if not r:
         return None
     tot = 0.0
@@ -65,7 +66,9 @@ b16 = os.path.join(GO, "prof_r2_batch16.ncu-rep")
 big = os.path.join(GO, "prof_r2_chipfull.ncu-rep")
 if os.path.exists(b16):
     rows = key_metrics(b16, os.path.join(PR, "r2_ncu_full_key_metrics.csv"))
-    for key, name in (("als_sparse", "als_pages_kernel"), ("als_sparsify", "als_sparsify_raw_kernel"), ("als_dense", "als_kernel"), ("fuse_tail", "fuse_tail_kernel")):
+    # a lone batch-16 call takes the cluster form of the page kernel, the 29-batch launch the one-CTA form
+    for key, name in (("als_sparse", ("als_pages_kernel", "als_pages_cluster_kernel")), ("als_sparsify", "als_sparsify_raw_kernel"),
+                      ("als_dense", "als_kernel"), ("fuse_tail", "fuse_tail_kernel")):
         traffic[f"{key}_dram_bytes_per_launch"] = dram_bytes(rows, name)
 if os.path.exists(big):
     rows = key_metrics(big, os.path.join(PR, "r2_chip_full_key_metrics.csv"))
@@ -123,6 +126,7 @@ sass = subprocess.run(["cuobjdump", "-sass", os.path.join(ROOT, "md_rdm_b200", "
 funcs = re.split(r"\n\s*Function : ", sass)
 ex = []
 for name, pats in (("als_sparsify_raw_kernel", r"UBLKCP|SYNCS|MBARRIER"), ("als_pages_kernel", r"BAR\.(ARV|SYNC)"),
+                   ("als_pages_cluster_kernel", r"MAPA|SYNCS|STAS|ST\.ASYNC|UCGABAR|MEMBAR"),
                    ("als_kernelENS", r"UCGABAR|CGABAR|BAR\."), ("conv_head_kernel", r"UCGABAR|MAPA|LD\.E|ST\.E"),
                    ("gt_prepare_kernel", r"UCGABAR|MAPA")):
     for f in funcs:
