@@ -1274,9 +1274,9 @@ int als_sparse_launch(const rdm_als_scale_t* scales, int32_t n_scales, int64_t n
   if (!iterate) return 0;
   // Two forms of the page kernel, same results bit for bit.  One CTA of 16 warps per (batch, page) has the better
   // throughput once the chip is full; a cluster of 4 CTAs of 4 warps spreads a SMALL launch over 4x the SMs (a lone
-  // batch-16 call: 82 vs 131 us) and is as efficient per SM as long as every cluster is resident at once - a second
+  // batch-16 call: 66 vs 131 us) and wins as long as every cluster is resident at once - a second
   // wave of clusters costs a whole extra pass (29 batches per launch: 7.5 vs 4.7 us per batch).  Default: the cluster
-  // form while the clusters fill at most 4/5 of one wave; RDM_ALS_PAGES_ONE_CTA / RDM_ALS_PAGES_CLUSTER force one.
+  // form while all clusters are resident at once; RDM_ALS_PAGES_ONE_CTA / RDM_ALS_PAGES_CLUSTER force one.
   const size_t dync = ((sizeof(PagesClusterShared) + 15) & ~size_t(15)) + (size_t)kClusterWarps * kWarpFloats * sizeof(float);
   bool one_cta = group != kGroupWarps;
   if (!one_cta) {
@@ -1306,9 +1306,9 @@ int als_sparse_launch(const rdm_als_scale_t* scales, int32_t n_scales, int64_t n
       max_clusters[slot] = n;
       if (getenv("RDM_B200_DEBUG")) fprintf(stderr, "rdm_b200: als_pages_cluster_kernel: %d clusters of %d CTAs resident at once\n", n, kClusterCtas);
     }
-    // per SM the cluster form is ~12 % behind at equal occupancy (the exchange costs 60 instructions per iteration):
-    // measured crossover at ~115 of 142 resident clusters
-    one_cta = 5 * n_items > 4 * (int64_t)max_clusters[slot];
+    // measured, us per batch (one CTA / cluster): 40 items 16.8 / 11.0, 70: 9.6 / 6.3, 85: 8.0 / 6.5, 100: 6.8 / 5.6
+    // (104 clusters resident), 145: 4.7 / 7.5
+    one_cta = n_items > max_clusters[slot];
   }
   for (int k = 0; k < n_scales; ++k) {
     if (scales[k].flags & RDM_ALS_PAGES_CLUSTER) one_cta = group != kGroupWarps;

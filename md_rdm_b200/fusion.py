@@ -159,7 +159,8 @@ class FusionPlan:
     def kernel_names() -> Dict[str, str]:
         return {"als_sparsify": "als_sparsify_raw_kernel / als_sparsify_map_kernel (structure check + Lloyd: reads every raw pair matrix once)",
                 "als_sparse": "als_pages_kernel (100 ALS iterations per page on the compact form, one CTA per (batch, page), one warp per "
-                              "image, batch-wide arg-min + normalise + re-tile inside)",
+                              "image, batch-wide arg-min + normalise + re-tile inside; small launches take its cluster form "
+                              "als_pages_cluster_kernel: 4 CTAs of 4 warps per (batch, page))",
                 "als_dense": "als_kernel (dense ALS of the 8x8 maps, one cluster per batch, arg-min inside; fallback for pages without pair structure)",
                 "fuse_tail": "fuse_tail_kernel (decompose + combine + recombine)"}
 
