@@ -1142,7 +1142,11 @@ __global__ void __launch_bounds__(32 * kGroupWarps, 1) als_pages_kernel(const __
 
 // The same work with the 16 warps of a group spread over a cluster of 4 CTAs (ClusterSync).  grid = 4 x (group, page)
 // items; group must be 16.
+#ifdef RDM_PAGES_CLUSTER_MAXNREG   // A/B builds: leave part of the register file to co-resident CTAs of the sparsify kernel
+__global__ void __cluster_dims__(kClusterCtas, 1, 1) __maxnreg__(RDM_PAGES_CLUSTER_MAXNREG)
+#else
 __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(32 * kClusterWarps, RDM_PAGES_CLUSTER_MINB)
+#endif
     als_pages_cluster_kernel(const __grid_constant__ PagesParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   PagesClusterShared& sh = *reinterpret_cast<PagesClusterShared*>(smem_raw);
