@@ -999,8 +999,22 @@ def test_training_step_config3_batch16_fast_path(dev, books):
     assert _rel_err(ts.weights.grad.cpu(), g_ref) < 1e-4
     assert torch.allclose(ts.logits.grad.cpu(), lg.grad, rtol=1e-4, atol=1e-9)
     # a second step on the same inputs reproduces the first bit for bit (no state leaks between steps)
+    g_first = ts.weights.grad.clone()
     out2 = ts.step()
     assert torch.equal(out2["loss"], out["loss"])
+    # the CUDA graph of the whole step (two parallel branches: ground truth | network side; fork/join of the dense
+    # ALS) replays to the same bits, twice
+    ts.capture()
+    for _ in range(2):
+        out3 = ts.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out3["loss"], out["loss"]) and torch.equal(ts.weights.grad, g_first)
+    # the stand-alone ground-truth ops + per-scale torch MSE instead of rdm::gt_prepare + rdm::component_loss
+    ts2 = TrainingStep(B, scales, device=dev, fused_gt=False)
+    ts2.load(rel, y_raw, logits, w_flat)
+    out4 = ts2.step()
+    assert abs(out4["loss"].item() - out["loss"].item()) <= 1e-12 * abs(out["loss"].item())
+    assert torch.equal(ts2.weights.grad, g_first)
 
 
 def test_fuse_maps_autograd_and_cache(dev, books):
