@@ -830,6 +830,38 @@ def test_codebook_fallbacks(dev, books):
         assert int(k.item()) == k_ref and _rel_err(m.cpu(), ref_map) < REL_MAP
 
 
+def test_sparsify_threshold_search_adversarial(dev, books):
+    """Pair-structured matrices whose fill and window values sit ON the Lloyd thresholds, one f64 ulp either side, on
+    their f32 roundings and one ulp either side of those (plus zero and values beyond the f32 range) must give the
+    reference's bins bit for bit through the sparsify kernel - with the shipped table, with two thresholds closer than
+    an f32 ulp and with an unsorted table (the literal 40 compares).  (Guards any cheaper search: a two-stage f32-then-
+    f64 search was measured and dropped - same speed - but this is the test it has to pass.)"""
+    from md_rdm_b200 import _cabi
+    g = torch.Generator().manual_seed(4242)
+    q, lv = books[16]
+    mask = fr.window_mask(8, 16)                                   # (256, 64) bool: window columns of every row
+    inf = torch.tensor(float("inf"), dtype=torch.float64)
+    qf = q.float().double()
+    cands = torch.cat([q, torch.nextafter(q, inf), torch.nextafter(q, -inf), qf, torch.nextafter(qf, inf), torch.nextafter(qf, -inf),
+                       torch.exp(0.5 * torch.randn(64, generator=g, dtype=torch.float64)),
+                       torch.tensor([1e-300, 1e300, 0.0, 3.5e38, 3.4028234663852886e38], dtype=torch.float64)])
+    B = 4
+    x = torch.empty(B, 256, 64, dtype=torch.float64)
+    for b in range(B):
+        fill = cands[torch.randint(0, cands.numel(), (256,), generator=g)]
+        x[b] = fill[:, None].expand(256, 64)
+        x[b][mask] = cands[torch.randint(0, cands.numel(), (int(mask.sum()),), generator=g)]
+    close = q.clone()
+    close[21] = close[20] * (1 + 1e-9)                             # equal after rounding to f32
+    close, _ = torch.sort(close)
+    assert close.float()[20] == close.float()[21] and close[20] < close[21]
+    for thr in (q, close, q[torch.randperm(40, generator=g)]):
+        rv, rb = fr.lloyd(x, thr, lv)
+        _, _, _, k, bins, vals = R.als_rank1(x.to(dev), _cabi.SRC_RAW_F64, 256, 16, 100, B, thr.to(dev), lv.to(dev), True, True)
+        assert torch.equal(bins.view(B, 256, 64).cpu(), rb)
+        assert torch.equal(vals.view(B, 256, 64).cpu(), rv.float())
+
+
 # ============================================================================ repeat-run stress (race hunting; compute-sanitizer is closed on the pool)
 def test_stress_pages_argmin_protocol_repeatable(dev, books):
     """The grouped page kernel takes the batch-wide arg-min with a lagged verdict ring between 16 warps (named
