@@ -47,6 +47,7 @@ UNIT = "maps/s"
 BATCH = 16
 SCALES = (8, 16, 32)
 PLAN_FLAGS = int(os.environ.get("RDM_BENCH_PLAN_FLAGS", "0"))   # A/B measurements: rdm_als_scale_t.flags for every plan of the bench
+PLAN_OVERLAP = bool(int(os.environ.get("RDM_BENCH_OVERLAP", "0")))   # A/B: FusionPlan(overlap=True), the dense ALS beside the page ALS
 
 
 def shared_config(kind: str = "fusion"):
@@ -258,7 +259,8 @@ def build_ring(dev, rank, n_plans, source, call_images, want_bins=True, compact=
     ring = []
     for b in range(n_plans):
         x_d1, rel, weights = synthetic_batch(call_images, SCALES, seed=batch_seed(rank, b))
-        plan = FusionPlan(call_images, SCALES, source, device=dev, want_bins=want_bins, compact_result=compact, flags=PLAN_FLAGS)
+        plan = FusionPlan(call_images, SCALES, source, device=dev, want_bins=want_bins, compact_result=compact, flags=PLAN_FLAGS,
+                          overlap=PLAN_OVERLAP)
         rel_d = [r.to(dev) for r in rel]
         if source == "raw":   # raw pair matrices derived from the maps with the pair-build kernels (not timed)
             srcs = [R.pair_v1(r) if r.shape[2] == 8 else R.pair_id(r)[0] for r in rel_d]

@@ -1314,13 +1314,9 @@ extern "C" int rdm_fuse_tail(const int64_t* x_d1, const float* const* rel, const
   // bands: a cluster of `bands` CTAs per image shortens a SMALL launch (the f64 div + log stage is split over the
   // cluster), but every band redoes the pyramids and a cluster has to be placed as a whole: with a reference batch of
   // 16 per call and 32 calls in flight, 4 bands (64 CTAs per call) cost 12 % of the path's throughput against 1 band
-  // (measured: 1.53 -> 1.72 M maps/s; the lone launch 11 -> 18 us).  So: >= 16 CTAs in total, no more.
+  // (measured with a temporary override of this count: 1.53 -> 1.72 M maps/s; the lone launch 11 -> 18 us).  So: >= 16 CTAs in total, no more.
   int bands = 1;   // a band must hold whole constant blocks: rows per band >= 2^(7-kmax)
   while (bands < 8 && bands < (1 << P.kmax) && n_images * bands < 16) bands <<= 1;   // one thread-block cluster per image
-  if (const char* ov = getenv("RDM_TAIL_BANDS")) {   // A/B measurements only
-    const int b = atoi(ov);
-    if ((b == 1 || b == 2 || b == 4 || b == 8) && b <= (1 << P.kmax)) bands = b;
-  }
   P.bands = bands;
   RDM_REQUIRE(n_images * bands < (1ll << 31), "rdm_fuse_tail: too many images");
   const size_t smem = (size_t)P.dtotal * sizeof(double) + ((size_t)off_level(P.kmax + 1) + (size_t)ltotal) * sizeof(float);
