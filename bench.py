@@ -544,6 +544,11 @@ def run_fusion(args, kind="fusion"):
                      "launch_seconds": t_dom, "launch": f"one call ({call_images} images) per launch, timed alone",
                      "traffic": traffic.get(f"{dom}_dram_bytes_per_launch")})
     roof["frac"] = roof["achieved"] / peak
+    if dom == "als_sparse":
+        # why the dominant kernel sits far below the HBM line: it iterates 100 times on 16 KB per page held in registers
+        # (38 MB of DRAM traffic per 464-image launch); what it saturates is the SM, not the memory system
+        roof["limiter"] = ("instruction issue + shared-memory pipe, not HBM: ncu, chip full - issue slots 65 %, shared/shuffle pipe 61 %, "
+                           "FMA pipe 44 %, 16 warps per SM (register file), DRAM throughput 3 % (profiles/r2_chip_full_key_metrics.csv)")
     roof["single_call_launch"] = {"achieved": kernel_b[dom] * call_images / kernel_s[dom] / 1e9,
                                   "frac": kernel_b[dom] * call_images / kernel_s[dom] / 1e9 / peak, "launch_seconds": kernel_s[dom]}
     roof["path_at_value"] = {"achieved": path_gbs, "frac": path_gbs / peak,
