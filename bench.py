@@ -426,7 +426,7 @@ def run_fusion(args, kind="fusion"):
     ring_calls = max(args.ring // tiles, S)
     n_plans = max(ring_calls // S, 1) * S       # whole plans per lane
     source = "raw"
-    ring = build_ring(dev, rank, n_plans, source, call_images)
+    ring = build_ring(dev, rank, n_plans, source, call_images, want_bins=not os.environ.get("RDM_BENCH_NO_BINS"))
     launches_per_call = ring[0].launches_per_run
     ring_in_bytes = sum(p.h2d_bytes() for p in ring)
     K, W = args.steps, args.warmup
