@@ -105,7 +105,12 @@ enum {
   RDM_ALS_PAGES_ONE_CTA = 16, /* page ALS: the 16 images of a batch in ONE CTA per page (best when the chip is full) */
   RDM_ALS_PAGES_CLUSTER = 32, /* page ALS: a cluster of 4 CTAs per (batch, page) (lowest latency of a small launch);
                                  neither bit = chosen from the launch size; same results bit for bit either way */
-  RDM_ALS_FLAGS_ALL = 63
+  RDM_ALS_SKIP_UNUSED_PAGES = 64, /* opt-in: leave out the pages CP:218-238 (`reconstruct`, as written) never copies into
+                                     the map - pages >= side/16 of every image; the reference computes and drops them.  The
+                                     map and everything after it are unchanged bit for bit; pages_out / record_out /
+                                     kstar_out / bins_out entries of those pages are not written.  Ignored together with
+                                     RDM_ALS_CORRECT_TILING (then every page is used). */
+  RDM_ALS_FLAGS_ALL = 127
 };
 /* rdm_als_fused_phases phase_mask bits: the launches of rdm_als_fused, selectable one by one (profiling) */
 enum {

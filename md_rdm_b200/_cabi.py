@@ -18,7 +18,7 @@ ABI_VERSION = 2
 # rdm_als_scale_t.src_kind
 SRC_RAW_F64, SRC_RAW_F32, SRC_VAL_F32, SRC_VAL_F64, SRC_MAP_F32 = range(5)
 # rdm_als_scale_t.flags and rdm_als_fused_phases masks (include/rdm_b200.h)
-ALS_DENSE_ONLY, ALS_TRUE_TRANSPOSE, ALS_TRUE_GM, ALS_CORRECT_TILING, ALS_PAGES_ONE_CTA, ALS_PAGES_CLUSTER = 1, 2, 4, 8, 16, 32
+ALS_DENSE_ONLY, ALS_TRUE_TRANSPOSE, ALS_TRUE_GM, ALS_CORRECT_TILING, ALS_PAGES_ONE_CTA, ALS_PAGES_CLUSTER, ALS_SKIP_UNUSED_PAGES = 1, 2, 4, 8, 16, 32, 64
 PHASE_SPARSIFY, PHASE_PAGES, PHASE_DENSE, PHASE_ALL = 1, 2, 4, 7
 # rdm_quick_gm / rdm_gm_normalize dtype
 DT_F32, DT_F64, DT_I64 = range(3)

@@ -744,8 +744,10 @@ __global__ void __launch_bounds__(kAlsThreads, 2) als_kernel(const __grid_consta
   const int64_t stride256 = als_ws_stride(256, sc.limit);
   // does the compact kernel own this (group, page) item?  (all of its units carry the four band flags)
   auto item_is_compact = [&](int64_t item) {
-    if (sc.dense_only) return false;
     const int64_t g = item / sc.pages, pg = item - g * sc.pages;
+    // RDM_ALS_SKIP_UNUSED_PAGES: pages CP:218-238 never copies into the map are nobody's work
+    if ((sc.flags & RDM_ALS_SKIP_UNUSED_PAGES) && !(sc.flags & RDM_ALS_CORRECT_TILING) && pg >= (sc.side >> 4)) return true;
+    if (sc.dense_only) return false;
     bool all = true;
     for (int b = 0; b < group; ++b) {
       const float4 fl = *reinterpret_cast<const float4*>(sc.ws + ((g * group + b) * sc.pages + pg) * stride256 + kCompactFloats);

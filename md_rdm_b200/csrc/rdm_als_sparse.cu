@@ -55,6 +55,7 @@ struct SparseScaleDev {
   float* ws;
   int32_t kind, pages, side, limit;
   int32_t unit_begin;   // first unit of this scale in the kernel's unit numbering
+  int32_t live;         // pages of an image the launch works on (pg < live): `pages`, or side/16 under RDM_ALS_SKIP_UNUSED_PAGES
 };
 
 struct SparseParams {
@@ -173,7 +174,8 @@ __global__ void __launch_bounds__(kBandRows) als_sparsify_raw_kernel(const __gri
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gunit = blockIdx.x >> 2, band = blockIdx.x & 3;
   const SparseScaleDev& sc = find_scale(P, gunit);
-  const int64_t unit = gunit - sc.unit_begin;
+  const int64_t live_unit = gunit - sc.unit_begin;                 // (image, live page)
+  const int64_t unit = (live_unit / sc.live) * sc.pages + live_unit % sc.live;   // (image, page) as laid out in memory
   const bool quant = sc.kind == RDM_SRC_RAW_F64;
   if (tid == 0) {
     mbar_init(sm_addr(&full_bar), 1);
@@ -382,10 +384,11 @@ __global__ void __launch_bounds__(256) als_sparsify_map_kernel(const __grid_cons
   const int tid = threadIdx.x;
   const int gunit = blockIdx.x;
   const SparseScaleDev& sc = find_scale(P, gunit);
-  const int64_t unit = gunit - sc.unit_begin;
+  const int64_t live_unit = gunit - sc.unit_begin;
   const int side = sc.side;
-  const int64_t img = unit / sc.pages;
-  const int pg = (int)(unit - img * sc.pages);
+  const int64_t img = live_unit / sc.live;
+  const int pg = (int)(live_unit - img * sc.live);
+  const int64_t unit = img * sc.pages + pg;
   const float* map = reinterpret_cast<const float*>(sc.src) + img * (int64_t)side * side;
   load_book(sc, thr_d, lvl_f, &sorted, tid, 256);   // ends with __syncthreads
   compact_page_from_map(sc, unit, map, side, pg, thr_d, lvl_f, sorted, inv_d, tid);
@@ -492,7 +495,7 @@ __global__ void __launch_bounds__(256) conv_head_kernel(const float* __restrict_
   if (!build_pages) return;
   // ---- compact page form of pages rank, rank + 8, ...
   load_book(sc, sm.thr_d, sm.lvl_f, &sm.sorted, tid, 256);
-  for (int pg = rank; pg < sc.pages; pg += kConvCluster) {
+  for (int pg = rank; pg < sc.live; pg += kConvCluster) {
     compact_page_from_map(sc, img * sc.pages + pg, sm.map, side, pg, sm.thr_d, sm.lvl_f, sm.sorted, sm.inv_d, tid);
     __syncthreads();   // inv_d is reused by the next page
   }
@@ -563,6 +566,7 @@ struct PagesScaleDev {
   int32_t pages, side, limit;
   int32_t cta_begin;   // first (group, page) item of this scale
   int32_t flags;       // RDM_ALS_TRUE_GM | RDM_ALS_CORRECT_TILING
+  int32_t live;        // pages of an image the launch works on (pg < live)
 };
 struct PagesParams {
   PagesScaleDev s[kMaxSparseScales];
@@ -1051,7 +1055,7 @@ __global__ void __launch_bounds__(32 * kGroupWarps, 1) als_pages_kernel(const __
     if ((int)blockIdx.x >= P.s[k].cta_begin) si = k;
   const PagesScaleDev& sc = P.s[si];
   const int item = (int)blockIdx.x - sc.cta_begin;
-  const int g = item / sc.pages, pg = item - g * sc.pages;
+  const int g = item / sc.live, pg = item - g * sc.live;
   const int group = P.group, limit = sc.limit;
   const int W0 = blockDim.x >> 5;                        // warps per round
   const int rounds = (group + W0 - 1) / W0;
@@ -1164,7 +1168,7 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(32 * kClu
     if (item_all >= P.s[k].cta_begin) si = k;
   const PagesScaleDev& sc = P.s[si];
   const int item = item_all - sc.cta_begin;
-  const int g = item / sc.pages, pg = item - g * sc.pages;
+  const int g = item / sc.live, pg = item - g * sc.live;
   const int limit = sc.limit;
   const int gw = (int)crank * kClusterWarps + warp;                 // image of the group this warp iterates
   const int64_t stride = als_ws_stride(256, limit);
@@ -1238,7 +1242,11 @@ int als_sparse_launch(const rdm_als_scale_t* scales, int32_t n_scales, int64_t n
     d.pages = h.pages;
     d.side = h.side;
     d.limit = h.limit;
-    const int64_t units = n_images * h.pages;
+    // CP:218-238 as written copies only pages 0 .. side/16 - 1 into the map; the others are computed by the reference and
+    // dropped.  RDM_ALS_SKIP_UNUSED_PAGES leaves them out (their pages_out / record / kstar / bins entries stay unwritten).
+    const bool skip = (h.flags & RDM_ALS_SKIP_UNUSED_PAGES) && !(h.flags & RDM_ALS_CORRECT_TILING);
+    d.live = skip ? h.side / 16 : h.pages;
+    const int64_t units = n_images * d.live;
     SparseParams& part = is_map ? map : raw;
     int64_t& n_part = is_map ? n_map : n_raw;
     d.unit_begin = (int32_t)n_part;
@@ -1255,7 +1263,8 @@ int als_sparse_launch(const rdm_als_scale_t* scales, int32_t n_scales, int64_t n
     a.limit = h.limit;
     a.cta_begin = (int32_t)n_items;
     a.flags = h.flags;
-    n_items += n_groups * h.pages;
+    a.live = d.live;
+    n_items += n_groups * d.live;
   }
   if (n_items == 0) return 0;
   RDM_REQUIRE(n_raw + n_map < (1ll << 28), "rdm_als_fused: too many work units");
@@ -1370,6 +1379,7 @@ extern "C" int rdm_conv_head_f32(const float* feat, const float* weight, const f
     d.side = side;
     d.limit = h.limit;
     d.unit_begin = 0;
+    d.live = ((h.flags & RDM_ALS_SKIP_UNUSED_PAGES) && !(h.flags & RDM_ALS_CORRECT_TILING)) ? side / 16 : h.pages;
     build = 1;
   }
   if (n_images == 0) return 0;

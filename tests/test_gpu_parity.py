@@ -956,6 +956,45 @@ def test_pages_kernel_forms_agree(dev, books):
                 assert same_bits(u, v), (G, name)
 
 
+def test_skip_unused_pages_flag_changes_nothing_downstream(dev, books):
+    """CP:218-238 as written copies only pages 0 .. side/16 - 1 of an image into the re-tiled map; the reference computes
+    the other pages (2 of 4 at 32x32, 12 of 16 at 64x64) and drops them.  The opt-in RDM_ALS_SKIP_UNUSED_PAGES leaves
+    them out: the filled maps, y_hat and the final depth must not move by a bit, the live pages keep their k*, record and
+    page vectors, for both sources and both forms of the page kernel; and with RDM_ALS_CORRECT_TILING (every page is
+    used) the flag is ignored."""
+    from md_rdm_b200 import _cabi
+    from md_rdm_b200.fusion import FusionPlan
+    scales = (8, 16, 32, 64)
+    for G, source in ((1, "map"), (1, "raw"), (3, "raw")):
+        N = 16 * G
+        x_d1, rel, weights = fr.synthetic_batch(N, scales, seed=5150 + G)
+        w = torch.cat([t.reshape(-1) for t in weights]).to(dev)
+        srcs = rel if source == "map" else [R.pair_v1(r.to(dev)) if r.shape[2] == 8 else R.pair_id(r.to(dev))[0] for r in rel]
+        for extra in (0, _cabi.ALS_PAGES_ONE_CTA, _cabi.ALS_CORRECT_TILING):
+            outs = []
+            for skip in (0, _cabi.ALS_SKIP_UNUSED_PAGES):
+                plan = FusionPlan(N, scales, source, group=16, device=dev, flags=extra | skip)
+                plan.load_inputs(x_d1.to(dev), [t.to(dev) for t in srcs], w)
+                for s_ in scales:
+                    plan.kstar[s_].fill_(-7)
+                out = plan.run()
+                torch.cuda.synchronize()
+                outs.append((out.clone(), plan.yhat.clone(), {s_: plan.rel[s_].clone() for s_ in scales},
+                             {s_: plan.kstar[s_].clone() for s_ in scales}, {s_: plan.record[s_].clone() for s_ in scales},
+                             {s_: plan.pages[s_].clone() for s_ in scales}))
+            full, skipped = outs
+            assert _eq_nan(full[0], skipped[0]) and torch.equal(full[1].view(torch.int32), skipped[1].view(torch.int32)), (G, source, extra)
+            for s_ in scales:
+                assert torch.equal(full[2][s_], skipped[2][s_]), (G, source, extra, s_)
+                ratio = max(s_ // 16, 1)
+                live = 1 if s_ == 8 else ((s_ // 16) ** 2 if (extra & _cabi.ALS_CORRECT_TILING) else ratio)
+                assert torch.equal(full[3][s_][:, :live], skipped[3][s_][:, :live])
+                assert torch.equal(full[4][s_][:, :live], skipped[4][s_][:, :live])
+                assert torch.equal(full[5][s_][:, :live], skipped[5][s_][:, :live])
+                if live < full[3][s_].shape[1]:      # the skipped pages were really skipped
+                    assert bool((skipped[3][s_][:, live:] == -7).all())
+
+
 # ============================================================================ the literal call sequence of the reference
 def test_literal_call_sequence_rn_383_396(dev, books):
     """RN:383-396 written against the drop-in NAMES exactly as the reference calls them - cp.resize,
