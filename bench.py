@@ -474,6 +474,25 @@ def run_fusion(args, kind="fusion"):
         if kind == "fusion" and not args.no_grouped:
             grouped = grouped_call_table(dev, rank, ab, args)
 
+        # beside the default: the same steps with RDM_ALS_SKIP_UNUSED_PAGES (opt-in; the pages the reference's reconstruct
+        # never copies into the map are left out - final maps bit-identical, tests/test_gpu_parity.py).  Never the headline.
+        skip_ms = None
+        if kind == "fusion" and not args.no_grouped:
+            for p_ in ring:
+                for i in range(len(p_.scales)):
+                    p_._descs[i].flags |= _cabi.ALS_SKIP_UNUSED_PAGES
+            main_lanes = lanes
+            lanes = [capture_lane(ring[j::S]) for j in range(S)]
+            timed_region(lambda: run_steps(W))
+            dist_barrier()
+            s_dev, s_wall = timed_region(lambda: run_steps(K))
+            dist_barrier()
+            skip_ms = dist_max(max(s_dev, s_wall), dev)
+            lanes = main_lanes
+            for p_ in ring:
+                for i in range(len(p_.scales)):
+                    p_._descs[i].flags &= ~_cabi.ALS_SKIP_UNUSED_PAGES
+
         # end-to-end through the public host API: pinned host maps -> pinned host log-depth.  One call =
         # FusionPlan.submit_pinned(): a graph of [H2D copy of the packed inputs, pair build + the path's kernels,
         # D2H copy of the log-depth maps], calls issued round-robin on `e2e_lanes` streams (asynchronous API),
@@ -588,6 +607,14 @@ def run_fusion(args, kind="fusion"):
     }
     if grouped:
         out["grouped_call"] = {k: grouped[k] for k in ("value", "us_per_batch", "batches_per_call", "kernel_us")}
+    if skip_ms:
+        live = sum(max(s_ // 16, 1) for s_ in SCALES if s_ > 8)
+        allp = sum((s_ // 16) ** 2 for s_ in SCALES if s_ > 8)
+        out["skip_unused_pages"] = {"value": total_images / (skip_ms * 1e-3), "page_items_per_batch": [live, allp],
+                                    "note": "opt-in FusionPlan(flags=ALS_SKIP_UNUSED_PAGES): network/computations.py:218-238 copies only pages "
+                                            "0..side/16-1 of an image into the re-tiled map, the reference computes the others and drops them; "
+                                            "leaving them out changes no bit of the maps or the depth.  Reported beside the default, which does "
+                                            "all the work the reference does."}
     if rank == 0 and world == 1 and not args.no_cpu_baseline and kind == "fusion":
         lit_rate, vec_rate, dt = cpu_baseline_port(args.cpu_calls)
         out["cpu_baseline"] = {"value": lit_rate, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
