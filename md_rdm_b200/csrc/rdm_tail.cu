@@ -840,8 +840,11 @@ constexpr int kGtSide = 128;
 constexpr int kGtBand = kGtSide / kBandCluster;        // 16 rows
 constexpr int kGtStageRows = kGtBand + 2;
 
+#ifndef RDM_GT_THREADS
+#define RDM_GT_THREADS 256   // every phase is a latency chain (f64 div ~500, f64 log ~1200 cycles): 256 threads 44.5k cycles per CTA, 512: 41.5k, 1024: 35.3k - but the training step, where this kernel runs beside the fusion path, is faster with 256 (0.191 vs 0.197 ms)
+#endif
 template <typename TIn>
-__global__ void __launch_bounds__(256) gt_prepare_kernel(const TIn* __restrict__ y_raw, int ih, int iw, int64_t n_images, double sid_K,
+__global__ void __launch_bounds__(RDM_GT_THREADS) gt_prepare_kernel(const TIn* __restrict__ y_raw, int ih, int iw, int64_t n_images, double sid_K,
                                                          double sid_alpha, double sid_log_ratio, double* __restrict__ y_out,
                                                          double* __restrict__ pyr_out, int32_t* __restrict__ ord_out) {
   extern __shared__ __align__(16) unsigned char band_raw[];
@@ -852,6 +855,12 @@ __global__ void __launch_bounds__(256) gt_prepare_kernel(const TIn* __restrict__
   const int tid = threadIdx.x;
   const TIn* src = y_raw + img * (int64_t)ih * iw;
   const int row_lo = kGtBand * rank - 1;                       // global row of staged row 0
+#ifdef RDM_GT_TIMING
+  long long tt[10]; int ti = 0; tt[ti++] = clock64();
+#define GT_MARK() do { __syncthreads(); tt[ti++] = clock64(); } while (0)
+#else
+#define GT_MARK() do {} while (0)
+#endif
   // ---- 1. resize (torch bicubic, align_corners=False, A=-0.75, clamped taps, horizontal first) + mask
   {
     const double sy = (double)ih / (double)kGtSide, sx = (double)iw / (double)kGtSide;
@@ -885,6 +894,7 @@ __global__ void __launch_bounds__(256) gt_prepare_kernel(const TIn* __restrict__
     }
   }
   __syncthreads();
+  GT_MARK();
   // ---- 2. row `rank` of cp.resize(y, 8) (scale 16: taps 16 rank + 6 .. + 9), utils.depth2label_sid
   if (tid < 8) {
     const double s8 = (double)kGtSide / 8.0;
@@ -913,6 +923,7 @@ __global__ void __launch_bounds__(256) gt_prepare_kernel(const TIn* __restrict__
     ord_out[img * 64 + rank * 8 + tid] = lab;
     *cluster.map_shared_rank(&sm.labels[rank * 8 + tid], 0) = lab;
   }
+  GT_MARK();
   // ---- 3. geometric mean over the whole map (MOD:145-149, rc = 128: the true geometric mean) as exp(mean log)
   {
     double a0 = 0.0;
@@ -920,14 +931,18 @@ __global__ void __launch_bounds__(256) gt_prepare_kernel(const TIn* __restrict__
     const double mine = block_sum<double>(a0, sm.scratch);
     if (tid == 0) sm.part = mine;
   }
+  GT_MARK();
   cluster.sync();
+  GT_MARK();
   double gm = 0.0;
   for (int r = 0; r < kBandCluster; ++r) gm += *cluster.map_shared_rank(&sm.part, r);   // rank order: deterministic
   gm = exp(gm * (1.0 / ((double)kGtSide * (double)kGtSide)));
   for (int i = tid; i < kGtStageRows * kGtSide; i += blockDim.x) sm.Y[i] = sm.Y[i] / gm;
   __syncthreads();
+  GT_MARK();
   // ---- 4. F_7 band, D_6 -> CTA 0, levels 6..1 (D_0 of the ground truth itself is not a target: MOD:127 replaces it)
   if (!band_decompose(sm, cluster, rank, kGtSide, 7, 1, pyr_out, n_images, img)) return;
+  GT_MARK();
   // ---- 5. ordinal D_0: normalize(labels) in f32 like torch (int -> pow(., 1/64) f32 product, int / gm in f32), then the
   // 8x8 map decomposed in f64 (MOD:126)
   {
@@ -940,6 +955,14 @@ __global__ void __launch_bounds__(256) gt_prepare_kernel(const TIn* __restrict__
     __syncthreads();
     if (tid == 0) pyr_out[img] = sm.pyr[0];
   }
+#ifdef RDM_GT_TIMING
+  GT_MARK();
+  if (tid == 0 && blockIdx.x == 0) {
+    printf("gt_prepare CTA 0:");
+    for (int i = 1; i < ti; ++i) printf(" +%lld", tt[i] - tt[i - 1]);
+    printf(" = %lld cycles (resize+mask | labels | logs+blocksum | cluster.sync | gm+divide | band_decompose incl. levels 6..1 | ordinal D0)\n", tt[ti - 1] - tt[0]);
+  }
+#endif
 }
 
 static int grid_cap(int64_t items, int per_block) {
@@ -1366,7 +1389,7 @@ extern "C" int rdm_gt_prepare(const void* y_raw, int32_t in_is_f64, int64_t n_im
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(n_images * kBandCluster));
-  cfg.blockDim = dim3(256);
+  cfg.blockDim = dim3(RDM_GT_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = (cudaStream_t)stream;
   cudaLaunchAttribute attr[1];
