@@ -38,6 +38,23 @@ def test_abi_version_and_sizes(lib):
     assert ctypes.sizeof(_cabi.AlsScale) == 8 + 6 * 4 + 9 * 8
 
 
+def test_binding_constants_match_the_header():
+    """The enum values the ctypes host uses are the header's (flags, phase masks, source kinds)."""
+    text = open(os.path.join(ROOT, "include", "rdm_b200.h")).read()
+    enums = {k: int(v) for k, v in re.findall(r"\b(RDM_[A-Z0-9_]+)\s*=\s*(\d+)", text)}
+    for name in ("DENSE_ONLY", "TRUE_TRANSPOSE", "TRUE_GM", "CORRECT_TILING", "PAGES_ONE_CTA", "PAGES_CLUSTER", "SKIP_UNUSED_PAGES"):
+        assert enums["RDM_ALS_" + name] == getattr(_cabi, "ALS_" + name), name
+    every = 0
+    for k, v in enums.items():
+        if k.startswith("RDM_ALS_") and not k.startswith("RDM_ALS_PHASE_") and k != "RDM_ALS_FLAGS_ALL":
+            every |= v
+    assert enums["RDM_ALS_FLAGS_ALL"] == every
+    for name in ("SPARSIFY", "PAGES", "DENSE", "ALL"):
+        assert enums["RDM_ALS_PHASE_" + name] == getattr(_cabi, "PHASE_" + name), name
+    for name in ("RAW_F64", "RAW_F32", "VAL_F32", "VAL_F64", "MAP_F32"):
+        assert enums["RDM_SRC_" + name] == getattr(_cabi, "SRC_" + name), name
+
+
 def test_argument_errors_do_not_launch(lib):
     null = ctypes.c_void_p(0)
     rc = lib.rdm_pair_v1_f32(null, 4, null, null)
@@ -59,7 +76,7 @@ def test_argument_errors_do_not_launch(lib):
     sc.ws = 16
     rc = lib.rdm_als_fused_phases(sc, 1, 4, 4, 8, null)
     assert rc < 0 and b"phase_mask" in lib.rdm_last_error()
-    sc.flags = 64
+    sc.flags = 128
     rc = lib.rdm_als_fused(sc, 1, 4, 4, null)
     assert rc < 0 and b"unknown flag bits" in lib.rdm_last_error()
     sc.flags = 0
