@@ -819,7 +819,7 @@ __global__ void __launch_bounds__(256) decompose_cluster_kernel(const TIn* __res
     const int rr = i / side, c = i - rr * side;
     sm.Y[i] = (double)src[min(max(row_lo + rr, 0), side - 1) * side + c];
   }
-  __syncthreads();
+  cluster.sync();   // the CTA barrier for Y, and: every CTA of the cluster is running before band_decompose writes into CTA 0's shared memory
   if (band_decompose(sm, cluster, rank, side, n, relative ? 0 : 1, out, n_images, img) && !relative && threadIdx.x == 0) out[img] = sm.pyr[0];
 }
 
@@ -896,6 +896,7 @@ __global__ void __launch_bounds__(RDM_GT_THREADS) gt_prepare_kernel(const TIn* _
   __syncthreads();
   GT_MARK();
   // ---- 2. row `rank` of cp.resize(y, 8) (scale 16: taps 16 rank + 6 .. + 9), utils.depth2label_sid
+  int my_label = 0;
   if (tid < 8) {
     const double s8 = (double)kGtSide / 8.0;
     const double fy = s8 * ((double)rank + 0.5) - 0.5, fx = s8 * ((double)tid + 0.5) - 0.5;
@@ -921,7 +922,7 @@ __global__ void __launch_bounds__(RDM_GT_THREADS) gt_prepare_kernel(const TIn* _
     const double label = __ddiv_rn(__dmul_rn(sid_K, log(__ddiv_rn(acc, sid_alpha))), sid_log_ratio);
     const int lab = __double2int_rz(fmax(label, 0.0));         // a NaN label (negative depth) becomes 0 like torch's CUDA cast
     ord_out[img * 64 + rank * 8 + tid] = lab;
-    *cluster.map_shared_rank(&sm.labels[rank * 8 + tid], 0) = lab;
+    my_label = lab;
   }
   GT_MARK();
   // ---- 3. geometric mean over the whole map (MOD:145-149, rc = 128: the true geometric mean) as exp(mean log)
@@ -934,6 +935,9 @@ __global__ void __launch_bounds__(RDM_GT_THREADS) gt_prepare_kernel(const TIn* _
   GT_MARK();
   cluster.sync();
   GT_MARK();
+  // every CTA of the cluster is running now: remote shared memory may be written (CTA 0 reads the labels after
+  // band_decompose's cluster barrier)
+  if (tid < 8) *cluster.map_shared_rank(&sm.labels[rank * 8 + tid], 0) = my_label;
   double gm = 0.0;
   for (int r = 0; r < kBandCluster; ++r) gm += *cluster.map_shared_rank(&sm.part, r);   // rank order: deterministic
   gm = exp(gm * (1.0 / ((double)kGtSide * (double)kGtSide)));
