@@ -87,21 +87,26 @@ class TrainingStep:
             self._gt_stream = torch.cuda.Stream(self.device)
         self._gt_stream.wait_stream(cur)
         with torch.cuda.stream(self._gt_stream):
+            # the second branch: everything that does not wait for the ALS - ground truth, the DORN head (RN:313-345) and
+            # its Ordinal_Loss (loss.py:17-59); autograd runs their backward kernels on this stream as well
             y, pyr, comps, ord_t = self.targets()
-        x_d1, ord_ = R.dorn_regression(self.logits)                            # RN:313-345
+            x_d1, ord_ = R.dorn_regression(self.logits)
+            ord_loss = R.ordinal_loss(ord_, ord_t)
         rel = self.plan.run_als()                                              # RN:358-396 for every relative decoder
+        cur.wait_stream(self._gt_stream)                                       # join: the tail needs decoder 1's map
         final, yhat = fuse_tail_autograd(x_d1, [rel[s] for s in self.scales], self.weights)   # RN:117-133 + MOD:132
-        cur.wait_stream(self._gt_stream)
-        # CP:499-510: per-scale MSE, summed through torch.as_tensor => detached (no host sync here)
-        with torch.no_grad():
+        # CP:499-510: per-scale MSE, summed through torch.as_tensor => detached: it only enters the VALUE of the loss, so it
+        # is taken on the second stream while this one goes on to the MSE and the backward pass (no host sync anywhere)
+        self._gt_stream.wait_stream(cur)
+        with torch.cuda.stream(self._gt_stream), torch.no_grad():
             if pyr is not None:
                 fine = R.component_loss(yhat, pyr, self.plan.kmax)
             else:
                 fine = torch.stack([torch.nn.functional.mse_loss(a.double(), b) for a, b in zip(split_yhat(yhat, self.plan.kmax), comps)]).sum()
-        ord_loss = R.ordinal_loss(ord_, ord_t)                                 # loss.py:17-59
         mse = torch.nn.functional.mse_loss(final, y)                           # MOD:89
-        loss = mse + fine + ord_loss                                           # MOD:90-92
-        loss.backward()
+        (mse + ord_loss).backward()                                            # MOD:90-95: `fine` carries no gradient
+        cur.wait_stream(self._gt_stream)
+        loss = mse.detach() + fine + ord_loss.detach()                         # MOD:90-92, in the reference's order
         return {"loss": loss.detach(), "mse": mse.detach(), "fine": fine, "ord": ord_loss.detach(), "final": final.detach()}
 
     # ------------------------------------------------------------------ CUDA graph of the whole step
