@@ -287,6 +287,14 @@ int rdm_fuse_tail(const int64_t* x_d1, const float* const* rel, const int32_t* s
                   int32_t n_rel, const float* weights, int64_t n_images, float* yhat_out,
                   double* depth_out, double* depth_compact_out, double* const* A_out,
                   rdm_stream_t stream);
+/* The same with the number of CTAs per image chosen by the caller: bands = 1, 2, 4 or 8 (a thread-block cluster per
+ * image; clamped to 2^kmax), 0 = as rdm_fuse_tail (one CTA per image from 16 images up: best with many calls in flight).
+ * A caller whose launch is alone on the GPU (a training step) gets a shorter launch from 4 bands (batch 16: 11 vs 18 us).
+ * Results are bit-identical for every band count. */
+int rdm_fuse_tail_bands(const int64_t* x_d1, const float* const* rel, const int32_t* sides,
+                  int32_t n_rel, const float* weights, int64_t n_images, float* yhat_out,
+                  double* depth_out, double* depth_compact_out, double* const* A_out,
+                  int32_t bands, rdm_stream_t stream);
 /* number of f32 weights rdm_fuse_tail expects for these relative decoder sides (-1 = bad sides) */
 int64_t rdm_fuse_tail_weight_count(const int32_t* sides, int32_t n_rel);
 

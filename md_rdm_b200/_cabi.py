@@ -69,6 +69,8 @@ PROTOTYPES = {
     "rdm_recombination_bwd": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_int32), c_int32, c_int32, c_int64, c_int32, c_void_p]),
     "rdm_fuse_tail": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_int32), c_int32, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
                               POINTER(c_void_p), c_void_p]),
+    "rdm_fuse_tail_bands": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_int32), c_int32, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
+                                    POINTER(c_void_p), c_int32, c_void_p]),
     "rdm_fuse_tail_weight_count": (c_int64, [POINTER(c_int32), c_int32]),
     "rdm_fuse_tail_bwd": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_int32), c_int32, c_int64, c_void_p, c_void_p, c_void_p]),
     "rdm_component_loss": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p]),

@@ -1284,10 +1284,12 @@ extern "C" int64_t rdm_fuse_tail_weight_count(const int32_t* sides, int32_t n_re
   return total;
 }
 
-extern "C" int rdm_fuse_tail(const int64_t* x_d1, const float* const* rel, const int32_t* sides, int32_t n_rel,
-                             const float* weights, int64_t n_images, float* yhat_out, double* depth_out,
-                             double* depth_compact_out, double* const* A_out, rdm_stream_t stream) {
+static int fuse_tail_impl(const int64_t* x_d1, const float* const* rel, const int32_t* sides, int32_t n_rel, const float* weights,
+                          int64_t n_images, float* yhat_out, double* depth_out, double* depth_compact_out, double* const* A_out,
+                          int32_t bands_req, rdm_stream_t stream) {
   RDM_REQUIRE(x_d1 && weights && (depth_out || depth_compact_out), "rdm_fuse_tail: null pointer");
+  RDM_REQUIRE(bands_req == 0 || bands_req == 1 || bands_req == 2 || bands_req == 4 || bands_req == 8,
+              "rdm_fuse_tail_bands: bands must be 0 (chosen from the batch), 1, 2, 4 or 8 (got %d)", bands_req);
   RDM_REQUIRE(n_rel >= 0 && n_rel <= kMaxRel, "rdm_fuse_tail: n_rel must be 0..%d (got %d)", kMaxRel, n_rel);
   RDM_REQUIRE(n_rel == 0 || (rel && sides), "rdm_fuse_tail: rel/sides required");
   RDM_REQUIRE(!depth_out || aligned16(depth_out), "rdm_fuse_tail: depth_out must be 16-byte aligned");
@@ -1344,6 +1346,7 @@ extern "C" int rdm_fuse_tail(const int64_t* x_d1, const float* const* rel, const
   // (measured with a temporary override of this count: 1.53 -> 1.72 M maps/s; the lone launch 11 -> 18 us).  So: >= 16 CTAs in total, no more.
   int bands = 1;   // a band must hold whole constant blocks: rows per band >= 2^(7-kmax)
   while (bands < 8 && bands < (1 << P.kmax) && n_images * bands < 16) bands <<= 1;   // one thread-block cluster per image
+  if (bands_req) bands = bands_req < (1 << P.kmax) ? bands_req : (1 << P.kmax);          // the caller knows it is alone on the GPU
   P.bands = bands;
   RDM_REQUIRE(n_images * bands < (1ll << 31), "rdm_fuse_tail: too many images");
   const size_t smem = (size_t)P.dtotal * sizeof(double) + ((size_t)off_level(P.kmax + 1) + (size_t)ltotal) * sizeof(float);
@@ -1371,6 +1374,18 @@ extern "C" int rdm_fuse_tail(const int64_t* x_d1, const float* const* rel, const
     return (int)e;
   }
   return launch_status("fuse_tail_kernel");
+}
+
+extern "C" int rdm_fuse_tail(const int64_t* x_d1, const float* const* rel, const int32_t* sides, int32_t n_rel,
+                             const float* weights, int64_t n_images, float* yhat_out, double* depth_out,
+                             double* depth_compact_out, double* const* A_out, rdm_stream_t stream) {
+  return fuse_tail_impl(x_d1, rel, sides, n_rel, weights, n_images, yhat_out, depth_out, depth_compact_out, A_out, 0, stream);
+}
+
+extern "C" int rdm_fuse_tail_bands(const int64_t* x_d1, const float* const* rel, const int32_t* sides, int32_t n_rel,
+                                   const float* weights, int64_t n_images, float* yhat_out, double* depth_out,
+                                   double* depth_compact_out, double* const* A_out, int32_t bands, rdm_stream_t stream) {
+  return fuse_tail_impl(x_d1, rel, sides, n_rel, weights, n_images, yhat_out, depth_out, depth_compact_out, A_out, bands, stream);
 }
 
 static size_t smem_set_gt_prepare_float_[64];

@@ -640,10 +640,12 @@ def tail_layout(sides: Sequence[int]):
 
 
 @torch.library.custom_op("rdm::fuse_tail", mutates_args=())
-def fuse_tail(x_d1: Tensor, rel: Sequence[Tensor], weights: Tensor, want_A: bool) -> Tuple[Tensor, Tensor, List[Tensor]]:
+def fuse_tail(x_d1: Tensor, rel: Sequence[Tensor], weights: Tensor, want_A: bool, bands: int = 0) -> Tuple[Tensor, Tensor, List[Tensor]]:
     """RN:117-133 + network/module.py:132 in one launch.  x_d1 (B,1,8,8) int64; rel: filled
     relative maps (B,1,s,s) f32 (s <= 64); weights: flat f32, slots concatenated [d0|f1|...].
-    Returns (depth (B,1,128,128) f64, yhat packed (B, sum 4^k) f32, [A_k (B,K_k,4^k) f64] if want_A)."""
+    Returns (depth (B,1,128,128) f64, yhat packed (B, sum 4^k) f32, [A_k (B,K_k,4^k) f64] if want_A).
+    bands: CTAs per image (1/2/4/8; 0 = chosen from the batch, best with many calls in flight; a call that is alone on the
+    GPU is shorter with 4); the results do not depend on it."""
     _need_cuda("fuse_tail", x_d1, weights, *rel)
     if x_d1.dtype != torch.int64 or x_d1.numel() % 64:
         raise RuntimeError("rdm::fuse_tail: x_d1 must be int64 (B,1,8,8)")
@@ -661,13 +663,14 @@ def fuse_tail(x_d1: Tensor, rel: Sequence[Tensor], weights: Tensor, want_A: bool
     A = [torch.empty((B, K[k], 4 ** k), dtype=torch.float64, device=dev) for k in range(kmax + 1)] if want_A else []
     a_ptrs = ptr_array([A[k].data_ptr() if (want_A and k <= kmax) else None for k in range(8)])
     with torch.cuda.device(dev):
-        check(load().rdm_fuse_tail(_p(x_d1.contiguous()), ptr_array([r.data_ptr() for r in rc]), i32_array(sides), len(rc),
-                                   _p(weights.contiguous()), B, _p(yhat), _p(depth), c_void_p(0), a_ptrs, _stream()), "rdm_fuse_tail")
+        check(load().rdm_fuse_tail_bands(_p(x_d1.contiguous()), ptr_array([r.data_ptr() for r in rc]), i32_array(sides), len(rc),
+                                         _p(weights.contiguous()), B, _p(yhat), _p(depth), c_void_p(0), a_ptrs, int(bands), _stream()),
+              "rdm_fuse_tail_bands")
     return depth, yhat, A
 
 
 @fuse_tail.register_fake
-def _(x_d1, rel, weights, want_A):
+def _(x_d1, rel, weights, want_A, bands=0):
     B = x_d1.numel() // 64
     sides = [int(r.shape[2]) for r in rel]
     K, _, kmax, _ = tail_layout(sides)
@@ -733,16 +736,17 @@ def split_yhat(yhat: Tensor, kmax: int) -> List[Tensor]:
     return out
 
 
-def fuse_tail_autograd(x_d1: Tensor, rel: Sequence[Tensor], weights: Tensor):
+def fuse_tail_autograd(x_d1: Tensor, rel: Sequence[Tensor], weights: Tensor, bands: int = 0):
     """fuse_tail with gradients to `weights` (and to y_hat consumers): the forward is the single
-    fused launch; the backward chains recombination_bwd and make_pred_bwd on the saved A."""
-    return _FuseTailFn.apply(x_d1, weights, *rel)
+    fused launch; the backward is rdm_fuse_tail_bwd on the saved A (or, when y_hat carries a gradient,
+    recombination_bwd and make_pred_bwd slot by slot).  bands: see fuse_tail."""
+    return _FuseTailFn.apply(x_d1, weights, int(bands), *rel)
 
 
 class _FuseTailFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x_d1, weights, *rel):
-        depth, yhat, A = torch.ops.rdm.fuse_tail(x_d1, list(rel), weights, True)
+    def forward(ctx, x_d1, weights, bands, *rel):
+        depth, yhat, A = torch.ops.rdm.fuse_tail(x_d1, list(rel), weights, True, bands)
         ctx.set_materialize_grads(False)   # y_hat feeds only the detached component loss: its gradient stays None
         sides = [int(r.shape[2]) for r in rel]
         K, off, kmax, _ = tail_layout(sides)
@@ -758,7 +762,7 @@ class _FuseTailFn(torch.autograd.Function):
         B = A[0].shape[0]
         sides = [2 ** k for k in range(kmax + 1)]
         if g_depth is not None and g_yhat is None:   # the training step: two launches
-            return (None, torch.ops.rdm.fuse_tail_bwd(g_depth, list(A)).to(weights.dtype)) + tuple(None for _ in range(ctx.n_rel))
+            return (None, torch.ops.rdm.fuse_tail_bwd(g_depth, list(A)).to(weights.dtype), None) + tuple(None for _ in range(ctx.n_rel))
         if g_depth is not None:
             gs = torch.ops.rdm.recombination_bwd(g_depth, sides, False, 7)
         else:
@@ -770,7 +774,7 @@ class _FuseTailFn(torch.autograd.Function):
             _, gwk = torch.ops.rdm.make_pred_bwd(A[k], weights[off[k]:off[k] + K[k]], gs[k].reshape(B, -1))
             gw[off[k]:off[k] + K[k]] = gwk
         # relative maps / x_d1: zero gradients (numerically severed by Lloyd / integer input)
-        return (None, gw) + tuple(None for _ in range(ctx.n_rel))
+        return (None, gw, None) + tuple(None for _ in range(ctx.n_rel))
 
 
 # ---------------------------------------------------------------------------- zero-gradient ops

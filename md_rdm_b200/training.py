@@ -94,7 +94,8 @@ class TrainingStep:
             ord_loss = R.ordinal_loss(ord_, ord_t)
         rel = self.plan.run_als()                                              # RN:358-396 for every relative decoder
         cur.wait_stream(self._gt_stream)                                       # join: the tail needs decoder 1's map
-        final, yhat = fuse_tail_autograd(x_d1, [rel[s] for s in self.scales], self.weights)   # RN:117-133 + MOD:132
+        # (a training step is alone on the GPU: four CTAs per image make the tail launch shorter)
+        final, yhat = fuse_tail_autograd(x_d1, [rel[s] for s in self.scales], self.weights, bands=4)   # RN:117-133 + MOD:132
         # CP:499-510: per-scale MSE, summed through torch.as_tensor => detached: it only enters the VALUE of the loss, so it
         # is taken on the second stream while this one goes on to the MSE and the backward pass (no host sync anywhere)
         self._gt_stream.wait_stream(cur)

@@ -1145,6 +1145,10 @@ def test_stress_tail_bands_and_gm_cluster(dev, books):
             ref_depth = d0
         else:
             assert _eq_nan(d0, ref_depth[:n]), n
+        if n == 16:   # the caller's choice of bands (rdm_fuse_tail_bands): same bits
+            for bands in (1, 2, 4, 8):
+                db, yb, _ = R.fuse_tail(xd[:n], [f[:n] for f in filled], w, False, bands)
+                assert _eq_nan(db, d0) and _eq_nan(yb, y0), bands
     y = (0.5 + 9.5 * torch.rand(256, 1, 128, 128, generator=g, dtype=torch.float64)).to(dev)
     n0 = R.gm_normalize(y)
     p0 = R.decompose(n0, False)
