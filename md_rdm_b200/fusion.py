@@ -180,8 +180,9 @@ class FusionPlan:
         (the join costs more than the idle SMs it fills), so it is off unless the plan was built with
         `overlap=True` (latency-bound callers)."""
         with self._guard():
-            self._run_als(self.overlap if overlap is None else overlap)
-            self._run_tail()
+            ov = self.overlap if overlap is None else overlap
+            self._run_als(ov)
+            self._run_tail(ov)
         return self.depth
 
     def _guard(self):
@@ -277,15 +278,19 @@ class FusionPlan:
         self.yhat.copy_(torch.cat([y.reshape(B, -1) for y in y_hat], 1))
         self.depth.copy_(cp.recombination(list(y_hat)))
 
-    def _run_tail(self) -> None:
+    def _run_tail(self, latency_bound: Optional[bool] = None) -> None:
+        if latency_bound is None:
+            latency_bound = self.overlap
         if self.composed_tail:
             return self._run_tail_composed()
         st = c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-        check(self.lib.rdm_fuse_tail(c_void_p(self.x_d1.data_ptr()), self._rel_ptrs, self._sides, len(self.scales),
-                                     c_void_p(self.weights.data_ptr()), self.N, c_void_p(self.yhat.data_ptr()),
-                                     c_void_p(self.depth.data_ptr()),
-                                     c_void_p(self.depth_compact.data_ptr()) if self.depth_compact is not None else c_void_p(0),
-                                     self._a_ptrs, st), "rdm_fuse_tail")
+        # a latency-bound caller (overlap=True) also takes four CTAs per image in the tail; otherwise the
+        # launch picks the count from the batch (one per image from 16 images up: best with many calls in flight)
+        check(self.lib.rdm_fuse_tail_bands(c_void_p(self.x_d1.data_ptr()), self._rel_ptrs, self._sides, len(self.scales),
+                                           c_void_p(self.weights.data_ptr()), self.N, c_void_p(self.yhat.data_ptr()),
+                                           c_void_p(self.depth.data_ptr()),
+                                           c_void_p(self.depth_compact.data_ptr()) if self.depth_compact is not None else c_void_p(0),
+                                           self._a_ptrs, 4 if latency_bound else 0, st), "rdm_fuse_tail_bands")
 
     def expand_compact(self, compact: torch.Tensor) -> torch.Tensor:
         """(N,1,2^kmax,2^kmax) compact result -> the (N,1,128,128) map it stands for (nearest-neighbour, exact)."""
